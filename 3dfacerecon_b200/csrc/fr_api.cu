@@ -1,0 +1,379 @@
+// C ABI of facerecon_b200 (include/facerecon_b200.h): argument validation, workspace carving and kernel
+// launches.  No CPU fallback anywhere: every compute entry point launches sm_100a kernels or fails.
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "fr_common.cuh"
+#include "raster.cuh"
+#include "recon.cuh"
+#include "recon_tc.cuh"
+
+using namespace fr;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+
+struct ReconWorkspace {
+  float* coefT;   // [kpad][bpad]
+  float* pose;    // [bpad][24]
+  float* G;       // [bpad][kpad]
+  float* dt;      // [bpad][4]
+  void* tc;       // tensor-core path scratch (split coefficients)
+  size_t bytes;
+};
+
+ReconWorkspace carve_recon(void* base, int batch, const BasisGeom& g) {
+  const int bpad = batch_padded(batch);
+  ReconWorkspace w;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align_up(n, kAlign);
+    return p;
+  };
+  w.coefT = static_cast<float*>(take(sizeof(float) * (size_t)g.kpad * bpad));
+  w.pose = static_cast<float*>(take(sizeof(float) * (size_t)bpad * kPoseStride));
+  w.G = static_cast<float*>(take(sizeof(float) * (size_t)bpad * g.kpad));
+  w.dt = static_cast<float*>(take(sizeof(float) * (size_t)bpad * 4));
+  w.tc = take(recon_tc_workspace_bytes(batch, g));
+  w.bytes = off;
+  return w;
+}
+
+int check_model_dims(int batch, int nver, int ks, int ke) {
+  FR_REQUIRE(batch >= 0, "batch must be >= 0 (got %d)", batch);
+  FR_REQUIRE(nver > 0, "nver must be > 0 (got %d)", nver);
+  FR_REQUIRE(ks >= 0 && ke >= 0 && ks + ke > 0, "ndim_shape/ndim_exp must be >= 0 and not both 0 (got %d, %d)", ks, ke);
+  return FR_OK;
+}
+
+int check_workspace(void* ws, size_t have, size_t need) {
+  if (need == 0) return FR_OK;
+  if (ws == nullptr) return fail(FR_ERR_WORKSPACE, "workspace is null (%zu bytes required)", need);
+  if (reinterpret_cast<uintptr_t>(ws) % kAlign != 0) return fail(FR_ERR_WORKSPACE, "workspace must be %zu-byte aligned", kAlign);
+  if (have < need) return fail(FR_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", have, need);
+  return FR_OK;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+template <int FB>
+int launch_recon_fwd_simt(const float* packed, const ReconWorkspace& w, float* vertex_proj, int batch, int nver,
+                          const BasisGeom& g, float im_size, unsigned flags, int gy, cudaStream_t st) {
+  const int fbt = FB * gy;
+  const size_t smem = sizeof(float) * (size_t)g.kpad * fbt;
+  FR_CUDA(cudaFuncSetAttribute(recon_fwd_simt_kernel<FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(g.ntiles, ceil_div(batch, fbt)), block(kTileVerts, gy);
+  recon_fwd_simt_kernel<FB><<<grid, block, smem, st>>>(reinterpret_cast<const float4*>(packed), w.coefT, w.pose,
+                                                       vertex_proj, batch, batch_padded(batch), nver, g.kg, im_size, flags);
+  FR_LAUNCHED("recon_fwd_simt_kernel");
+  return FR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fr_last_error(void) { return error_buffer(); }
+int fr_version(void) { return FR_VERSION; }
+unsigned long long fr_launch_count(void) { return launch_counter().load(); }
+
+// ------------------------------------------------------------------------------------------------ packing
+size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp) {
+  if (nver <= 0 || ndim_shape < 0 || ndim_exp < 0) return 0;
+  return basis_geom(nver, ndim_shape, ndim_exp).bytes();
+}
+
+int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, int nver, int ndim_shape, int ndim_exp,
+                  unsigned layout_flags, float* packed, void* stream) {
+  if (int rc = check_model_dims(0, nver, ndim_shape, ndim_exp)) return rc;
+  FR_REQUIRE(mu && packed && (pc_shape || ndim_shape == 0) && (pc_exp || ndim_exp == 0), "null model pointer");
+  FR_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 16 == 0, "packed basis must be 16-byte aligned");
+  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp);
+  const size_t total = (size_t)g.ntiles * 3 * g.kg * kTileVerts;
+  pack_basis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mu, pc_shape, pc_exp, nver, ndim_shape, ndim_exp, g.kg, g.ntiles, layout_flags, reinterpret_cast<float4*>(packed));
+  FR_LAUNCHED("pack_basis_kernel");
+  return FR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ recon
+size_t fr_recon_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp) {
+  if (batch <= 0 || nver <= 0 || ndim_shape < 0 || ndim_exp < 0) return 0;
+  return carve_recon(nullptr, batch, basis_geom(nver, ndim_shape, ndim_exp)).bytes;
+}
+
+int fr_recon_project_forward(const float* params, const float* packed, float* vertex_proj, int batch, int nver,
+                             int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
+  if (batch == 0) return FR_OK;
+  FR_REQUIRE(params && packed && vertex_proj, "null pointer argument");
+  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp);
+  const ReconWorkspace w = carve_recon(workspace, batch, g);
+  if (int rc = check_workspace(workspace, workspace_bytes, w.bytes)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int bpad = batch_padded(batch);
+  const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
+
+  recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
+                                                                 g.kpad, flags, w.coefT, w.pose);
+  FR_LAUNCHED("recon_prep_kernel");
+
+  if (recon_tc_applicable(batch, g, flags))
+    return launch_recon_fwd_tc(packed, w.coefT, w.pose, w.tc, vertex_proj, batch, nver, g, im_size, flags, sm_count(), st);
+  if (batch <= 4) return launch_recon_fwd_simt<4>(packed, w, vertex_proj, batch, nver, g, im_size, flags, 1, st);
+  if (batch <= 8) return launch_recon_fwd_simt<8>(packed, w, vertex_proj, batch, nver, g, im_size, flags, 1, st);
+  const int gy = batch <= 16 ? 1 : (batch <= 32 ? 2 : 4);
+  return launch_recon_fwd_simt<16>(packed, w, vertex_proj, batch, nver, g, im_size, flags, gy, st);
+}
+
+int fr_recon_project_backward(const float* params, const float* packed, const float* vertex_grad, float* params_grad,
+                              int batch, int nver, int ndim_shape, int ndim_exp, unsigned flags, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
+  if (batch == 0) return FR_OK;
+  FR_REQUIRE(params && packed && vertex_grad && params_grad, "null pointer argument");
+  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp);
+  const ReconWorkspace w = carve_recon(workspace, batch, g);
+  if (int rc = check_workspace(workspace, workspace_bytes, w.bytes)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int bpad = batch_padded(batch);
+  const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
+
+  // recomputed rather than trusted from a previous forward: the workspace is the caller's scratch
+  recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
+                                                                 g.kpad, flags, w.coefT, w.pose);
+  FR_LAUNCHED("recon_prep_kernel");
+  FR_CUDA(cudaMemsetAsync(w.G, 0, sizeof(float) * (size_t)bpad * g.kpad, st));
+  recon_bwd_dt_kernel<<<dim3(batch, 3), 256, 0, st>>>(vertex_grad, nver, flags, w.dt);
+  FR_LAUNCHED("recon_bwd_dt_kernel");
+
+  const int gy = batch <= 16 ? 1 : (batch <= 32 ? 2 : 4);
+  const int fbt = kBwdFB * gy;
+  const size_t smem = sizeof(float) * ((size_t)3 * kBwdKG * kBwdRow * 4 + (size_t)3 * kBwdVC * (fbt + 4));
+  FR_CUDA(cudaFuncSetAttribute(recon_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ygroups = ceil_div(batch, fbt), zgroups = ceil_div(g.kg, kBwdKG);
+  int ctas = (3 * sm_count()) / (ygroups * zgroups);
+  if (ctas < 1) ctas = 1;
+  if (ctas > g.ntiles) ctas = g.ntiles;
+  recon_bwd_simt_kernel<<<dim3(ctas, ygroups, zgroups), dim3(kBwdKG, gy), smem, st>>>(
+      reinterpret_cast<const float4*>(packed), w.pose, vertex_grad, w.G, batch, nver, g.kg, g.ntiles, flags);
+  FR_LAUNCHED("recon_bwd_simt_kernel");
+  recon_bwd_finalize_kernel<<<batch, 256, 0, st>>>(w.G, w.coefT, w.pose, w.dt, bpad, ndim_shape, ndim_exp, g.kpad, dparam,
+                                                  params_grad);
+  FR_LAUNCHED("recon_bwd_finalize_kernel");
+  return FR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ render
+size_t fr_render_workspace_bytes(int batch, int height, int width) {
+  if (batch <= 0 || height <= 0 || width <= 0) return 0;
+  return align_up(sizeof(unsigned long long) * (size_t)batch * height * width, kAlign);
+}
+
+int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
+                            float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
+                            int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream) {
+  FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
+             "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
+  // render_depth_op.cc:161-166: the reference refuses ntri >= 10M (its static scratch); nver < 2^24 keeps float indices exact
+  FR_REQUIRE(ntri < 10 * 1000 * 1000, "Too many triangular %d >= %d", ntri, 10 * 1000 * 1000);
+  FR_REQUIRE(nver <= (1 << 24), "nver %d exceeds the exact range of float triangle indices", nver);
+  FR_REQUIRE((long long)height * width < (1ll << 31), "image too large");
+  if (batch == 0) return FR_OK;
+  FR_REQUIRE(vertex && tri && depth && tri_ind, "null pointer argument");
+  FR_REQUIRE(texture_image == nullptr || texture != nullptr, "texture_image requested without a texture");
+  FR_REQUIRE(texture_batch_stride == 0 || texture_batch_stride >= 3ll * nver, "texture_batch_stride must be 0 or >= 3*nver");
+  const size_t need = fr_render_workspace_bytes(batch, height, width);
+  if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* keys = static_cast<unsigned long long*>(workspace);
+  const int npix = height * width;
+
+  FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
+  if (ntri > 0) {
+    const unsigned gx = (unsigned)ceil_div(ntri, kRasterThreads);
+    if (batch >= 4)
+      raster_keys_kernel<4><<<dim3(gx, ceil_div(batch, 4)), kRasterThreads, 0, st>>>(vertex, tri, keys, batch, nver, ntri, height, width);
+    else if (batch >= 2)
+      raster_keys_kernel<2><<<dim3(gx, ceil_div(batch, 2)), kRasterThreads, 0, st>>>(vertex, tri, keys, batch, nver, ntri, height, width);
+    else
+      raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(vertex, tri, keys, batch, nver, ntri, height, width);
+    FR_LAUNCHED("raster_keys_kernel");
+  }
+  raster_resolve_kernel<<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(
+      keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
+  FR_LAUNCHED("raster_resolve_kernel");
+  return FR_OK;
+}
+
+int fr_render_depth_backward(const float* depth_grad, const float* tri, const float* tri_ind, float* vertex_grad,
+                             int batch, int nver, int ntri, int height, int width, void* stream) {
+  FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
+             "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
+  FR_REQUIRE((long long)height * width < (1ll << 31), "image too large");
+  if (batch == 0) return FR_OK;
+  FR_REQUIRE(depth_grad && tri && tri_ind && vertex_grad, "null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int npix = height * width;
+  FR_CUDA(cudaMemsetAsync(vertex_grad, 0, sizeof(float) * (size_t)batch * 3 * nver, st));
+  render_backward_kernel<<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(depth_grad, tri, tri_ind,
+                                                                                              vertex_grad, nver, ntri, npix);
+  FR_LAUNCHED("render_backward_kernel");
+  return FR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused
+size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width) {
+  return fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp) + fr_render_workspace_bytes(batch, height, width);
+}
+
+int fr_recon_render_forward(const float* params, const float* packed, const float* tri, float* vertex_proj, float* depth,
+                            float* tri_ind, int batch, int nver, int ntri, int ndim_shape, int ndim_exp, int height,
+                            int width, float im_size, unsigned flags, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  const size_t rb = fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp);
+  const size_t need = rb + fr_render_workspace_bytes(batch, height, width);
+  if (batch > 0) {
+    if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
+  }
+  if (int rc = fr_recon_project_forward(params, packed, vertex_proj, batch, nver, ndim_shape, ndim_exp, im_size, flags,
+                                        workspace, rb, stream))
+    return rc;
+  return fr_render_depth_forward(vertex_proj, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height,
+                                 width, workspace ? static_cast<char*>(workspace) + rb : nullptr, workspace_bytes - rb, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ session
+struct fr_session {
+  int device, nver, ntri, ks, ke, height, width, max_batch, last_batch;
+  unsigned flags;
+  float last_im_size;
+  cudaStream_t stream;
+  float *packed, *tri, *params, *vertex, *depth, *tri_ind, *depth_grad, *vgrad, *pgrad;
+  void* ws;
+  size_t ws_bytes;
+};
+
+static void session_free(fr_session* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  float* bufs[] = {s->packed, s->tri, s->params, s->vertex, s->depth, s->tri_ind, s->depth_grad, s->vgrad, s->pgrad};
+  for (float* p : bufs)
+    if (p) cudaFree(p);
+  if (s->ws) cudaFree(s->ws);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int fr_session_create(const float* mu, const float* pc_shape, const float* pc_exp, const float* tri, int nver, int ntri,
+                      int ndim_shape, int ndim_exp, int height, int width, int max_batch, unsigned flags, int device,
+                      fr_session** out) {
+  FR_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  if (int rc = check_model_dims(max_batch, nver, ndim_shape, ndim_exp)) return rc;
+  FR_REQUIRE(mu && tri && ntri > 0 && height > 0 && width > 0 && max_batch > 0, "bad session arguments");
+  FR_CUDA(cudaSetDevice(device));
+  fr_session* s = new (std::nothrow) fr_session();
+  if (!s) return fail(FR_ERR_CUDA, "out of host memory");
+  std::memset(s, 0, sizeof(*s));
+  s->device = device; s->nver = nver; s->ntri = ntri; s->ks = ndim_shape; s->ke = ndim_exp;
+  s->height = height; s->width = width; s->max_batch = max_batch; s->flags = flags;
+  const size_t n3 = (size_t)3 * nver, npix = (size_t)height * width;
+  const int d = FR_NDIM_POSE + ndim_shape + ndim_exp;
+  float *d_mu = nullptr, *d_ps = nullptr, *d_pe = nullptr;
+  int rc = FR_OK;
+  auto chk = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == FR_OK) rc = fail(FR_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  s->ws_bytes = fr_pipeline_workspace_bytes(max_batch, nver, ndim_shape, ndim_exp, height, width);
+  chk(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  chk(cudaMalloc(&s->packed, fr_packed_basis_bytes(nver, ndim_shape, ndim_exp)), "cudaMalloc(packed)");
+  chk(cudaMalloc(&s->tri, sizeof(float) * 3 * (size_t)ntri), "cudaMalloc(tri)");
+  chk(cudaMalloc(&s->params, sizeof(float) * (size_t)max_batch * d), "cudaMalloc(params)");
+  chk(cudaMalloc(&s->vertex, sizeof(float) * (size_t)max_batch * n3), "cudaMalloc(vertex)");
+  chk(cudaMalloc(&s->depth, sizeof(float) * (size_t)max_batch * npix), "cudaMalloc(depth)");
+  chk(cudaMalloc(&s->tri_ind, sizeof(float) * (size_t)max_batch * npix), "cudaMalloc(tri_ind)");
+  chk(cudaMalloc(&s->depth_grad, sizeof(float) * (size_t)max_batch * npix), "cudaMalloc(depth_grad)");
+  chk(cudaMalloc(&s->vgrad, sizeof(float) * (size_t)max_batch * n3), "cudaMalloc(vertex_grad)");
+  chk(cudaMalloc(&s->pgrad, sizeof(float) * (size_t)max_batch * d), "cudaMalloc(params_grad)");
+  chk(cudaMalloc(&s->ws, s->ws_bytes), "cudaMalloc(workspace)");
+  chk(cudaMalloc(&d_mu, sizeof(float) * n3), "cudaMalloc(mu)");
+  if (ndim_shape) chk(cudaMalloc(&d_ps, sizeof(float) * n3 * ndim_shape), "cudaMalloc(pc_shape)");
+  if (ndim_exp) chk(cudaMalloc(&d_pe, sizeof(float) * n3 * ndim_exp), "cudaMalloc(pc_exp)");
+  if (rc == FR_OK) {
+    chk(cudaMemcpyAsync(d_mu, mu, sizeof(float) * n3, cudaMemcpyHostToDevice, s->stream), "copy mu");
+    if (ndim_shape) chk(cudaMemcpyAsync(d_ps, pc_shape, sizeof(float) * n3 * ndim_shape, cudaMemcpyHostToDevice, s->stream), "copy pc_shape");
+    if (ndim_exp) chk(cudaMemcpyAsync(d_pe, pc_exp, sizeof(float) * n3 * ndim_exp, cudaMemcpyHostToDevice, s->stream), "copy pc_exp");
+    chk(cudaMemcpyAsync(s->tri, tri, sizeof(float) * 3 * (size_t)ntri, cudaMemcpyHostToDevice, s->stream), "copy tri");
+  }
+  if (rc == FR_OK) rc = fr_pack_basis(d_mu, d_ps, d_pe, nver, ndim_shape, ndim_exp, flags, s->packed, s->stream);
+  if (rc == FR_OK) chk(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize");
+  if (d_mu) cudaFree(d_mu);
+  if (d_ps) cudaFree(d_ps);
+  if (d_pe) cudaFree(d_pe);
+  if (rc != FR_OK) {
+    session_free(s);
+    return rc;
+  }
+  *out = s;
+  return FR_OK;
+}
+
+void fr_session_destroy(fr_session* s) { session_free(s); }
+
+int fr_session_forward(fr_session* s, const float* params, int batch, float im_size, float* depth, float* tri_ind,
+                       float* vertex_proj) {
+  FR_REQUIRE(s && params && depth, "null pointer argument");
+  FR_REQUIRE(batch > 0 && batch <= s->max_batch, "batch %d outside (0, %d]", batch, s->max_batch);
+  FR_CUDA(cudaSetDevice(s->device));
+  const int d = FR_NDIM_POSE + s->ks + s->ke;
+  const size_t npix = (size_t)s->height * s->width;
+  FR_CUDA(cudaMemcpyAsync(s->params, params, sizeof(float) * (size_t)batch * d, cudaMemcpyHostToDevice, s->stream));
+  if (int rc = fr_recon_render_forward(s->params, s->packed, s->tri, s->vertex, s->depth, s->tri_ind, batch, s->nver, s->ntri,
+                                       s->ks, s->ke, s->height, s->width, im_size, s->flags, s->ws, s->ws_bytes, s->stream))
+    return rc;
+  FR_CUDA(cudaMemcpyAsync(depth, s->depth, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, s->stream));
+  if (tri_ind) FR_CUDA(cudaMemcpyAsync(tri_ind, s->tri_ind, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, s->stream));
+  if (vertex_proj)
+    FR_CUDA(cudaMemcpyAsync(vertex_proj, s->vertex, sizeof(float) * (size_t)batch * 3 * s->nver, cudaMemcpyDeviceToHost, s->stream));
+  FR_CUDA(cudaStreamSynchronize(s->stream));
+  s->last_batch = batch;
+  s->last_im_size = im_size;
+  return FR_OK;
+}
+
+int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float* params_grad) {
+  FR_REQUIRE(s && depth_grad && params_grad, "null pointer argument");
+  FR_REQUIRE(batch > 0 && batch == s->last_batch, "batch %d does not match the last forward (%d)", batch, s->last_batch);
+  FR_CUDA(cudaSetDevice(s->device));
+  const int d = FR_NDIM_POSE + s->ks + s->ke;
+  const size_t npix = (size_t)s->height * s->width;
+  FR_CUDA(cudaMemcpyAsync(s->depth_grad, depth_grad, sizeof(float) * batch * npix, cudaMemcpyHostToDevice, s->stream));
+  if (int rc = fr_render_depth_backward(s->depth_grad, s->tri, s->tri_ind, s->vgrad, batch, s->nver, s->ntri, s->height,
+                                        s->width, s->stream))
+    return rc;
+  if (int rc = fr_recon_project_backward(s->params, s->packed, s->vgrad, s->pgrad, batch, s->nver, s->ks, s->ke, s->flags,
+                                         s->ws, s->ws_bytes, s->stream))
+    return rc;
+  FR_CUDA(cudaMemcpyAsync(params_grad, s->pgrad, sizeof(float) * (size_t)batch * d, cudaMemcpyDeviceToHost, s->stream));
+  FR_CUDA(cudaStreamSynchronize(s->stream));
+  return FR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Shared host-side plumbing for the C ABI (error reporting, launch accounting) and small device helpers.
+#ifndef FR_COMMON_CUH_
+#define FR_COMMON_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/facerecon_b200.h"
+
+namespace fr {
+
+// ---- errors: status code + thread-local message (replaces the reference's printf-and-return,
+// render_depth_op.cc:161-172 / render_depth_op.cu.cc:290-295)
+inline char* error_buffer() {
+  static thread_local char buf[512] = "";
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+inline std::atomic<unsigned long long>& launch_counter() {
+  static std::atomic<unsigned long long> n(0);
+  return n;
+}
+
+#define FR_REQUIRE(cond, ...) \
+  do {                        \
+    if (!(cond)) return ::fr::fail(FR_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+#define FR_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::fr::fail(FR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+#define FR_LAUNCHED(name)                                                                          \
+  do {                                                                                             \
+    ::fr::launch_counter().fetch_add(1, std::memory_order_relaxed);                                \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) return ::fr::fail(FR_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- packed-basis geometry (see DESIGN.md "Packed basis")
+constexpr int kTileVerts = 128;  // vertices per tile == TMEM lanes == threads of one SIMT row block
+
+struct BasisGeom {
+  int nver, ks, ke;
+  int kreal;   // ks + ke + 1 (the extra column is the mean, coefficient 1)
+  int kpad;    // kreal rounded up to 8 (one tf32 MMA K step)
+  int kg;      // kpad / 4 float4 groups
+  int ntiles;  // ceil(nver / 128)
+  size_t tile_floats() const { return (size_t)3 * kg * kTileVerts * 4; }
+  size_t bytes() const { return (size_t)ntiles * tile_floats() * sizeof(float); }
+};
+inline BasisGeom basis_geom(int nver, int ks, int ke) {
+  BasisGeom g;
+  g.nver = nver;
+  g.ks = ks;
+  g.ke = ke;
+  g.kreal = ks + ke + 1;
+  g.kpad = (g.kreal + 7) / 8 * 8;
+  g.kg = g.kpad / 4;
+  g.ntiles = (nver + kTileVerts - 1) / kTileVerts;
+  return g;
+}
+
+#ifdef __CUDACC__
+// 128-bit streaming load through the read-only path without polluting L1 (basis is read once per CTA).
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float f4_get(const float4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+#endif
+
+}  // namespace fr
+#endif  // FR_COMMON_CUH_

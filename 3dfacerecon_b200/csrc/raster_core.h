@@ -1,0 +1,154 @@
+// Per-triangle / per-pixel arithmetic of the z-buffer rasterizer, shared by the CUDA kernels
+// (raster.cuh) and by a host build that tests/test_raster_core_host.py drives on the CPU to
+// check this logic against the oracle without a GPU (test infrastructure; the product path is
+// the CUDA build only).
+//
+// Semantics: /root/reference/rendering_layer/ops_src/render_depth_op.cc:76-122 (PointInTri),
+// :201-246 (per-triangle setup), :263-316 (raster loop) -- see SURVEY.md App. A.3.
+// Bit-exactness contract: every double operation below is a separately rounded IEEE operation
+// in the reference's order (the reference is built without FMA contraction, ops.py:51), so on
+// the device they are spelled with __dmul_rn/__dadd_rn/... which the compiler may not fuse.
+#ifndef FR_RASTER_CORE_H_
+#define FR_RASTER_CORE_H_
+
+#include <limits.h>
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FR_HD __host__ __device__ __forceinline__
+#else
+#define FR_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define FR_DMUL(a, b) __dmul_rn((a), (b))
+#define FR_DADD(a, b) __dadd_rn((a), (b))
+#define FR_DSUB(a, b) __dsub_rn((a), (b))
+#define FR_DDIV(a, b) __ddiv_rn((a), (b))
+#define FR_FADD(a, b) __fadd_rn((a), (b))
+#define FR_FSUB(a, b) __fsub_rn((a), (b))
+#define FR_FDIV(a, b) __fdiv_rn((a), (b))
+#else  // host build: compiled with -ffp-contract=off
+#define FR_DMUL(a, b) ((a) * (b))
+#define FR_DADD(a, b) ((a) + (b))
+#define FR_DSUB(a, b) ((a) - (b))
+#define FR_DDIV(a, b) ((a) / (b))
+#define FR_FADD(a, b) ((a) + (b))
+#define FR_FSUB(a, b) ((a) - (b))
+#define FR_FDIV(a, b) ((a) / (b))
+#endif
+
+// render_depth_op.h:15-16: the reference's min/max are these macros; keep their NaN behaviour.
+#define FR_RMIN(a, b) ((a) < (b) ? (a) : (b))
+#define FR_RMAX(a, b) ((a) > (b) ? (a) : (b))
+
+// Bit pattern of (float)(-99999999999999), the reference's background depth (render_depth_op.cc:187).
+#define FR_BACKGROUND_DEPTH_BITS 0xD6B5E621u
+
+// (int)double as the reference binary does it (x86-64 cvttsd2si): NaN / out of range -> INT_MIN.
+FR_HD int fr_cvt_int_x86(double d) {
+  if (!(d > -2147483649.0 && d < 2147483648.0)) return INT_MIN;
+  return (int)d;
+}
+
+struct FrBBox {
+  int x_min, x_max, y_min, y_max;
+};
+
+// Integer bounding box (:276-280) and whole-triangle cull (:282).  Returns false when culled.
+FR_HD bool fr_tri_bbox(float x1, float y1, float x2, float y2, float x3, float y3, int width, int height, FrBBox* bb) {
+  const double ax = x1, ay = y1, bx = x2, by = y2, cx = x3, cy = y3;
+  const double lox = FR_RMIN(FR_RMIN(ax, bx), cx);
+  const double hix = FR_RMAX(FR_RMAX(ax, bx), cx);
+  const double loy = FR_RMIN(FR_RMIN(ay, by), cy);
+  const double hiy = FR_RMAX(FR_RMAX(ay, by), cy);
+  bb->x_min = fr_cvt_int_x86(ceil(lox));
+  bb->x_max = fr_cvt_int_x86(floor(hix));
+  bb->y_min = fr_cvt_int_x86(ceil(loy));
+  bb->y_max = fr_cvt_int_x86(floor(hiy));
+  if (bb->x_max < bb->x_min || bb->y_max < bb->y_min || bb->x_max > width - 1 || bb->x_min < 0 ||
+      bb->y_max > height - 1 || bb->y_min < 0)
+    return false;
+  return true;
+}
+
+// Flat depth of a triangle (:217): float adds left to right, IEEE float divide by 3.0f.
+FR_HD float fr_tri_depth(float z1, float z2, float z3) { return FR_FDIV(FR_FADD(FR_FADD(z1, z2), z3), 3.0f); }
+
+// Mean of a per-vertex attribute (:223), same float arithmetic.
+FR_HD float fr_tri_mean(float a, float b, float c) { return FR_FDIV(FR_FADD(FR_FADD(a, b), c), 3.0f); }
+
+// Edge-function state of one triangle for PointInTri (:76-109): everything that does not depend on the pixel.
+struct FrTriEdge {
+  double ax, ay;        // pt1
+  double v0x, v0y;      // pt3 - pt1
+  double v1x, v1y;      // pt2 - pt1
+  double dot00, dot01, dot11;
+  double inv;           // 0 when the triangle has zero area (:105-109)
+};
+
+FR_HD void fr_tri_edge_setup(float x1, float y1, float x2, float y2, float x3, float y3, FrTriEdge* e) {
+  e->ax = x1;
+  e->ay = y1;
+  e->v0x = FR_DSUB((double)x3, e->ax);
+  e->v0y = FR_DSUB((double)y3, e->ay);
+  e->v1x = FR_DSUB((double)x2, e->ax);
+  e->v1y = FR_DSUB((double)y2, e->ay);
+  e->dot00 = FR_DADD(FR_DMUL(e->v0x, e->v0x), FR_DMUL(e->v0y, e->v0y));
+  e->dot01 = FR_DADD(FR_DMUL(e->v0x, e->v1x), FR_DMUL(e->v0y, e->v1y));
+  e->dot11 = FR_DADD(FR_DMUL(e->v1x, e->v1x), FR_DMUL(e->v1y, e->v1y));
+  const double den = FR_DSUB(FR_DMUL(e->dot00, e->dot11), FR_DMUL(e->dot01, e->dot01));
+  e->inv = (den == 0) ? 0.0 : FR_DDIV(1.0, den);
+}
+
+// PointInTri for pixel centre (px,py) (:96-121).  Edges through pt1 inclusive, edge pt2-pt3 exclusive.
+FR_HD bool fr_point_in_tri(const FrTriEdge* e, int px, int py) {
+  const double v2x = FR_DSUB((double)px, e->ax);
+  const double v2y = FR_DSUB((double)py, e->ay);
+  const double dot02 = FR_DADD(FR_DMUL(e->v0x, v2x), FR_DMUL(e->v0y, v2y));
+  const double dot12 = FR_DADD(FR_DMUL(e->v1x, v2x), FR_DMUL(e->v1y, v2y));
+  const double u = FR_DMUL(FR_DSUB(FR_DMUL(e->dot11, dot02), FR_DMUL(e->dot01, dot12)), e->inv);
+  if (u < 0 || u > 1) return false;
+  const double v = FR_DMUL(FR_DSUB(FR_DMUL(e->dot00, dot12), FR_DMUL(e->dot01, dot02)), e->inv);
+  if (v < 0 || v > 1) return false;
+  return FR_DADD(u, v) < 1;
+}
+
+// Face normal (:227-236): edge differences in FLOAT, cross product in double, rounded to float on write (:308).
+FR_HD void fr_tri_normal(float x1, float y1, float z1, float x2, float y2, float z2, float x3, float y3, float z3,
+                         float n[3]) {
+  const double e12x = FR_FSUB(x1, x2), e12y = FR_FSUB(y1, y2), e12z = FR_FSUB(z1, z2);
+  const double e13x = FR_FSUB(x1, x3), e13y = FR_FSUB(y1, y3), e13z = FR_FSUB(z1, z3);
+  n[0] = (float)FR_DSUB(FR_DMUL(e12y, e13z), FR_DMUL(e12z, e13y));
+  n[1] = (float)FR_DSUB(FR_DMUL(e12z, e13x), FR_DMUL(e12x, e13z));
+  n[2] = (float)FR_DSUB(FR_DMUL(e12x, e13y), FR_DMUL(e12y, e13x));
+}
+
+// ---- visibility key ------------------------------------------------------------------------------
+// The reference visits triangles in index order and overwrites a pixel iff depth < h (:295), so the
+// winner is (max h, then min index).  Packed as one u64 so a single atomicMax resolves it in any order:
+//   high 32 bits: order-preserving map of the float depth (with -0.0 folded onto +0.0, which compare equal)
+//   low  32 bits: 0xFFFFFFFF - triangle index (smaller index = larger key)
+// 0 is reserved for "background": a triangle only draws when h > background depth (NaN never draws),
+// and every such h maps to a non-zero high word.
+FR_HD uint32_t fr_float_order_bits(float h) {
+  union { float f; uint32_t u; } c;
+  c.f = h;
+  if ((c.u & 0x7FFFFFFFu) == 0u) c.u = 0u;  // -0.0 -> +0.0
+  return (c.u & 0x80000000u) ? ~c.u : (c.u | 0x80000000u);
+}
+
+FR_HD bool fr_depth_draws(float h) {
+  union { uint32_t u; float f; } bg;
+  bg.u = FR_BACKGROUND_DEPTH_BITS;
+  return bg.f < h;  // false for NaN and for anything at or below the background depth
+}
+
+FR_HD unsigned long long fr_pack_key(float h, int tri_index) {
+  return ((unsigned long long)fr_float_order_bits(h) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)tri_index);
+}
+
+FR_HD int fr_key_triangle(unsigned long long key) { return (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)); }
+
+#endif  // FR_RASTER_CORE_H_

@@ -1,0 +1,56 @@
+"""One-process-per-GPU plumbing for the batch-sharded path.
+
+The forward and both backward passes need NO data-path collective (independent faces, basis replicated per GPU), so
+``torch.distributed`` is used only for what a sharded job needs around the kernels: rendezvous, a barrier, and
+max / sum reductions of scalars (timings, unit counts).  Backend: NCCL over NVLink on GPUs, gloo in CPU tests.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    """(rank, local_rank, world_size) from the torchrun environment; (0, 0, 1) when launched directly."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group when WORLD_SIZE > 1.  Returns (rank, local_rank, world_size)."""
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def _device():
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def reduce_scalar(value: float, op: str = "max") -> float:
+    """All-reduce one scalar over ranks (``max`` for device timings, ``sum`` for processed units)."""
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_device())
+    dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN}[op])
+    return float(t.item())
+
+
+def shutdown():
+    if dist.is_initialized():
+        dist.destroy_process_group()

@@ -1,0 +1,67 @@
+"""Device-resident 3DMM: the ``read_3dmm_model`` dict packed once for the kernels.
+
+The reference keeps ``mu``, ``pc_shape`` and ``pc_exp`` as three TF constants and multiplies them separately
+(``nets/network.py:41-43,153-159``).  Here they are packed ONCE into a single tiled, K-contiguous matrix
+``[pc_shape | pc_exp | mu | pad]`` (DESIGN.md "Packed basis") that every forward/backward launch streams exactly once.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_CONVENTIONS = {
+    # name: (pack flags, run flags)            SURVEY.md App. A.2
+    "network": (_lib.FR_MEAN_PLANAR | _lib.FR_BASIS_PLANAR, _lib.FR_ROT_XYZ | _lib.FR_YFLIP_S_Y_1),
+    "sample_test": (_lib.FR_MEAN_INTERLEAVED | _lib.FR_BASIS_PLANAR, _lib.FR_ROT_ZYX | _lib.FR_YFLIP_S_Y),
+    "matlab": (_lib.FR_MEAN_INTERLEAVED | _lib.FR_BASIS_INTERLEAVED, _lib.FR_ROT_XYZ | _lib.FR_YFLIP_NONE),
+}
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class DeviceModel:
+    """Packed basis + triangles + textures of one 3DMM on one GPU."""
+
+    def __init__(self, model: dict, device="cuda:0", convention: str = "network", validate_tri: bool = True):
+        if convention not in _CONVENTIONS:
+            raise ValueError("convention must be one of %s" % sorted(_CONVENTIONS))
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("DeviceModel needs a CUDA device: there is no CPU path")
+        self.convention = convention
+        self.pack_flags, self.run_flags = _CONVENTIONS[convention]
+        mu = np.ascontiguousarray(np.asarray(model["mu"], np.float32).reshape(-1))
+        pc_shape = np.ascontiguousarray(model["pc_shape"], np.float32)
+        pc_exp = np.ascontiguousarray(model["pc_exp"], np.float32)
+        if mu.size % 3 or pc_shape.shape[0] != mu.size or pc_exp.shape[0] != mu.size:
+            raise ValueError("mu [3N,1], pc_shape [3N,Ks] and pc_exp [3N,Ke] disagree on 3N")
+        self.nver = mu.size // 3
+        self.ndim_shape, self.ndim_exp = int(pc_shape.shape[1]), int(pc_exp.shape[1])
+        self.ndim_pose = _lib.FR_NDIM_POSE
+        self.ndim = self.ndim_pose + self.ndim_shape + self.ndim_exp
+        tri = np.ascontiguousarray(model["tri"], np.float32)
+        if tri.ndim != 2 or tri.shape[0] != 3:
+            raise ValueError("The tri is not 3 x ntri")                           # render_depth_op.cc:417
+        if validate_tri and tri.size and (tri.min() < 0 or tri.max() >= self.nver):
+            raise ValueError("tri must hold 0-based vertex indices in [0, %d); the BFM .mat files are 1-based "
+                             "(pass tri - 1)" % self.nver)
+        self.ntri = int(tri.shape[1])
+        with torch.cuda.device(self.device):
+            self.tri = torch.from_numpy(tri).to(self.device)
+            self.vertex_code = torch.from_numpy(np.ascontiguousarray(model["vertex"], np.float32)).to(self.device)
+            self.mu_tex = torch.from_numpy(np.ascontiguousarray(model["mu_tex"], np.float32)).to(self.device)
+            nbytes = lib().fr_packed_basis_bytes(self.nver, self.ndim_shape, self.ndim_exp)
+            self.packed = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            d_mu = torch.from_numpy(mu).to(self.device)
+            d_ps = torch.from_numpy(pc_shape).to(self.device)
+            d_pe = torch.from_numpy(pc_exp).to(self.device)
+            check(lib().fr_pack_basis(d_mu.data_ptr(), d_ps.data_ptr() if d_ps.numel() else None,
+                                      d_pe.data_ptr() if d_pe.numel() else None, self.nver, self.ndim_shape,
+                                      self.ndim_exp, self.pack_flags, self.packed.data_ptr(), _stream_ptr(self.device)))
+            torch.cuda.current_stream(self.device).synchronize()   # d_mu/d_ps/d_pe die here
+        self.basis_bytes = int(nbytes)

@@ -1,0 +1,165 @@
+"""Geometry part of the reference's ``FaceRecNet`` (``nets/network.py``) on PyTorch + the CUDA library.
+
+Only the methods on the params -> depth-map path are mirrored, with the reference's names and argument meaning:
+
+=============================  =====================================  ==========================================
+here                           reference                              what runs
+=============================  =====================================  ==========================================
+``vertices_transform``         ``nets/network.py:140-171``            ``fr_recon_project_forward/backward`` (CUDA)
+``rendering_layer``            ``nets/network.py:174-201``            ``render_depth`` (CUDA) + torch elementwise
+``depth_rendering_layer``      ``nets/network.py:300-308``            both of the above
+``set_constraints``            ``nets/network.py:204-218``            torch elementwise
+``parse_pose_params``          ``nets/network.py:253-263``            slicing
+``rotation_matrix(_batch)``    ``nets/network.py:266-297``            numpy, host-side mirror for inspection only
+=============================  =====================================  ==========================================
+
+The CNN regressors, losses and checkpoint plumbing of ``FaceRecNet`` are out of scope.
+"""
+from __future__ import annotations
+
+from math import cos, sin
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import check, lib
+from ..model import DeviceModel
+from ..rendering_layer.ops import _workspace, render_depth
+
+
+class _ReconProject(torch.autograd.Function):
+    """params [B,d] -> vertex_proj [B,3,N]; gradient as TF autodiff gives it (no gradient to the three angles)."""
+
+    @staticmethod
+    def forward(ctx, params, model: DeviceModel, im_size: float, flags: int):
+        if not params.is_cuda:
+            raise RuntimeError("params is on %s: vertices_transform has no CPU path" % params.device)
+        if params.dim() != 2 or params.shape[1] != model.ndim:
+            raise ValueError("params must be [B, %d] (pose 7 | shape %d | expression %d)" %
+                             (model.ndim, model.ndim_shape, model.ndim_exp))
+        if params.device != model.device:
+            raise ValueError("params is on %s but the model lives on %s" % (params.device, model.device))
+        params = params.float().contiguous()
+        B = int(params.shape[0])
+        dev = params.device
+        out = torch.empty((B, 3, model.nver), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = lib().fr_recon_workspace_bytes(B, model.nver, model.ndim_shape, model.ndim_exp)
+            ws = _workspace(dev, nbytes)
+            check(lib().fr_recon_project_forward(params.data_ptr(), model.packed.data_ptr(), out.data_ptr(), B, model.nver,
+                                                 model.ndim_shape, model.ndim_exp, float(im_size), flags, ws.data_ptr(),
+                                                 ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(params)
+        ctx.model, ctx.flags = model, flags
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (params,) = ctx.saved_tensors
+        model, flags = ctx.model, ctx.flags
+        B = int(params.shape[0])
+        dev = params.device
+        grad_out = grad_out.float().contiguous()
+        dparams = torch.empty_like(params)
+        with torch.cuda.device(dev):
+            nbytes = lib().fr_recon_workspace_bytes(B, model.nver, model.ndim_shape, model.ndim_exp)
+            ws = _workspace(dev, nbytes)
+            check(lib().fr_recon_project_backward(params.data_ptr(), model.packed.data_ptr(), grad_out.data_ptr(),
+                                                  dparams.data_ptr(), B, model.nver, model.ndim_shape, model.ndim_exp, flags,
+                                                  ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return dparams, None, None, None
+
+
+def recon_project(params, model: DeviceModel, im_size=200, flags=None):
+    """Functional form of ``vertices_transform`` for a [B,d] parameter tensor."""
+    return _ReconProject.apply(params, model, float(im_size), model.run_flags if flags is None else int(flags))
+
+
+class FaceRecNet:
+    """The geometry/rendering slice of the reference's ``FaceRecNet`` (constructor arguments as ``network.py:19``)."""
+
+    def __init__(self, im_gray=None, params_label=None, mesh_data=None, nIter=4, batch_size=64, im_size=200,
+                 device="cuda:0", convention="network"):
+        self.im_gray = im_gray
+        self.params_label = params_label
+        self.nIter = nIter
+        self.batch_size = batch_size
+        self.im_size = im_size
+        self.model = mesh_data if isinstance(mesh_data, DeviceModel) else DeviceModel(mesh_data, device, convention)
+        self.vertex_code = self.model.vertex_code          # network.py:39
+        self.tri = self.model.tri                           # network.py:40
+        self.mu_tex = self.model.mu_tex
+        self.ndim_shape, self.ndim_exp, self.ndim_pose = self.model.ndim_shape, self.model.ndim_exp, self.model.ndim_pose
+        self.ndim = self.model.ndim
+        self.nvert = self.model.nver
+        # network.py:57-61: initial prediction = neutral face in the image centre
+        init = torch.zeros((batch_size, self.ndim), dtype=torch.float32, device=self.model.device)
+        init[:, 3] = im_size / 2.0
+        init[:, 4] = im_size / 2.0
+        init[:, 6] = 0.001
+        self.pred_params = init[:, None, None, :]
+
+    # ------------------------------------------------------------------ network.py:140-171
+    def vertices_transform(self, pred_params):
+        """pred_params [B,1,1,d] (or [B,d]) -> vertex_proj [B,3,N]."""
+        p = pred_params
+        if p.dim() == 4:
+            p = p.squeeze(2).squeeze(1)                      # tf.squeeze(pred_params, [1, 2]), network.py:142
+        return recon_project(p, self.model, self.im_size)
+
+    # ------------------------------------------------------------------ network.py:174-201
+    def rendering_layer(self, vertex_proj, triangles, colors):
+        B = vertex_proj.shape[0]
+        texture = colors if colors.dim() == 3 else colors.unsqueeze(0).expand(B, -1, -1)      # tf.tile, network.py:179
+        im_gray = self.im_gray
+        image = vertex_proj.new_empty((B, self.im_size, self.im_size, 3)) if im_gray is None else im_gray.expand(-1, -1, -1, 3)
+        tf_depth, tf_tex, tf_normal, _ = render_depth(ver=vertex_proj, tri=triangles, texture=texture, image=image)
+        pncc_batch = torch.clamp(tf_tex, 1e-6, 1.0)                                            # :185
+        flip = (tf_normal[..., 2:3] < 0)                                                       # :188
+        tf_normal = torch.where(flip, -1.0 * tf_normal, tf_normal)                             # :189
+        mag = (tf_normal * tf_normal).sum(dim=-1)                                              # :190
+        mag = torch.where(mag > 1e-6, mag, torch.ones_like(mag))                               # :191
+        normalimg_batch = tf_normal / (torch.sqrt(mag) + 1e-6).unsqueeze(-1)                   # :192
+        mask = torch.clamp(tf_depth, 1e-6, 1.0)                                                # :195
+        maskimg_batch = mask * im_gray if im_gray is not None else mask                        # :196
+        depthimg_batch = torch.clamp_min(tf_depth, 1e-6)                                       # :199
+        return pncc_batch, normalimg_batch, maskimg_batch, depthimg_batch
+
+    # ------------------------------------------------------------------ network.py:300-308
+    def depth_rendering_layer(self):
+        self.vertices_proj = self.vertices_transform(self.pred_params)
+        self.pncc_batch, self.normal_batch, self.maskimg_batch, self.coarse_depth_map = \
+            self.rendering_layer(self.vertices_proj, self.tri, self.vertex_code)
+        return self.coarse_depth_map
+
+    # ------------------------------------------------------------------ network.py:204-218
+    def set_constraints(self, pred_params):
+        s = torch.sigmoid(pred_params)
+        kp, ks = self.ndim_pose, self.ndim_shape
+        self.pred_params = torch.cat([s[..., 0:3] * 3.0 - 1.5,
+                                      s[..., 3:5] * self.im_size,
+                                      s[..., 5:6] * 0.0,
+                                      s[..., 6:7] * 1e-3,
+                                      s[..., kp:kp + ks] * 1e4,
+                                      s[..., kp + ks:self.ndim] * 3.0 - 1.5], dim=-1)
+        return self.pred_params
+
+    # ------------------------------------------------------------------ network.py:253-263
+    @staticmethod
+    def parse_pose_params(pose_params):
+        return (pose_params[:, 0:1], pose_params[:, 1:2], pose_params[:, 2:3], pose_params[:, 3:6], pose_params[:, 6:7])
+
+    # ------------------------------------------------------------------ network.py:266-297 (host mirror; the device
+    # computes the same matrices inside recon_prep_kernel, no py_func round trip)
+    @staticmethod
+    def rotation_matrix(angles):
+        phi, gamma, theta = [float(a) for a in angles]
+        r_pitch = np.array([[1, 0, 0], [0, cos(phi), sin(phi)], [0, -sin(phi), cos(phi)]])
+        r_yaw = np.array([[cos(gamma), 0, -sin(gamma)], [0, 1, 0], [sin(gamma), 0, cos(gamma)]])
+        r_roll = np.array([[cos(theta), sin(theta), 0], [-sin(theta), cos(theta), 0], [0, 0, 1]])
+        return np.dot(np.dot(r_pitch, r_yaw), r_roll).astype(np.float32)
+
+    @classmethod
+    def rotation_matrix_batch(cls, angles_batch):
+        return np.stack([cls.rotation_matrix(a) for a in np.asarray(angles_batch)]).astype(np.float32)

@@ -1,0 +1,130 @@
+/* facerecon_b200 -- C ABI of the B200-native 3DMM reconstruction + depth-rendering hot path.
+ *
+ * This library replaces the TensorFlow custom-op shared object the reference builds from
+ * rendering_layer/ops_src/ (rendering_layer/ops.py:23-72 compiles and loads render_depth_op.so)
+ * and the in-graph geometry of nets/network.py:140-171.  Each entry point below cites the
+ * reference interface it stands in for.  There is no CPU fallback: every compute entry point
+ * launches CUDA kernels built for sm_100a on the caller's stream.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers owned by the caller (PyTorch / the framework's
+ *     allocator); the library never allocates on the hot path (the reference's GPU op calls
+ *     cudaMalloc/cudaFree six times per launch, render_depth_op.cu.cc:272-277,335-340).
+ *   - Calls are stream-ordered on `stream` (a cudaStream_t passed as void*), never synchronise,
+ *     and are CUDA-graph capturable (the reference launches on the legacy default stream,
+ *     render_depth_op.cu.cc:284,302,321).
+ *   - Return value: FR_OK or an FR_ERR_* code; fr_last_error() returns a thread-local message
+ *     (the reference printf()s and returns with uninitialised outputs, render_depth_op.cc:161-172).
+ *   - Tensors are dense row-major float32 with the reference's layouts.
+ *
+ * The fr_session_* group at the end is the HOST-buffer flavour (inputs/outputs in host memory,
+ * copies done by the library) for callers that are not on the GPU already.
+ */
+#ifndef FACERECON_B200_H_
+#define FACERECON_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR_VERSION 100
+
+/* status codes */
+#define FR_OK 0
+#define FR_ERR_INVALID_ARGUMENT 1 /* shape rule violated (TF InvalidArgument, render_depth_op.cc:408-418) */
+#define FR_ERR_CUDA 2             /* a CUDA runtime call or launch failed */
+#define FR_ERR_WORKSPACE 3        /* workspace pointer null / too small / misaligned */
+#define FR_ERR_UNSUPPORTED 4
+
+/* convention flags.  Run-time flags of fr_recon_project_*: */
+#define FR_ROT_XYZ 0x0u           /* R = Rx.Ry.Rz   nets/network.py:288 (default) */
+#define FR_ROT_ZYX 0x1u           /* R = Rz.Ry.Rx   rendering_layer/sample_test.py:71 */
+#define FR_YFLIP_S_Y_1 0x0u       /* y' = S - y - 1 nets/network.py:168 (default) */
+#define FR_YFLIP_S_Y 0x2u         /* y' = S - y     rendering_layer/sample_test.py:105 */
+#define FR_YFLIP_NONE 0x4u        /* no flip        prepare_data/Project2D.m:12 */
+/* Pack-time flags of fr_pack_basis (memory layout of the 3N-long axis): */
+#define FR_MEAN_PLANAR 0x0u       /* mu[c*N+n]      nets/network.py:157 (default) */
+#define FR_MEAN_INTERLEAVED 0x10u /* mu[3*n+c]      rendering_layer/sample_test.py:101 */
+#define FR_BASIS_PLANAR 0x0u      /* pc[c*N+n,k]    nets/network.py:154,156 (default) */
+#define FR_BASIS_INTERLEAVED 0x20u/* pc[3*n+c,k]    prepare_data/Project2D.m:8-9 */
+
+/* number of pose parameters in front of the shape/expression coefficients (utils/parser_3dmm.py:49) */
+#define FR_NDIM_POSE 7
+
+const char* fr_last_error(void);
+int fr_version(void);
+
+/* ---- model packing: utils/parser_3dmm.py dict -> one K-contiguous device matrix -----------------
+ * Packs [pc_shape | pc_exp | mu | 0-pad] into the tiled layout the kernels stream (DESIGN.md
+ * "Packed basis").  mu [3N], pc_shape [3N,ndim_shape], pc_exp [3N,ndim_exp] are device pointers in
+ * the reference's layouts (nets/network.py:41-43).  One-off, at model load. */
+size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp);
+int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, int nver, int ndim_shape, int ndim_exp,
+                  unsigned layout_flags, float* packed, void* stream);
+
+/* ---- FaceRecNet.vertices_transform (nets/network.py:140-171) ------------------------------------
+ * params [batch, 7+ndim_shape+ndim_exp] (layout nets/network.py:143-145,258-262) -> vertex_proj [batch,3,nver].
+ * Rotation (network.py:266-297, a host py_func in the reference) is computed on the device. */
+size_t fr_recon_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp);
+int fr_recon_project_forward(const float* params, const float* packed, float* vertex_proj, int batch, int nver,
+                             int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* Gradient of the above as TF autodiff produces it: vertex_grad [batch,3,nver]
+ * (gradient w.r.t. vertex_proj) -> params_grad [batch, 7+ndim_shape+ndim_exp]; the three angle entries
+ * are 0 because tf.py_func (network.py:150) has no gradient. */
+int fr_recon_project_backward(const float* params, const float* packed, const float* vertex_grad, float* params_grad,
+                              int batch, int nver, int ndim_shape, int ndim_exp, unsigned flags, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* ---- TF op "RenderDepth" (render_depth_op.cc:378-458, :535-569; functor :132-322) ---------------
+ * vertex [batch,3,nver], tri [3,ntri] FLOAT 0-based indices, texture [batch,3,nver] addressed with
+ * texture_batch_stride floats between faces (0 = one [3,nver] texture shared by all faces, what
+ * network.py:179 materialises with tf.tile).  (batch,height,width) are what the reference takes from
+ * its `image` input (:397-403), whose values it never reads.
+ * Outputs: depth [batch,H,W,1], texture_image [batch,H,W,3], normal [batch,H,W,3], tri_ind [batch,H,W,1]
+ * (float, -1 = background).  texture_image and normal may be NULL to skip them (texture may then be NULL).
+ * Triangles whose indices fall outside [0,nver) are skipped (the reference reads out of bounds). */
+size_t fr_render_workspace_bytes(int batch, int height, int width);
+int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
+                            float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
+                            int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- TF op "RenderDepthGrad" (render_depth_op.cc:470-528, :571-589; functor :325-368) -----------
+ * depth_grad [batch,H,W,1], tri [3,ntri], tri_ind [batch,H,W,1] -> vertex_grad [batch,3,nver], fully
+ * written: rows 0,1 are zero, row 2 receives (g*1.0f)/3.0f per covered pixel and vertex.  Unlike the
+ * reference the output is zero-filled and background pixels are skipped.
+ * The reference's `vertex`, `depth` and `image` inputs are not needed (never read, :329,349-353). */
+int fr_render_depth_backward(const float* depth_grad, const float* tri, const float* tri_ind, float* vertex_grad,
+                             int batch, int nver, int ntri, int height, int width, void* stream);
+
+/* ---- fused convenience: params -> depth map (the north-star path in one call) ------------------- */
+size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width);
+int fr_recon_render_forward(const float* params, const float* packed, const float* tri, float* vertex_proj, float* depth,
+                            float* tri_ind, int batch, int nver, int ntri, int ndim_shape, int ndim_exp, int height,
+                            int width, float im_size, unsigned flags, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* ---- host-buffer session (what a non-GPU caller binds) ----------------------
+ * A session owns the device copy of the model, device staging for `max_batch` faces and one stream.
+ * Every pointer below is a HOST pointer (pinned memory makes the copies asynchronous). */
+typedef struct fr_session fr_session;
+int fr_session_create(const float* mu, const float* pc_shape, const float* pc_exp, const float* tri, int nver, int ntri,
+                      int ndim_shape, int ndim_exp, int height, int width, int max_batch, unsigned flags, int device,
+                      fr_session** out);
+void fr_session_destroy(fr_session* s);
+/* params [batch,d] -> depth [batch,H,W,1] and (optional, may be NULL) tri_ind [batch,H,W,1], vertex_proj [batch,3,nver].
+ * Copies in, runs recon + projection + render, copies out, and waits for completion. */
+int fr_session_forward(fr_session* s, const float* params, int batch, float im_size, float* depth, float* tri_ind,
+                       float* vertex_proj);
+/* depth_grad [batch,H,W,1] for the faces of the last fr_session_forward -> params_grad [batch,d]. */
+int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float* params_grad);
+/* counters: kernels launched by this library since load (for bench.py's gpu_launches) */
+unsigned long long fr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACERECON_B200_H_ */

@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE ONLY.  Host re-enactment of the CUDA rasterizer's data flow (raster.cuh): the same
+// raster_core.h functions the kernels call, driven by plain loops in a deliberately scrambled triangle order, so the
+// key packing / atomicMax visibility / resolve logic can be checked against the oracle on a machine without a GPU.
+// Built by tests/test_raster_core_host.py with g++ -O2 -ffp-contract=off.
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "../../3dfacerecon_b200/csrc/raster_core.h"
+
+static bool vidx(float f, int nver, int* out) {
+  if (!(f > -1.0f && f < (float)nver)) return false;
+  *out = (int)f;
+  return true;
+}
+
+extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, const float* texture, long long tex_stride,
+                                      int batch, int nver, int ntri, int height, int width, unsigned order_seed,
+                                      float* depth, float* teximg, float* normal, float* tri_ind) {
+  const size_t npix = (size_t)height * width;
+  std::vector<unsigned long long> keys(npix);
+  for (int b = 0; b < batch; ++b) {
+    const float* vx = vertex + (size_t)b * 3 * nver;
+    const float* vy = vx + nver;
+    const float* vz = vy + nver;
+    for (auto& k : keys) k = 0ull;
+    // "raster_keys_kernel": any order must give the same result -> visit triangles in a scrambled order
+    const unsigned long long stride = 2654435761ull % (ntri > 0 ? ntri : 1) | 1ull;
+    for (int i = 0; i < ntri; ++i) {
+      int t = order_seed ? (int)(((unsigned long long)i * stride + order_seed) % ntri) : i;
+      // a scrambled permutation needs gcd(stride, ntri) == 1; fall back to reversed order otherwise
+      if (order_seed && ntri % 2 == 0) t = ntri - 1 - i;
+      int p1, p2, p3;
+      if (!vidx(tri[t], nver, &p1) || !vidx(tri[ntri + t], nver, &p2) || !vidx(tri[2 * (size_t)ntri + t], nver, &p3)) continue;
+      FrBBox bb;
+      if (!fr_tri_bbox(vx[p1], vy[p1], vx[p2], vy[p2], vx[p3], vy[p3], width, height, &bb)) continue;
+      const float h = fr_tri_depth(vz[p1], vz[p2], vz[p3]);
+      if (!fr_depth_draws(h)) continue;
+      FrTriEdge e;
+      fr_tri_edge_setup(vx[p1], vy[p1], vx[p2], vy[p2], vx[p3], vy[p3], &e);
+      const unsigned long long key = fr_pack_key(h, t);
+      for (int y = bb.y_min; y <= bb.y_max; ++y)
+        for (int x = bb.x_min; x <= bb.x_max; ++x)
+          if (fr_point_in_tri(&e, x, y)) {
+            unsigned long long& k = keys[(size_t)y * width + x];
+            if (key > k) k = key;  // atomicMax
+          }
+    }
+    // "raster_resolve_kernel"
+    for (size_t p = 0; p < npix; ++p) {
+      const size_t o = (size_t)b * npix + p;
+      union { uint32_t u; float f; } bg;
+      bg.u = FR_BACKGROUND_DEPTH_BITS;
+      float d = bg.f, ti = -1.0f, n[3] = {0, 0, 0}, tx[3] = {0, 0, 0};
+      if (keys[p] != 0ull) {
+        const int t = fr_key_triangle(keys[p]);
+        const int p1 = (int)tri[t], p2 = (int)tri[ntri + t], p3 = (int)tri[2 * (size_t)ntri + t];
+        d = fr_tri_depth(vz[p1], vz[p2], vz[p3]);
+        ti = (float)t;
+        fr_tri_normal(vx[p1], vy[p1], vz[p1], vx[p2], vy[p2], vz[p2], vx[p3], vy[p3], vz[p3], n);
+        const float* tex = texture + (size_t)b * tex_stride;
+        for (int c = 0; c < 3; ++c) tx[c] = fr_tri_mean(tex[(size_t)c * nver + p1], tex[(size_t)c * nver + p2], tex[(size_t)c * nver + p3]);
+      }
+      depth[o] = d;
+      tri_ind[o] = ti;
+      for (int c = 0; c < 3; ++c) {
+        normal[3 * o + c] = n[c];
+        teximg[3 * o + c] = tx[c];
+      }
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,160 @@
+"""GPU parity: 3DMM reconstruction + projection kernels (recon_project / FaceRecNet.vertices_transform -> C ABI) against
+the numpy float64 restatement of nets/network.py:140-171 and the golden vectors made by executing the reference.
+Tolerances (BASELINE.json north_star): vertices 1e-5 relative, gradients 1e-4 relative (norm-wise)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import recon
+from conftest import GOLDEN, fr
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+DEV = "cuda:0"
+VERT_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _model_from_golden(g):
+    n = g["mu"].shape[0] // 3
+    return {"mu": g["mu"], "pc_shape": g["pc_shape"], "pc_exp": g["pc_exp"], "tri": g["tri"], "vertex": g["vertex"],
+            "mu_tex": g["mu_tex"], "ndim_shape": g["pc_shape"].shape[1], "ndim_exp": g["pc_exp"].shape[1], "ndim_pose": 7}
+
+
+def _gpu_vertices(model, params, im_size, convention="network"):
+    dm = fr("model").DeviceModel(model, DEV, convention)
+    out = fr("nets.network").recon_project(torch.from_numpy(np.asarray(params, np.float32)).to(DEV), dm, im_size)
+    torch.cuda.synchronize()
+    return dm, out.cpu().numpy()
+
+
+@pytest.mark.parametrize("tag", ["tiny", "truek"])
+def test_golden_variant_A(tag):
+    g = np.load(os.path.join(GOLDEN, "recon_A_%s.npz" % tag))
+    _, got = _gpu_vertices(_model_from_golden(g), g["params"], int(g["im_size"]))
+    assert np.abs(got - g["vertex_proj"]).max() <= VERT_TOL * np.abs(g["vertex_proj"]).max()
+
+
+def test_golden_variant_B():
+    g = np.load(os.path.join(GOLDEN, "recon_B_sample_test.npz"))
+    _, got = _gpu_vertices(_model_from_golden(g), g["params"], int(g["im_size"]), "sample_test")
+    assert np.abs(got[0] - g["vertex_proj"]).max() <= VERT_TOL * np.abs(g["vertex_proj"]).max()
+
+
+@pytest.fixture(scope="module")
+def bfm():
+    return fr("synth").make_synthetic_model(seed=0, jitter=0.2)          # true dims: 53 215 / 105 840 / 199 / 29
+
+
+@pytest.mark.parametrize("B,full", [(1, False), (3, True), (8, False), (16, True), (20, False), (64, False), (70, True)])
+def test_bfm_size_forward(bfm, B, full):
+    p = fr("synth").sample_params_constrained(B, seed=2 + B, full_range=full)
+    _, got = _gpu_vertices(bfm, p, 200)
+    want = recon.vertices_transform(p, bfm, 200)                           # float64 ground truth
+    assert got.shape == want.shape == (B, 3, 53215)
+    err = np.abs(got - want).max(axis=(1, 2)) / np.abs(want).max(axis=(1, 2))
+    assert err.max() <= VERT_TOL, err
+
+
+@pytest.mark.parametrize("convention,conv", [("sample_test", recon.VARIANT_B), ("matlab", recon.VARIANT_C)])
+def test_other_conventions(small_model, convention, conv):
+    p = fr("synth").sample_params_constrained(5, small_model["ndim_shape"], small_model["ndim_exp"], 64, seed=5, full_range=True)
+    _, got = _gpu_vertices(small_model, p, 64, convention)
+    want = recon.vertices_transform(p, small_model, 64, conv=conv)
+    assert np.abs(got - want).max() <= VERT_TOL * np.abs(want).max()
+
+
+@pytest.mark.parametrize("B", [2, 20, 64])
+def test_bfm_size_backward(bfm, B):
+    """d params of sum(vertex_proj * g) for a full [B,3,N] upstream gradient (the TF autodiff chain, App. A.4)."""
+    p = fr("synth").sample_params_constrained(B, seed=40 + B)
+    rng = np.random.default_rng(B)
+    g = rng.normal(size=(B, 3, 53215)).astype(np.float32)
+    dm = fr("model").DeviceModel(bfm, DEV)
+    pt = torch.from_numpy(p).to(DEV).requires_grad_(True)
+    vp = fr("nets.network").recon_project(pt, dm, 200)
+    (vp * torch.from_numpy(g).to(DEV)).sum().backward()
+    got = pt.grad.cpu().numpy().astype(np.float64)
+    want = recon.vertices_transform_backward(p, bfm, g)
+    assert not got[:, 0:3].any()
+    for sl in (slice(3, 6), slice(6, 7), slice(7, 206), slice(206, 235)):
+        scale = np.abs(want[:, sl]).max(axis=1, keepdims=True)
+        assert (np.abs(got[:, sl] - want[:, sl]) <= GRAD_TOL * scale).all(), sl
+
+
+def test_depth_only_gradient_chain(bfm):
+    """BASELINE config 4 shape of the computation: params -> depth, d depth -> d params (z row only)."""
+    net = fr("nets.network")
+    B = 4
+    p = fr("synth").sample_params_constrained(B, seed=77)
+    dm = fr("model").DeviceModel(bfm, DEV)
+    pt = torch.from_numpy(p).to(DEV).requires_grad_(True)
+    vp = net.recon_project(pt, dm, 200)
+    image = torch.empty((B, 200, 200, 3), device=DEV)
+    depth, _, _, tri_ind = fr("rendering_layer.ops").render_depth(vp, dm.tri, dm.vertex_code.unsqueeze(0).expand(B, -1, -1), image)
+    gd = torch.from_numpy(np.random.default_rng(3).normal(size=(B, 200, 200, 1)).astype(np.float32)).to(DEV) * (tri_ind >= 0)
+    (depth * gd).sum().backward()
+    vgrad = oracle.oracle_render_depth_backward(gd.cpu().numpy(), bfm["tri"], tri_ind.cpu().numpy(), 53215)
+    want = recon.vertices_transform_backward(p, bfm, vgrad)
+    got = pt.grad.cpu().numpy()
+    for sl in (slice(3, 6), slice(6, 7), slice(7, 206), slice(206, 235)):
+        scale = np.abs(want[:, sl]).max(axis=1, keepdims=True) + 1e-30
+        assert (np.abs(got[:, sl] - want[:, sl]) <= GRAD_TOL * scale).all(), sl
+
+
+def test_pipeline_matches_reference_path(bfm):
+    """recon (GPU) -> render (GPU) vs the reference CPU op fed the SAME float32 vertex buffer: bit-exact; and vs the
+    oracle fed float64-restated vertices: tri_ind may differ only where <= 1-ulp vertex differences move an edge."""
+    B = 6
+    p = fr("synth").sample_params_constrained(B, seed=11)
+    dm, vp = _gpu_vertices(bfm, p, 200)
+    image = torch.empty((B, 200, 200, 3), device=DEV)
+    out = fr("rendering_layer.ops").render_depth(torch.from_numpy(vp).to(DEV), dm.tri, dm.vertex_code.unsqueeze(0).expand(B, -1, -1), image)
+    got = [o.cpu().numpy() for o in out]
+    want = oracle.oracle_render_depth_forward(vp, bfm["tri"], bfm["vertex"], 200, 200)
+    for g, w in zip(got, want):
+        assert g.tobytes() == w.tobytes()
+    vp64 = recon.vertices_transform(p, bfm, 200).astype(np.float32)
+    ref = oracle.oracle_render_depth_forward(vp64, bfm["tri"], bfm["vertex"], 200, 200)
+    mismatch = (ref[3] != got[3]).mean()
+    assert mismatch < 2e-3, mismatch                                      # documented budget
+    same = ref[3] == got[3]
+    rel = np.abs(ref[0][same] - got[0][same]) / np.maximum(np.abs(ref[0][same]), 1e-3)
+    assert rel.max() <= 1e-5
+
+
+def test_session_host_buffers_match_tensor_path(bfm):
+    B = 5
+    p = fr("synth").sample_params_constrained(B, seed=21)
+    dm, vp = _gpu_vertices(bfm, p, 200)
+    image = torch.empty((B, 200, 200, 3), device=DEV)
+    out = fr("rendering_layer.ops").render_depth(torch.from_numpy(vp).to(DEV), dm.tri, dm.vertex_code.unsqueeze(0).expand(B, -1, -1), image)
+    sess = fr("session").Session(bfm, 200, 200, max_batch=8, device=0)
+    vps = np.empty((B, 3, 53215), np.float32)
+    depth, tri_ind = sess.forward(p, 200.0, vertex_proj=vps)
+    assert vps.tobytes() == vp.tobytes()
+    assert depth.tobytes() == out[0].cpu().numpy().tobytes() and tri_ind.tobytes() == out[3].cpu().numpy().tobytes()
+    gd = (np.random.default_rng(5).normal(size=depth.shape).astype(np.float32)) * (tri_ind >= 0)
+    pg = sess.backward(gd)
+    vgrad = oracle.oracle_render_depth_backward(gd, bfm["tri"], tri_ind, 53215)
+    want = recon.vertices_transform_backward(p, bfm, vgrad)
+    for sl in (slice(3, 6), slice(6, 7), slice(7, 206), slice(206, 235)):
+        scale = np.abs(want[:, sl]).max(axis=1, keepdims=True) + 1e-30
+        assert (np.abs(pg[:, sl] - want[:, sl]) <= GRAD_TOL * scale).all(), sl
+    sess.close()
+
+
+def test_facerecnet_mirror(bfm):
+    """The FaceRecNet geometry slice end to end: default pred_params -> depth_rendering_layer (network.py:300-308)."""
+    net = fr("nets.network").FaceRecNet(mesh_data=bfm, batch_size=2, im_size=200, device=DEV)
+    depth = net.depth_rendering_layer()
+    assert depth.shape == (2, 200, 200, 1) and float(depth.min()) >= 1e-6 * 0.999
+    vp = net.vertices_proj.cpu().numpy()
+    want = recon.vertices_transform(net.pred_params[:, 0, 0, :].cpu().numpy(), bfm, 200)
+    assert np.abs(vp - want).max() <= VERT_TOL * np.abs(want).max()
+    assert net.pncc_batch.shape == (2, 200, 200, 3) and net.normal_batch.shape == (2, 200, 200, 3)
+    nrm = (net.normal_batch ** 2).sum(-1)
+    cov = net.coarse_depth_map[..., 0] > 1e-6
+    assert torch.allclose(nrm[cov], torch.ones_like(nrm[cov]), atol=1e-3)

@@ -1,0 +1,157 @@
+"""GPU parity: the CUDA rasterizer (through the public render_depth API -> C ABI) against the CPU oracle and the
+golden vectors produced by the reference.  Forward outputs are compared BIT FOR BIT; gradients within 1e-4."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import recon
+from conftest import fr
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+DEV = "cuda:0"
+NAMES = ("depth", "texture_image", "normal", "tri_ind")
+
+
+def _gpu_render(vertex, tri, texture, H, W, expand_texture=False):
+    ops = fr("rendering_layer.ops")
+    v = torch.from_numpy(np.ascontiguousarray(vertex, np.float32)).to(DEV)
+    t = torch.from_numpy(np.ascontiguousarray(tri, np.float32)).to(DEV)
+    x = torch.from_numpy(np.ascontiguousarray(texture, np.float32)).to(DEV)
+    if expand_texture:
+        x = x.unsqueeze(0).expand(v.shape[0], -1, -1)
+    image = torch.empty((v.shape[0], H, W, 3), device=DEV)
+    out = ops.render_depth(v, t, x, image)
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in out]
+
+
+def _assert_same(got, want, tag=""):
+    for g, w, n in zip(got, want, NAMES):
+        assert g.shape == w.shape, (tag, n)
+        if g.tobytes() != w.tobytes():
+            bad = np.argwhere(g.view(np.uint32) != w.view(np.uint32))
+            raise AssertionError("%s %s: %d mismatching elements, first at %s: got %r want %r" %
+                                 (tag, n, len(bad), bad[0], g[tuple(bad[0])], w[tuple(bad[0])]))
+
+
+def test_library_is_the_cuda_build():
+    lib = fr("_lib").lib()
+    assert lib.fr_version() == 100
+    before = lib.fr_launch_count()
+    _gpu_render(np.zeros((1, 3, 3), np.float32), np.array([[0], [1], [2]], np.float32), np.zeros((1, 3, 3), np.float32), 8, 8)
+    assert lib.fr_launch_count() >= before + 2
+
+
+def test_golden_cases_bit_exact(render_golden):
+    for name, c in render_golden.items():
+        B, H, W, _ = [int(x) for x in c["image_shape"]]
+        got = _gpu_render(c["vertex"], c["tri"], c["texture"], H, W)
+        _assert_same(got, [c[k] for k in NAMES], name)
+
+
+def test_golden_backward(render_golden):
+    ops = fr("rendering_layer.ops")
+    for name, c in render_golden.items():
+        B, H, W, _ = [int(x) for x in c["image_shape"]]
+        image = torch.empty((B, H, W, 3), device=DEV)
+        got = ops.render_depth_grad(torch.from_numpy(c["depth_grad"]).to(DEV), torch.from_numpy(c["vertex"]).to(DEV),
+                                    torch.from_numpy(c["tri"]).to(DEV), torch.from_numpy(c["depth"]).to(DEV),
+                                    torch.from_numpy(c["tri_ind"]).to(DEV), image).cpu().numpy()
+        want = c["vertex_grad"]
+        assert not got[:, 0:2].any()
+        assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), name
+
+
+def _bfm_vertices(B, seed, jitter=0.2, im=200, full_range=False):
+    synth = fr("synth")
+    m = synth.make_synthetic_model(ndim_shape=6, ndim_exp=3, seed=0, jitter=jitter)     # true N and T, small K (CPU recon)
+    p = synth.sample_params_constrained(B, 6, 3, im, seed=seed, full_range=full_range)
+    p[:, 7:13] *= 10.0                                                                   # keep ~2 px deformations with 6 modes
+    vp = recon.vertices_transform(p, m, im, dtype=np.float32).astype(np.float32)
+    return m, vp
+
+
+@pytest.mark.parametrize("jitter,full_range,B", [(0.2, False, 4), (0.0, False, 3), (0.2, True, 5), (0.2, False, 1)])
+def test_bfm_size_forward_bit_exact(jitter, full_range, B):
+    """53 215 vertices / 105 840 triangles / 200x200 (BASELINE configs 1-2 geometry) on a shared float32 vertex buffer."""
+    m, vp = _bfm_vertices(B, seed=4, jitter=jitter, full_range=full_range)
+    assert m["tri"].shape == (3, 105840) and vp.shape == (B, 3, 53215)
+    want = oracle.oracle_render_depth_forward(vp, m["tri"], m["vertex"], 200, 200)
+    got = _gpu_render(vp, m["tri"], m["vertex"], 200, 200, expand_texture=True)
+    _assert_same(got, want, "bfm")
+    if not full_range:
+        assert (want[3] >= 0).mean() > 0.3
+    got2 = _gpu_render(vp, m["tri"], m["vertex"], 200, 200, expand_texture=True)         # run-to-run determinism
+    _assert_same(got2, got, "determinism")
+
+
+def test_bfm_size_backward_and_autograd():
+    ops = fr("rendering_layer.ops")
+    m, vp = _bfm_vertices(3, seed=6)
+    v = torch.from_numpy(vp).to(DEV).requires_grad_(True)
+    tri = torch.from_numpy(m["tri"]).to(DEV)
+    tex = torch.from_numpy(m["vertex"]).to(DEV).unsqueeze(0).expand(3, -1, -1)
+    image = torch.empty((3, 200, 200, 3), device=DEV)
+    depth, teximg, normal, tri_ind = ops.render_depth(v, tri, tex, image)
+    assert depth.requires_grad and not tri_ind.requires_grad and not normal.requires_grad
+    g = torch.from_numpy(np.random.default_rng(0).normal(size=(3, 200, 200, 1)).astype(np.float32)).to(DEV)
+    g = g * (tri_ind >= 0)                                            # tf.maximum gating, nets/network.py:199
+    (depth * g).sum().backward()
+    want = oracle.oracle_render_depth_backward(g.cpu().numpy(), m["tri"], tri_ind.cpu().numpy(), vp.shape[2])
+    got = v.grad.cpu().numpy()
+    assert not got[:, 0:2].any()
+    assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+    # checksum property: sum of vertex_grad == sum of depth_grad over covered pixels
+    assert abs(got.astype(np.float64).sum() - g.cpu().numpy().astype(np.float64).sum()) <= 1e-3 * np.abs(g.cpu().numpy()).sum()
+
+
+def test_validation_errors():
+    ops = fr("rendering_layer.ops")
+    z = lambda *s: torch.zeros(s, device=DEV)
+    with pytest.raises(ValueError, match="vertex's batch"):
+        ops.render_depth(z(2, 3, 5), z(3, 1), z(2, 3, 5), z(1, 8, 8, 3))
+    with pytest.raises(ValueError, match="Batch x 3 x nver"):
+        ops.render_depth(z(2, 4, 5), z(3, 1), z(2, 3, 5), z(2, 8, 8, 3))
+    with pytest.raises(ValueError, match="3 x ntri"):
+        ops.render_depth(z(2, 3, 5), z(2, 1), z(2, 3, 5), z(2, 8, 8, 3))
+    with pytest.raises(ValueError, match="texture channel"):
+        ops.render_depth(z(2, 3, 5), z(3, 1), z(2, 4, 5), z(2, 8, 8, 3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.render_depth(torch.zeros(2, 3, 5), z(3, 1), z(2, 3, 5), z(2, 8, 8, 3))
+
+
+def test_edge_shapes():
+    """Empty triangle list, out-of-range indices (skipped), non-square image, huge coordinates."""
+    v = np.array([[[0, 4, 0, 1e20, np.nan], [0, 0, 4, 1, 2], [1, 1, 1, 1, 1]]], np.float32)
+    tex = np.zeros_like(v)
+    got = _gpu_render(v, np.zeros((3, 0), np.float32), tex, 5, 9)
+    assert (got[3] == -1).all() and (got[0].view(np.uint32) == 0xD6B5E621).all() and not got[1].any() and not got[2].any()
+    tri = np.array([[0, 0, 0, 7], [1, 3, 4, 1], [2, 2, 2, 2]], np.float32)            # last column: index 7 >= nver
+    want = oracle.oracle_render_depth_forward(v, tri[:, :3], tex, 5, 9)
+    _assert_same(_gpu_render(v, tri, tex, 5, 9), want, "edge")
+
+
+def test_full_batch_properties():
+    """BASELINE config-2 size (B = 64): properties that need no oracle run per face + oracle on a sample of faces."""
+    B = 64
+    m, vp = _bfm_vertices(B, seed=2)
+    got = _gpu_render(vp, m["tri"], m["vertex"], 200, 200, expand_texture=True)
+    depth, teximg, normal, tri_ind = got
+    covered = tri_ind[..., 0] >= 0
+    assert (depth[..., 0][~covered].view(np.uint32) == 0xD6B5E621).all()
+    assert np.isfinite(depth[..., 0][covered]).all() and (tri_ind[..., 0] < m["tri"].shape[1]).all()
+    # depth of a covered pixel is the flat depth of its triangle
+    b_idx, y_idx, x_idx = np.nonzero(covered)
+    t = tri_ind[b_idx, y_idx, x_idx, 0].astype(np.int64)
+    idx = m["tri"].astype(np.int64)[:, t]
+    z = vp[b_idx[None, :], 2, idx]
+    assert np.array_equal(depth[b_idx, y_idx, x_idx, 0], ((z[0] + z[1]) + z[2]) / np.float32(3.0))
+    # batch permutation invariance and independence of faces
+    perm = np.random.default_rng(1).permutation(B)
+    got_p = _gpu_render(vp[perm], m["tri"], m["vertex"], 200, 200, expand_texture=True)
+    _assert_same(got_p, [g[perm] for g in got], "perm")
+    for b in (0, 17, 63):
+        want = oracle.oracle_render_depth_forward(vp[b:b + 1], m["tri"], m["vertex"], 200, 200)
+        _assert_same([g[b:b + 1] for g in got], want, "face %d" % b)

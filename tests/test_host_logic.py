@@ -1,0 +1,114 @@
+"""CPU: host-side logic -- C-ABI surface, sharding, the multi-process plumbing (gloo, world_size 2), synthetic model."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, fr
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "facerecon_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fr_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    lib_mod = fr("_lib")
+    names = _declared_symbols()
+    assert len(names) >= 17 and "fr_render_depth_forward" in names and "fr_session_forward" in names
+    assert sorted(lib_mod.SIGNATURES) == names                      # the ctypes table covers the header exactly
+    handle = ctypes.CDLL(lib_mod.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), n
+    lib = lib_mod.lib()
+    assert lib.fr_version() == 100
+    # size queries are pure host arithmetic: safe without a GPU
+    assert lib.fr_packed_basis_bytes(53215, 199, 29) == 416 * 3 * 58 * 128 * 16
+    assert lib.fr_render_workspace_bytes(64, 200, 200) == 64 * 200 * 200 * 8
+    assert lib.fr_recon_workspace_bytes(64, 53215, 199, 29) >= 232 * 64 * 4
+    assert lib.fr_packed_basis_bytes(0, 199, 29) == 0
+
+
+def test_abi_rejects_bad_arguments_without_a_gpu():
+    """Validation happens before any CUDA call, so it is checkable here; messages follow the reference's."""
+    lib_mod = fr("_lib")
+    lib = lib_mod.lib()
+    rc = lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 1, 10, 10 * 1000 * 1000, 8, 8, None, 0, None)
+    assert rc == lib_mod.FR_ERR_INVALID_ARGUMENT and "Too many triangular" in lib_mod.last_error()
+    rc = lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 1, 10, 5, 8, 8, None, 0, None)
+    assert rc == lib_mod.FR_ERR_INVALID_ARGUMENT and "null pointer" in lib_mod.last_error()
+    rc = lib.fr_recon_project_forward(None, None, None, 1, 10, 0, 0, 200.0, 0, None, 0, None)
+    assert rc == lib_mod.FR_ERR_INVALID_ARGUMENT
+    with pytest.raises(ValueError):
+        lib_mod.check(rc)
+    assert lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 0, 10, 5, 8, 8, None, 0, None) == 0   # empty batch
+
+
+def test_product_has_no_oracle_or_cpu_path():
+    """The shipped package must not import the oracle or numpy-compute its results (DESIGN.md 'no fallback')."""
+    pkg = os.path.join(ROOT, "3dfacerecon_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "libref_render_depth" not in text, f
+
+
+def test_shard_batch():
+    sh = fr("sharding")
+    for B in (0, 1, 7, 64, 4096, 4099):
+        for W in (1, 2, 4, 8):
+            parts = sh.shard_slices(B, W)
+            assert sum(c for _, c in parts) == B
+            assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(W - 1)) and parts[0][0] == 0
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+    with pytest.raises(ValueError):
+        sh.shard_batch(4, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    d = importlib.import_module("3dfacerecon_b200.distributed")
+    sh = importlib.import_module("3dfacerecon_b200.sharding")
+    r, lr, w = d.init_from_env(backend="gloo")
+    start, count = sh.shard_batch(4099, w, r)
+    d.barrier()
+    total = d.reduce_scalar(count, "sum")
+    slowest = d.reduce_scalar(10.0 + r, "max")
+    q.put((r, start, count, total, slowest))
+    d.shutdown()
+
+
+def test_two_rank_gloo_plumbing():
+    """What bench.py does at N > 1: shard units over ranks, barrier, sum the units, take the max of the timings."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [r[1:3] for r in res] == [(0, 2050), (2050, 2049)]
+    assert all(r[3] == 4099.0 and r[4] == 11.0 for r in res)
+
+
+def test_synthetic_model_shapes():
+    m = fr("synth").make_synthetic_model(grid=(9, 11), ndim_shape=4, ndim_exp=2, seed=1)
+    n = 99
+    assert m["mu"].shape == (3 * n, 1) and m["pc_shape"].shape == (3 * n, 4) and m["pc_exp"].shape == (3 * n, 2)
+    assert m["tri"].shape == (3, 2 * 8 * 10) and m["tri"].dtype == np.float32
+    assert m["tri"].min() == 0 and m["tri"].max() == n - 1
+    assert set(m) == {"vertex", "tri", "mu", "mu_tex", "pc_tex", "param_tex", "pc_shape", "pc_exp", "ndim_shape", "ndim_exp", "ndim_pose"}
+    p = fr("synth").sample_params_constrained(5, 4, 2)
+    assert p.shape == (5, 13) and (p[:, 5] == 0).all() and (np.abs(p[:, :3]) <= 1.5).all()
