@@ -215,8 +215,12 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
       raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(vertex, tri, keys, batch, nver, ntri, height, width);
     FR_LAUNCHED("raster_keys_kernel");
   }
-  raster_resolve_kernel<<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(
-      keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
+  if (texture_image != nullptr || normal != nullptr)
+    raster_resolve_kernel<true><<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(
+        keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
+  else
+    raster_resolve_kernel<false><<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(
+        keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
   FR_LAUNCHED("raster_resolve_kernel");
   return FR_OK;
 }

@@ -151,4 +151,30 @@ FR_HD unsigned long long fr_pack_key(float h, int tri_index) {
 
 FR_HD int fr_key_triangle(unsigned long long key) { return (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)); }
 
+// Depth stored in a (non-zero) key.  The map is invertible except that -0.0 was folded onto +0.0: when the result
+// is +0.0 the caller must recompute the winner's depth from its vertices to recover the sign (*ambiguous = true).
+FR_HD float fr_key_depth(unsigned long long key, bool* ambiguous) {
+  const uint32_t o = (uint32_t)(key >> 32);
+  union { uint32_t u; float f; } c;
+  c.u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  *ambiguous = (c.u == 0u);
+  return c.f;
+}
+
+// Same result as fr_tri_bbox for every input, but in float arithmetic when no coordinate is NaN: min/max/ceil/floor
+// of float values are exact in float, and comparing the float bounds against [0, W-1] culls exactly the cases where
+// the reference's (int) conversion leaves the image or overflows to INT_MIN.  NaNs take the literal path.
+FR_HD bool fr_tri_bbox_fast(float x1, float y1, float x2, float y2, float x3, float y3, int width, int height, FrBBox* bb) {
+  const float sx = (x1 + x2) + x3, sy = (y1 + y2) + y3;   // NaN iff a coordinate is NaN (or inf - inf: also slow path)
+  if (sx != sx || sy != sy) return fr_tri_bbox(x1, y1, x2, y2, x3, y3, width, height, bb);
+  const float lox = ceilf(fminf(fminf(x1, x2), x3)), hix = floorf(fmaxf(fmaxf(x1, x2), x3));
+  const float loy = ceilf(fminf(fminf(y1, y2), y3)), hiy = floorf(fmaxf(fmaxf(y1, y2), y3));
+  if (hix < lox || hiy < loy || hix > (float)(width - 1) || lox < 0.0f || hiy > (float)(height - 1) || loy < 0.0f) return false;
+  bb->x_min = (int)lox;
+  bb->x_max = (int)hix;
+  bb->y_min = (int)loy;
+  bb->y_max = (int)hiy;
+  return true;
+}
+
 #endif  // FR_RASTER_CORE_H_

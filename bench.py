@@ -110,18 +110,21 @@ class CpuArm:
 
 # ----------------------------------------------------------------------------------------------------------------------
 def _clock_sampler_start(gpu_index):
-    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling in the background (B200_PROFILING.md clocks line, plus a timestamp)."""
+    q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     try:
         f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                              stdout=f, stderr=subprocess.DEVNULL)
         return p, f
     except Exception:
         return None, None
 
 
-def _clock_sampler_stop(p, f):
+def _clock_sampler_stop(p, f, t_begin, t_end):
+    """Summarise the samples whose timestamp falls inside [t_begin, t_end] (time.time() seconds)."""
+    import datetime
     if p is None:
         return None
     p.terminate()
@@ -131,12 +134,16 @@ def _clock_sampler_stop(p, f):
         p.kill()
     f.flush()
     f.seek(0)
-    sm, mx, reasons = [], [], set()
+    sm, mx, reasons, total = [], [], set(), 0
     for line in f.read().splitlines():
         c = [x.strip() for x in line.split(",")]
         if len(c) < 9:
             continue
+        total += 1
         try:
+            ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            if ts < t_begin - 0.05 or ts > t_end + 0.05:
+                continue
             sm.append(float(c[1]))
             mx.append(float(c[2]))
         except ValueError:
@@ -150,8 +157,12 @@ def _clock_sampler_stop(p, f):
     except OSError:
         pass
     if not sm:
-        return None
-    return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "samples_total": total}
+    return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+            "window": "timed loops + %.1f s soak of the same step" % SOAK_SECONDS}
+
+
+SOAK_SECONDS = 1.5
 
 
 def _peak_hbm():
@@ -246,13 +257,22 @@ def run_ours(args):
         return sum(a.elapsed_time(b) for a, b in evs) / steps          # ms per step
 
     sampler = _clock_sampler_start(local_rank) if rank == 0 else (None, None)
+    time.sleep(0.3 if rank == 0 else 0.0)                             # let nvidia-smi come up
+    t_begin = time.time()
     launches0 = lib.fr_launch_count()
     ms_full = timed(step_full, args.steps, args.warmup)
     launches = (lib.fr_launch_count() - launches0)
     launches_timed = launches * args.steps // (args.steps + args.warmup)
-    clocks = _clock_sampler_stop(*sampler) if rank == 0 else None
     ms_recon = timed(step_recon, args.steps, args.warmup)
     ms_render = timed(step_render, args.steps, args.warmup)
+    # the timed loops last only milliseconds: keep the same step running so the 50 ms clock sampler sees it under load
+    t_soak = time.time()
+    while time.time() - t_soak < SOAK_SECONDS:
+        for _ in range(20):
+            step_full()
+        torch.cuda.synchronize(dev)
+    t_end = time.time()
+    clocks = _clock_sampler_stop(*sampler, t_begin, t_end) if rank == 0 else None
     ms_full_max = dist.reduce_scalar(ms_full, "max")
     ms_recon_max = dist.reduce_scalar(ms_recon, "max")
     ms_render_max = dist.reduce_scalar(ms_render, "max")

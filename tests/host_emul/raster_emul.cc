@@ -33,7 +33,12 @@ extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, con
       int p1, p2, p3;
       if (!vidx(tri[t], nver, &p1) || !vidx(tri[ntri + t], nver, &p2) || !vidx(tri[2 * (size_t)ntri + t], nver, &p3)) continue;
       FrBBox bb;
-      if (!fr_tri_bbox(vx[p1], vy[p1], vx[p2], vy[p2], vx[p3], vy[p3], width, height, &bb)) continue;
+      FrBBox bb_ref;
+      const bool keep_ref = fr_tri_bbox(vx[p1], vy[p1], vx[p2], vy[p2], vx[p3], vy[p3], width, height, &bb_ref);
+      const bool keep = fr_tri_bbox_fast(vx[p1], vy[p1], vx[p2], vy[p2], vx[p3], vy[p3], width, height, &bb);
+      if (keep != keep_ref) return 100;  // the float fast path must agree with the literal path
+      if (!keep) continue;
+      if (bb.x_min != bb_ref.x_min || bb.x_max != bb_ref.x_max || bb.y_min != bb_ref.y_min || bb.y_max != bb_ref.y_max) return 101;
       const float h = fr_tri_depth(vz[p1], vz[p2], vz[p3]);
       if (!fr_depth_draws(h)) continue;
       FrTriEdge e;
@@ -55,7 +60,10 @@ extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, con
       if (keys[p] != 0ull) {
         const int t = fr_key_triangle(keys[p]);
         const int p1 = (int)tri[t], p2 = (int)tri[ntri + t], p3 = (int)tri[2 * (size_t)ntri + t];
-        d = fr_tri_depth(vz[p1], vz[p2], vz[p3]);
+        bool ambiguous;
+        d = fr_key_depth(keys[p], &ambiguous);
+        if (ambiguous) d = fr_tri_depth(vz[p1], vz[p2], vz[p3]);
+        else if (d != fr_tri_depth(vz[p1], vz[p2], vz[p3])) return 102;  // decoded depth must equal the recomputed one
         ti = (float)t;
         fr_tri_normal(vx[p1], vy[p1], vz[p1], vx[p2], vy[p2], vz[p2], vx[p3], vy[p3], vz[p3], n);
         const float* tex = texture + (size_t)b * tex_stride;

@@ -121,8 +121,8 @@ def test_pipeline_matches_reference_path(bfm):
     mismatch = (ref[3] != got[3]).mean()
     assert mismatch < 2e-3, mismatch                                      # documented budget
     same = ref[3] == got[3]
-    rel = np.abs(ref[0][same] - got[0][same]) / np.maximum(np.abs(ref[0][same]), 1e-3)
-    assert rel.max() <= 1e-5
+    cov = same & (ref[3] >= 0)
+    assert np.abs(ref[0][cov] - got[0][cov]).max() <= 1e-5 * np.abs(ref[0][cov]).max()     # norm-wise, like the vertices
 
 
 def test_session_host_buffers_match_tensor_path(bfm):

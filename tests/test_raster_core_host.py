@@ -31,8 +31,9 @@ def emul():
         B, _, N = vertex.shape
         outs = [np.empty((B, H, W, c), np.float32) for c in (1, 3, 3, 1)]
         p = lambda a: a.ctypes.data_as(_f32p)
-        lib.fr_emul_render_forward(p(vertex), p(tri), p(texture), 3 * N, B, N, tri.shape[1], H, W, seed,
-                                   p(outs[0]), p(outs[1]), p(outs[2]), p(outs[3]))
+        rc = lib.fr_emul_render_forward(p(vertex), p(tri), p(texture), 3 * N, B, N, tri.shape[1], H, W, seed,
+                                        p(outs[0]), p(outs[1]), p(outs[2]), p(outs[3]))
+        assert rc == 0, "emulation self-check %d failed" % rc
         return outs
     return run
 
@@ -74,3 +75,19 @@ def test_key_order_properties():
     assert order_bits(-0.0) == order_bits(0.0)
     assert all(b > 0 for b in bits)
     assert order_bits(oracle.BACKGROUND_DEPTH) < order_bits(np.float32(-9.9e13))
+
+
+def test_emulation_extreme_coordinates(emul):
+    """NaN / inf / beyond-int-range xy: the float fast path of the bbox must agree with the literal double path
+    (self-checked inside the emulation) and with the oracle."""
+    v = np.array([[[0, 4, 0, 1e20, -1e20, np.nan, 3e9, 2, 1, np.inf, -np.inf, 7.5, -0.5],
+                   [0, 0, 4, 1, 2, 3, 1, -3e9, np.inf, 1, 2, 7.0, -0.0],
+                   [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1]]], np.float32)
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, v.shape[2], (3, 400)).astype(np.float32)
+    tex = np.zeros_like(v)
+    want = oracle.oracle_render_depth_forward(v, t, tex, 8, 8)
+    for seed in (0, 5):
+        got = emul(v, t, tex, 8, 8, seed)
+        for g, w in zip(got, want):
+            assert g.tobytes() == w.tobytes()
