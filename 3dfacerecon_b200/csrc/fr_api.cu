@@ -180,9 +180,10 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ render
-size_t fr_render_workspace_bytes(int batch, int height, int width) {
-  if (batch <= 0 || height <= 0 || width <= 0) return 0;
-  return align_up(sizeof(unsigned long long) * (size_t)batch * height * width, kAlign);
+size_t fr_render_workspace_bytes(int batch, int nver, int height, int width) {
+  if (batch <= 0 || nver <= 0 || height <= 0 || width <= 0) return 0;
+  return align_up(sizeof(unsigned long long) * (size_t)batch * height * width, kAlign) +   // visibility keys
+         align_up(sizeof(uint2) * (size_t)batch * nver, kAlign);                             // snapped vertices
 }
 
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
@@ -193,26 +194,31 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
   // render_depth_op.cc:161-166: the reference refuses ntri >= 10M (its static scratch); nver < 2^24 keeps float indices exact
   FR_REQUIRE(ntri < 10 * 1000 * 1000, "Too many triangular %d >= %d", ntri, 10 * 1000 * 1000);
   FR_REQUIRE(nver <= (1 << 24), "nver %d exceeds the exact range of float triangle indices", nver);
-  FR_REQUIRE((long long)height * width < (1ll << 31), "image too large");
+  FR_REQUIRE(height <= 32000 && width <= 32000 && (long long)height * width < (1ll << 31), "image too large");
+  FR_REQUIRE((long long)batch * 3 * nver < (1ll << 31), "batch * 3 * nver must stay below 2^31: split the batch");
   if (batch == 0) return FR_OK;
-  FR_REQUIRE(vertex && tri && depth && tri_ind, "null pointer argument");
+  FR_REQUIRE(vertex && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
   FR_REQUIRE(texture_image == nullptr || texture != nullptr, "texture_image requested without a texture");
   FR_REQUIRE(texture_batch_stride == 0 || texture_batch_stride >= 3ll * nver, "texture_batch_stride must be 0 or >= 3*nver");
-  const size_t need = fr_render_workspace_bytes(batch, height, width);
+  const size_t need = fr_render_workspace_bytes(batch, nver, height, width);
   if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* keys = static_cast<unsigned long long*>(workspace);
   const int npix = height * width;
+  uint2* snap = reinterpret_cast<uint2*>(static_cast<char*>(workspace) +
+                                         align_up(sizeof(unsigned long long) * (size_t)batch * npix, kAlign));
 
   FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   if (ntri > 0) {
+    raster_snap_kernel<<<dim3(ceil_div(nver, kRasterThreads), batch), kRasterThreads, 0, st>>>(vertex, snap, nver, width, height);
+    FR_LAUNCHED("raster_snap_kernel");
     const unsigned gx = (unsigned)ceil_div(ntri, kRasterThreads);
-    if (batch >= 4)
-      raster_keys_kernel<4><<<dim3(gx, ceil_div(batch, 4)), kRasterThreads, 0, st>>>(vertex, tri, keys, batch, nver, ntri, height, width);
-    else if (batch >= 2)
-      raster_keys_kernel<2><<<dim3(gx, ceil_div(batch, 2)), kRasterThreads, 0, st>>>(vertex, tri, keys, batch, nver, ntri, height, width);
+    if (batch >= 8)
+      raster_keys_kernel<8><<<dim3(gx, ceil_div(batch, 8)), kRasterThreads, 0, st>>>(vertex, snap, tri, keys, batch, nver, ntri, height, width);
+    else if (batch >= 3)
+      raster_keys_kernel<4><<<dim3(gx, ceil_div(batch, 4)), kRasterThreads, 0, st>>>(vertex, snap, tri, keys, batch, nver, ntri, height, width);
     else
-      raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(vertex, tri, keys, batch, nver, ntri, height, width);
+      raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(vertex, snap, tri, keys, batch, nver, ntri, height, width);
     FR_LAUNCHED("raster_keys_kernel");
   }
   if (texture_image != nullptr || normal != nullptr)
@@ -231,7 +237,7 @@ int fr_render_depth_backward(const float* depth_grad, const float* tri, const fl
              "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
   FR_REQUIRE((long long)height * width < (1ll << 31), "image too large");
   if (batch == 0) return FR_OK;
-  FR_REQUIRE(depth_grad && tri && tri_ind && vertex_grad, "null pointer argument");
+  FR_REQUIRE(depth_grad && (tri || ntri == 0) && tri_ind && vertex_grad, "null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int npix = height * width;
   FR_CUDA(cudaMemsetAsync(vertex_grad, 0, sizeof(float) * (size_t)batch * 3 * nver, st));
@@ -243,7 +249,7 @@ int fr_render_depth_backward(const float* depth_grad, const float* tri, const fl
 
 // ------------------------------------------------------------------------------------------------ fused
 size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width) {
-  return fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp) + fr_render_workspace_bytes(batch, height, width);
+  return fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp) + fr_render_workspace_bytes(batch, nver, height, width);
 }
 
 int fr_recon_render_forward(const float* params, const float* packed, const float* tri, float* vertex_proj, float* depth,
@@ -251,7 +257,7 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
                             int width, float im_size, unsigned flags, void* workspace, size_t workspace_bytes,
                             void* stream) {
   const size_t rb = fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp);
-  const size_t need = rb + fr_render_workspace_bytes(batch, height, width);
+  const size_t need = rb + fr_render_workspace_bytes(batch, nver, height, width);
   if (batch > 0) {
     if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
   }

@@ -2,11 +2,13 @@
 //
 // Replaces the reference's CUDA op (render_depth_op.cu.cc:35-381, four kernels + 13 doubles of scratch
 // per triangle per face) and reproduces its CPU op (render_depth_op.cc:132-368) bit for bit:
-//   1. raster_keys_kernel    one thread per (triangle, face group): bbox + cull + FP64 inside test,
+//   0. raster_snap_kernel    one thread per (vertex, face): biased ceil/floor pixel coordinates, 8 bytes.
+//   1. raster_keys_kernel    one thread per (triangle, face group): exact integer bbox cull on the snapped
+//                            vertices, survivors compacted in shared memory, then FP64 inside tests;
 //                            visibility resolved with a packed (depth, ~index) u64 atomicMax -- order
 //                            independent, so no race (the reference's kernel 3 has one, .cu.cc:217-231).
-//   2. raster_resolve_kernel one thread per pixel: decode the winning triangle and recompute its depth,
-//                            normal and mean texture from the vertices (no per-triangle scratch).
+//   2. raster_resolve_kernel one thread per pixel: depth and index decoded from the key; normal and mean
+//                            texture recomputed from the winner's vertices (no per-triangle scratch).
 //   3. render_backward_kernel one thread per pixel: (g*1.0f)/3.0f to the z of the triangle's 3 vertices,
 //                            warp-aggregated when lanes share a triangle.
 #ifndef FR_RASTER_CUH_
@@ -27,23 +29,33 @@ __device__ __forceinline__ bool tri_vertex_index(float f, int nver, int* out) {
   return true;
 }
 
-// Phase A: one thread per (triangle, FPT faces): gather xy, exact bounding-box cull in float arithmetic
-// (fr_tri_bbox_fast).  ~70 % of the sub-pixel BFM triangles contain no pixel centre and stop here; the survivors are
-// compacted into a shared-memory queue so that
-// Phase B runs the FP64 edge setup + inside tests + atomicMax with every lane busy.
+// Snap every vertex of every face to its biased ceil/floor pixel coordinates once (raster_core.h "per-vertex pixel
+// snapping"): 8 bytes per vertex replace the 6 float gathers + min/max/ceil/floor per (triangle, face) of the cull.
+__global__ void __launch_bounds__(kRasterThreads)
+raster_snap_kernel(const float* __restrict__ vertex, uint2* __restrict__ snap, int nver, int width, int height) {
+  const int n = blockIdx.x * kRasterThreads + threadIdx.x;
+  if (n >= nver) return;
+  const int b = blockIdx.y;
+  const float* vx = vertex + (size_t)b * 3 * nver;
+  const FrSnap s = fr_snap_vertex(__ldg(vx + n), __ldg(vx + nver + n), width, height);
+  snap[(size_t)b * nver + n] = make_uint2(s.lo, s.hi);
+}
+
+// Phase A: one thread per (triangle, FPT faces): three 8-byte gathers of snapped vertices and a handful of packed
+// integer ops decide the reference's bounding-box cull exactly.  ~70 % of the sub-pixel BFM triangles contain no
+// pixel centre and stop here; the survivors are compacted into a shared-memory queue so that
+// Phase B gathers the float vertices and runs the FP64 edge setup + inside tests + atomicMax with every lane busy.
 template <int FPT>
 __global__ void __launch_bounds__(kRasterThreads)
-raster_keys_kernel(const float* __restrict__ vertex, const float* __restrict__ tri, unsigned long long* __restrict__ keys,
-                   int batch, int nver, int ntri, int height, int width) {
-  __shared__ float4 q_a[kRasterThreads * FPT];      // x1 y1 x2 y2
-  __shared__ float2 q_b[kRasterThreads * FPT];      // x3 y3
-  __shared__ unsigned short q_id[kRasterThreads * FPT];  // (local triangle << 3) | face slot
+raster_keys_kernel(const float* __restrict__ vertex, const uint2* __restrict__ snap, const float* __restrict__ tri,
+                   unsigned long long* __restrict__ keys, int batch, int nver, int ntri, int height, int width) {
+  __shared__ uint2 q_box[kRasterThreads * FPT];           // biased bbox (lo_min, hi_max)
+  __shared__ unsigned short q_id[kRasterThreads * FPT];   // (local triangle << 3) | face slot
   __shared__ int s_idx[3][kRasterThreads];
   __shared__ int q_count;
   static_assert(FPT <= 8, "face slot is packed into 3 bits");
 
   const int tid = threadIdx.x;
-  const unsigned lane = tid & 31u;
   if (tid == 0) q_count = 0;
   __syncthreads();
 
@@ -58,34 +70,34 @@ raster_keys_kernel(const float* __restrict__ vertex, const float* __restrict__ t
   s_idx[1][tid] = p2;
   s_idx[2][tid] = p3;
 
-  float x1[FPT], y1[FPT], x2[FPT], y2[FPT], x3[FPT], y3[FPT];
+  const uint32_t limit = (uint32_t)width | ((uint32_t)height << 16);
+  uint2 sa[FPT], sb[FPT], sc[FPT];
 #pragma unroll
   for (int f = 0; f < FPT; ++f) {  // all gathers in flight before the first use
-    const int b = min(b0 + f, batch - 1);
-    const float* vx = vertex + (size_t)b * 3 * nver;
-    const float* vy = vx + nver;
-    x1[f] = __ldg(vx + p1);
-    x2[f] = __ldg(vx + p2);
-    x3[f] = __ldg(vx + p3);
-    y1[f] = __ldg(vy + p1);
-    y2[f] = __ldg(vy + p2);
-    y3[f] = __ldg(vy + p3);
+    const uint2* sp = snap + (size_t)min(b0 + f, batch - 1) * nver;
+    sa[f] = __ldg(sp + p1);
+    sb[f] = __ldg(sp + p2);
+    sc[f] = __ldg(sp + p3);
   }
+  uint2 box[FPT];
+  unsigned keepmask = 0u;
 #pragma unroll
   for (int f = 0; f < FPT; ++f) {
-    FrBBox bb;
-    const bool keep = valid && (b0 + f < batch) &&
-                      fr_tri_bbox_fast(x1[f], y1[f], x2[f], y2[f], x3[f], y3[f], width, height, &bb);
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-    if (m != 0u) {
-      int base = 0;
-      if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&q_count, __popc(m));
-      base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-      if (keep) {
-        const int pos = base + __popc(m & ((1u << lane) - 1u));
-        q_a[pos] = make_float4(x1[f], y1[f], x2[f], y2[f]);
-        q_b[pos] = make_float2(x3[f], y3[f]);
+    FrSnap a, b, c;
+    a.lo = sa[f].x; a.hi = sa[f].y;
+    b.lo = sb[f].x; b.hi = sb[f].y;
+    c.lo = sc[f].x; c.hi = sc[f].y;
+    const bool keep = fr_snap_keep(a, b, c, limit, &box[f].x, &box[f].y) && valid && (b0 + f < batch);
+    keepmask |= (keep ? 1u : 0u) << f;
+  }
+  if (keepmask != 0u) {
+    int pos = atomicAdd(&q_count, __popc(keepmask));
+#pragma unroll
+    for (int f = 0; f < FPT; ++f) {
+      if ((keepmask >> f) & 1u) {
+        q_box[pos] = box[f];
         q_id[pos] = (unsigned short)((tid << 3) | f);
+        ++pos;
       }
     }
   }
@@ -94,18 +106,22 @@ raster_keys_kernel(const float* __restrict__ vertex, const float* __restrict__ t
   const int n = q_count;
   const size_t npix = (size_t)height * width;
   for (int i = tid; i < n; i += kRasterThreads) {
-    const float4 a = q_a[i];
-    const float2 c = q_b[i];
+    const uint2 bx = q_box[i];
     const int id = q_id[i];
     const int tl = id >> 3;
     const int b = b0 + (id & 7);
-    const float* vz = vertex + ((size_t)b * 3 + 2) * nver;
-    const float h = fr_tri_depth(__ldg(vz + s_idx[0][tl]), __ldg(vz + s_idx[1][tl]), __ldg(vz + s_idx[2][tl]));
+    const int i1 = s_idx[0][tl], i2 = s_idx[1][tl], i3 = s_idx[2][tl];
+    const float* vx = vertex + (size_t)b * 3 * nver;
+    const float* vy = vx + nver;
+    const float* vz = vy + nver;
+    const float x1 = __ldg(vx + i1), x2 = __ldg(vx + i2), x3 = __ldg(vx + i3);
+    const float y1 = __ldg(vy + i1), y2 = __ldg(vy + i2), y3 = __ldg(vy + i3);
+    const float h = fr_tri_depth(__ldg(vz + i1), __ldg(vz + i2), __ldg(vz + i3));
     if (!fr_depth_draws(h)) continue;
     FrBBox bb;
-    fr_tri_bbox_fast(a.x, a.y, a.z, a.w, c.x, c.y, width, height, &bb);
+    fr_snap_bbox(bx.x, bx.y, &bb);
     FrTriEdge e;
-    fr_tri_edge_setup(a.x, a.y, a.z, a.w, c.x, c.y, &e);
+    fr_tri_edge_setup(x1, y1, x2, y2, x3, y3, &e);
     const unsigned long long key = fr_pack_key(h, blockIdx.x * kRasterThreads + tl);
     unsigned long long* kb = keys + (size_t)b * npix;
     for (int y = bb.y_min; y <= bb.y_max; ++y)

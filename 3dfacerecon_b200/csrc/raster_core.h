@@ -177,4 +177,77 @@ FR_HD bool fr_tri_bbox_fast(float x1, float y1, float x2, float y2, float x3, fl
   return true;
 }
 
+// ---- per-vertex pixel snapping -------------------------------------------------------------------
+// ceil() and floor() are monotone, so the reference's integer bounding box (:276-280) can be formed from per-vertex
+// values: x_min = min_i ceil(x_i), x_max = max_i floor(x_i).  A vertex is snapped ONCE per face to four small
+// integers, biased by +1 and clamped to [0, W+1] (resp. H+1), packed as 16-bit fields:
+//   lo = ceil-biased  (x | y << 16),   hi = floor-biased (x | y << 16)
+// The clamp keeps the cull decision (:282) exact: a clamped value only occurs when some x_i <= -1 or x_i >= W, and
+// then the triangle is culled either way.  A NaN coordinate snaps to ceil-biased 0, which forces the cull -- the
+// reference never draws such a triangle either (every PointInTri comparison with NaN is false).
+struct FrSnap {
+  uint32_t lo, hi;
+};
+
+FR_HD uint32_t fr_snap_axis(float v, int extent, bool want_ceil) {
+  float r = want_ceil ? ceilf(v) : floorf(v);
+  r = fminf(fmaxf(r, -1.0f), (float)extent);  // NaN -> -1
+  if (v != v) r = -1.0f;
+  return (uint32_t)((int)r + 1);
+}
+
+FR_HD FrSnap fr_snap_vertex(float x, float y, int width, int height) {
+  FrSnap s;
+  s.lo = fr_snap_axis(x, width, true) | (fr_snap_axis(y, height, true) << 16);
+  s.hi = fr_snap_axis(x, width, false) | (fr_snap_axis(y, height, false) << 16);
+  return s;
+}
+
+FR_HD uint32_t fr_min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __vminu2(__vminu2(a, b), c);
+#else
+  uint32_t l = a & 0xFFFFu, h = a >> 16;
+  if ((b & 0xFFFFu) < l) l = b & 0xFFFFu;
+  if ((c & 0xFFFFu) < l) l = c & 0xFFFFu;
+  if ((b >> 16) < h) h = b >> 16;
+  if ((c >> 16) < h) h = c >> 16;
+  return l | (h << 16);
+#endif
+}
+FR_HD uint32_t fr_max3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __vmaxu2(__vmaxu2(a, b), c);
+#else
+  uint32_t l = a & 0xFFFFu, h = a >> 16;
+  if ((b & 0xFFFFu) > l) l = b & 0xFFFFu;
+  if ((c & 0xFFFFu) > l) l = c & 0xFFFFu;
+  if ((b >> 16) > h) h = b >> 16;
+  if ((c >> 16) > h) h = c >> 16;
+  return l | (h << 16);
+#endif
+}
+
+// Cull test on snapped vertices; `limit` = width | height << 16.  On success *lo_min / *hi_max hold the biased
+// bounding box (x_min+1 | y_min+1 << 16, x_max+1 | y_max+1 << 16).  Fields are < 2^15, so bit 15 / 31 serve as
+// borrow guards: (a | G) - b keeps its guard bit iff a >= b, field by field, in one 32-bit subtraction.
+FR_HD bool fr_snap_keep(FrSnap a, FrSnap b, FrSnap c, uint32_t limit, uint32_t* lo_min, uint32_t* hi_max) {
+  const uint32_t G = 0x80008000u;
+  const uint32_t lo = fr_min3_u16x2(a.lo, b.lo, c.lo);
+  const uint32_t hi = fr_max3_u16x2(a.hi, b.hi, c.hi);
+  const uint32_t nonempty = (hi | G) - lo;          // x_max >= x_min, y_max >= y_min
+  const uint32_t inside_lo = (lo | G) - 0x00010001u; // x_min >= 0, y_min >= 0   (biased >= 1)
+  const uint32_t inside_hi = (limit | G) - hi;       // x_max <= W-1, y_max <= H-1 (biased <= W)
+  *lo_min = lo;
+  *hi_max = hi;
+  return (nonempty & inside_lo & inside_hi & G) == G;
+}
+
+FR_HD void fr_snap_bbox(uint32_t lo_min, uint32_t hi_max, FrBBox* bb) {
+  bb->x_min = (int)(lo_min & 0xFFFFu) - 1;
+  bb->y_min = (int)(lo_min >> 16) - 1;
+  bb->x_max = (int)(hi_max & 0xFFFFu) - 1;
+  bb->y_max = (int)(hi_max >> 16) - 1;
+}
+
 #endif  // FR_RASTER_CORE_H_

@@ -1,14 +1,369 @@
-// Tensor-core (tcgen05 / TMEM, 3xTF32) flavour of the reconstruction forward pass.  Placeholder until the
-// kernel lands: the dispatcher never selects it.
+// Tensor-core flavour of the reconstruction + projection forward pass: tcgen05 (5th-gen tensor cores) with TMEM
+// accumulators, 3xTF32 operand splitting for fp32-level accuracy, bulk-async (TMA engine) streaming of the basis.
+//
+//   V[b, (c,n)] = sum_k P[(c,n), k] * coef[b, k]        M = 128 vertices per tile (x3 coordinates), N = 64 faces, K = kpad
+//
+// Per CTA (persistent, one per SM, 14 warps):
+//   warp 12  producer   cp.async.bulk of 8 KB basis chunks (16 k-columns x 128 rows, contiguous in the packed layout)
+//                       into an 8-stage shared-memory ring, completion on mbarriers
+//   warps 0-7 converter two groups of 4 warps alternate chunks: shared memory -> registers, split every fp32 value into
+//                       hi = top 19 bits (exact tf32) and lo = x - hi, tcgen05.st both into a 4-stage TMEM ring as the
+//                       A operand (the basis never needs a second pass through shared memory)
+//   warp 13  MMA issuer one thread: per k8 step  D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (tcgen05.mma kind::tf32, A from
+//                       TMEM, B = pre-split coefficients resident in shared memory in the canonical K-major layout)
+//   warps 8-11 epilogue tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices), (f.R).v + t, y flip,
+//                       coalesced stores of vertex_proj; double-buffered against the next tile's MMAs
+// The hi/lo split follows the 3xTF32 scheme (drop lo.lo): relative error ~2^-21 per product instead of 2^-11.
 #ifndef FR_RECON_TC_CUH_
 #define FR_RECON_TC_CUH_
+
+#include <cstdlib>
+
 #include "fr_common.cuh"
+#include "recon.cuh"
+
 namespace fr {
-inline size_t recon_tc_workspace_bytes(int, const BasisGeom&) { return 0; }
-inline bool recon_tc_applicable(int, const BasisGeom&, unsigned) { return false; }
-inline int launch_recon_fwd_tc(const float*, const float*, const float*, void*, float*, int, int, const BasisGeom&, float,
-                               unsigned, int, cudaStream_t) {
-  return fail(FR_ERR_UNSUPPORTED, "tensor-core reconstruction path not built");
+namespace tc {
+
+constexpr int kN = 64;               // faces per batch tile (MMA N)
+constexpr int kChunkGroups = 4;      // float4 k-groups per chunk  -> 16 k columns, 8 KB of basis
+constexpr int kChunkK = kChunkGroups * 4;
+constexpr int kRawStages = 8;        // shared-memory ring (8 x 8 KB)
+constexpr int kAStages = 4;          // TMEM ring of split A chunks (4 x 32 columns)
+constexpr int kDCols = 3 * kN;       // one accumulator set: x, y, z
+constexpr int kACol0 = 2 * kDCols;   // TMEM columns [0,384): two accumulator sets; [384,512): A ring
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 14 * 32;
+constexpr int kConvWarps = 8, kEpiWarp0 = 8, kProducerWarp = 12, kMmaWarp = 13;
+constexpr uint32_t kChunkBytes = kChunkGroups * kTileVerts * 16;
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), K-major A/B,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Barriers {
+  uint64_t raw_full[kRawStages];
+  uint64_t raw_empty[kRawStages];
+  uint64_t a_full[kAStages];
+  uint64_t a_empty[kAStages];
+  uint64_t d_full[2];
+  uint64_t d_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug traps (-> launch error the API reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem_d] (+)= A[tmem_a] . B[smem desc]   (A: 128 lanes x 8 columns of tf32 in TMEM)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(kIdesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, no swizzle: 8-row x 16-byte core matrices,
+// LBO = bytes between the two 16-byte K chunks of one k8 step, SBO = bytes between 8-row groups; version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory carve-up (dynamic, 128-byte aligned base)
+struct SmemLayout {
+  uint32_t b_hi, b_lo, raw, pose, bars, total;
+  uint32_t sbo;  // bytes between 8-face groups of the coefficient operand
+};
+__host__ __device__ inline SmemLayout smem_layout(int kg) {
+  SmemLayout L;
+  L.sbo = (uint32_t)kg * 128u;                       // kg core matrices (8 faces x 4 k) per 8-face group
+  const uint32_t bsz = (kN / 8) * L.sbo;
+  L.b_hi = 0;
+  L.b_lo = bsz;
+  L.raw = 2 * bsz;
+  L.pose = L.raw + kRawStages * kChunkBytes;
+  L.bars = L.pose + kN * kPoseStride * 4;
+  L.total = L.bars + (uint32_t)sizeof(Barriers);
+  return L;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+recon_fwd_tc_kernel(const float4* __restrict__ packed, const float* __restrict__ coefT, const float* __restrict__ pose,
+                    float* __restrict__ vertex_proj, int batch, int bpad, int nver, int kg, int ntiles, float im_size,
+                    unsigned flags) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout L = smem_layout(kg);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + L.bars);
+  float* s_pose = reinterpret_cast<float*>(smem + L.pose);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * kN;
+  const int kpad = kg * 4;
+  const int nchunks = (kg + kChunkGroups - 1) / kChunkGroups;
+
+  // ---- one-time setup: barriers, TMEM, resident B operand (split coefficients) and poses
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRawStages; ++i) {
+      mbar_init(&bars->raw_full[i], 1);
+      mbar_init(&bars->raw_empty[i], 4);       // one arrival per converter warp of the owning group
+    }
+    for (int i = 0; i < kAStages; ++i) {
+      mbar_init(&bars->a_full[i], 4);
+      mbar_init(&bars->a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->d_full[i], 1);
+      mbar_init(&bars->d_empty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < kpad * kN; i += kThreads) {
+    const int k = i / kN, n = i - k * kN;
+    const float c = coefT[(size_t)k * bpad + b0 + n];
+    const uint32_t hi = __float_as_uint(c) & 0xFFFFE000u;
+    const float lo = c - __uint_as_float(hi);
+    const uint32_t off = (uint32_t)(n >> 3) * L.sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
+    *reinterpret_cast<uint32_t*>(smem + L.b_hi + off) = hi;
+    *reinterpret_cast<float*>(smem + L.b_lo + off) = lo;
+  }
+  for (int i = threadIdx.x; i < kN * kPoseStride; i += kThreads) s_pose[i] = pose[(size_t)b0 * kPoseStride + i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA's async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == kProducerWarp) {
+    // ================================================================== producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int c = 0; c < 3; ++c) {
+          const float4* src = packed + ((size_t)(tile * 3 + c) * kg) * kTileVerts;
+          for (int ci = 0; ci < nchunks; ++ci, ++it) {
+            const uint32_t s = it % kRawStages, ph = (it / kRawStages) & 1u;
+            const int ng = min(kChunkGroups, kg - ci * kChunkGroups);
+            const uint32_t bytes = (uint32_t)ng * kTileVerts * 16u;
+            mbar_wait(&bars->raw_empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&bars->raw_full[s], bytes);
+            bulk_load(smem + L.raw + s * kChunkBytes, src + (size_t)ci * kChunkGroups * kTileVerts, bytes, &bars->raw_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const uint32_t dbuf = tcount & 1u, dph = (tcount >> 1) & 1u;
+        mbar_wait(&bars->d_empty[dbuf], dph ^ 1u);     // epilogue has drained this accumulator set
+        tc_fence_after();
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t d_addr = tmem + dbuf * kDCols + c * kN;
+          for (int ci = 0; ci < nchunks; ++ci, ++it) {
+            const uint32_t as = it % kAStages, aph = (it / kAStages) & 1u;
+            const int nk8 = min(kChunkGroups, kg - ci * kChunkGroups) / 2;
+            mbar_wait(&bars->a_full[as], aph);
+            tc_fence_after();
+            const uint32_t a_hi = tmem + kACol0 + as * (2 * kChunkK);
+            const uint32_t a_lo = a_hi + kChunkK;
+            for (int j = 0; j < nk8; ++j) {
+              const uint32_t kk = (uint32_t)(ci * (kChunkGroups / 2) + j);          // global k8 step
+              const uint64_t dhi = make_b_desc(smem_u32(smem + L.b_hi) + kk * 256u, 128u, L.sbo);
+              const uint64_t dlo = make_b_desc(smem_u32(smem + L.b_lo) + kk * 256u, 128u, L.sbo);
+              mma_tf32_ts(d_addr, a_lo + 8 * j, dhi, (ci | j) != 0);
+              mma_tf32_ts(d_addr, a_hi + 8 * j, dlo, true);
+              mma_tf32_ts(d_addr, a_hi + 8 * j, dhi, true);
+            }
+            tc_commit(&bars->a_empty[as]);               // A stage reusable once these MMAs have read it
+          }
+        }
+        tc_commit(&bars->d_full[dbuf]);                  // all three accumulators of this tile are complete
+      }
+    }
+  } else if (warp < kConvWarps) {
+    // ================================================================== converters (two groups alternate chunks)
+    const int group = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;                       // TMEM lane == vertex row of the tile
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int c = 0; c < 3; ++c) {
+        for (int ci = 0; ci < nchunks; ++ci, ++it) {
+          if ((int)(it & 1u) != group) continue;
+          const uint32_t s = it % kRawStages, ph = (it / kRawStages) & 1u;
+          const uint32_t as = it % kAStages, aph = (it / kAStages) & 1u;
+          const int ng = min(kChunkGroups, kg - ci * kChunkGroups);
+          mbar_wait(&bars->raw_full[s], ph);
+          const float4* src = reinterpret_cast<const float4*>(smem + L.raw + s * kChunkBytes) + row;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int g = 0; g < kChunkGroups; ++g) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g < ng) v = src[g * kTileVerts];
+            const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+              hi[4 * g + e] = h;
+              lo[4 * g + e] = __float_as_uint(f[e] - __uint_as_float(h));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->raw_empty[s]);        // this warp's rows are in registers
+          mbar_wait(&bars->a_empty[as], aph ^ 1u);                // MMAs that read this TMEM stage have retired
+          tc_fence_after();
+          const uint32_t a_addr = tmem + lane_field + kACol0 + as * (2 * kChunkK);
+          tmem_st16(a_addr, hi);
+          tmem_st16(a_addr + kChunkK, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->a_full[as]);
+        }
+      }
+    }
+  } else {
+    // ================================================================== epilogue (warps 8..11)
+    const int q = warp - kEpiWarp0;                               // TMEM lane quarter == warp % 4
+    const int v = q * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const uint32_t dbuf = tcount & 1u, dph = (tcount >> 1) & 1u;
+      const int n = tile * kTileVerts + v;
+      mbar_wait(&bars->d_full[dbuf], dph);
+      tc_fence_after();
+      const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
+#pragma unroll 1
+      for (int jb = 0; jb < kN; jb += 16) {
+        float x[16], y[16], z[16];
+        tmem_ld16(d_addr + 0 * kN + jb, x);
+        tmem_ld16(d_addr + 1 * kN + jb, y);
+        tmem_ld16(d_addr + 2 * kN + jb, z);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n < nver) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int b = b0 + jb + j;
+            if (b < batch)
+              project_store(s_pose + (jb + j) * kPoseStride, x[j], y[j], z[j], im_size, flags,
+                            vertex_proj + (size_t)b * 3 * nver, (size_t)nver, (size_t)n);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+  }
+}
+
+}  // namespace tc
+
+inline size_t recon_tc_workspace_bytes(int, const BasisGeom&) { return 0; }
+
+// FR_RECON_PATH=simt|tc overrides the dispatch (debugging / A-B comparisons); default: tensor cores above 8 faces.
+inline int recon_path_override() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = std::getenv("FR_RECON_PATH");
+    cached = (e == nullptr) ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0));
+  }
+  return cached;
+}
+
+inline bool recon_tc_applicable(int batch, const BasisGeom& g, unsigned) {
+  const int ov = recon_path_override();
+  if (ov == 1) return false;
+  const tc::SmemLayout L = tc::smem_layout(g.kg);
+  if (L.total > 227u * 1024u) return false;          // K too large for a resident coefficient operand
+  if (ov == 2) return true;
+  return batch > 8;
+}
+
+inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const float* pose, void*, float* vertex_proj,
+                               int batch, int nver, const BasisGeom& g, float im_size, unsigned flags, int nsm,
+                               cudaStream_t st) {
+  const tc::SmemLayout L = tc::smem_layout(g.kg);
+  FR_CUDA(cudaFuncSetAttribute(tc::recon_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const int nbt = ceil_div(batch, tc::kN);
+  int ctas = nsm / nbt;
+  if (ctas < 1) ctas = 1;
+  if (ctas > g.ntiles) ctas = g.ntiles;
+  tc::recon_fwd_tc_kernel<<<dim3(ctas, nbt), tc::kThreads, L.total, st>>>(
+      reinterpret_cast<const float4*>(packed), coefT, pose, vertex_proj, batch, batch_padded(batch), nver, g.kg, g.ntiles,
+      im_size, flags);
+  FR_LAUNCHED("recon_fwd_tc_kernel");
+  return FR_OK;
+}
+
 }  // namespace fr
-#endif
+#endif  // FR_RECON_TC_CUH_

@@ -87,7 +87,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
  * Outputs: depth [batch,H,W,1], texture_image [batch,H,W,3], normal [batch,H,W,3], tri_ind [batch,H,W,1]
  * (float, -1 = background).  texture_image and normal may be NULL to skip them (texture may then be NULL).
  * Triangles whose indices fall outside [0,nver) are skipped (the reference reads out of bounds). */
-size_t fr_render_workspace_bytes(int batch, int height, int width);
+size_t fr_render_workspace_bytes(int batch, int nver, int height, int width);
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                             float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
                             int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream);

@@ -37,8 +37,33 @@ extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, con
       const bool keep_ref = fr_tri_bbox(vx[p1], vy[p1], vx[p2], vy[p2], vx[p3], vy[p3], width, height, &bb_ref);
       const bool keep = fr_tri_bbox_fast(vx[p1], vy[p1], vx[p2], vy[p2], vx[p3], vy[p3], width, height, &bb);
       if (keep != keep_ref) return 100;  // the float fast path must agree with the literal path
+      if (keep && (bb.x_min != bb_ref.x_min || bb.x_max != bb_ref.x_max || bb.y_min != bb_ref.y_min || bb.y_max != bb_ref.y_max)) return 101;
+      {  // the per-vertex snapped cull (what raster_keys_kernel runs) must agree as well, except that a triangle with a
+         // NaN coordinate may be culled early: it can never pass the inside test
+        const uint32_t limit = (uint32_t)width | ((uint32_t)height << 16);
+        uint32_t lo_min, hi_max;
+        const bool keep_snap = fr_snap_keep(fr_snap_vertex(vx[p1], vy[p1], width, height), fr_snap_vertex(vx[p2], vy[p2], width, height),
+                                            fr_snap_vertex(vx[p3], vy[p3], width, height), limit, &lo_min, &hi_max);
+        const bool has_nan = vx[p1] != vx[p1] || vx[p2] != vx[p2] || vx[p3] != vx[p3] || vy[p1] != vy[p1] || vy[p2] != vy[p2] || vy[p3] != vy[p3];
+        if (has_nan) {
+          if (keep_snap) return 103;
+          if (keep_ref) {  // literal path kept it: make sure it really draws nothing
+            FrTriEdge en;
+            fr_tri_edge_setup(vx[p1], vy[p1], vx[p2], vy[p2], vx[p3], vy[p3], &en);
+            for (int y = bb_ref.y_min; y <= bb_ref.y_max; ++y)
+              for (int x = bb_ref.x_min; x <= bb_ref.x_max; ++x)
+                if (fr_point_in_tri(&en, x, y)) return 104;
+          }
+          continue;
+        }
+        if (keep_snap != keep_ref) return 105;
+        if (keep_snap) {
+          FrBBox bs;
+          fr_snap_bbox(lo_min, hi_max, &bs);
+          if (bs.x_min != bb_ref.x_min || bs.x_max != bb_ref.x_max || bs.y_min != bb_ref.y_min || bs.y_max != bb_ref.y_max) return 106;
+        }
+      }
       if (!keep) continue;
-      if (bb.x_min != bb_ref.x_min || bb.x_max != bb_ref.x_max || bb.y_min != bb_ref.y_min || bb.y_max != bb_ref.y_max) return 101;
       const float h = fr_tri_depth(vz[p1], vz[p2], vz[p3]);
       if (!fr_depth_draws(h)) continue;
       FrTriEdge e;
