@@ -91,6 +91,16 @@ const char* fr_last_error(void) { return error_buffer(); }
 int fr_version(void) { return FR_VERSION; }
 unsigned long long fr_launch_count(void) { return launch_counter().load(); }
 
+// developer diagnostics (not part of the public header): per-role cycle counters of the tensor-core kernel's block 0
+int fr_debug_tc_counters(unsigned long long* out32, int reset) {
+  if (out32 && cudaMemcpyFromSymbol(out32, fr::tc::g_tc_dbg, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[32] = {0};
+    if (cudaMemcpyToSymbol(fr::tc::g_tc_dbg, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ packing
 size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp) {
   if (nver <= 0 || ndim_shape < 0 || ndim_exp < 0) return 0;

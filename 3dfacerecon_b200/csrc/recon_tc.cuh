@@ -4,11 +4,11 @@
 //   V[b, (c,n)] = sum_k P[(c,n), k] * coef[b, k]        M = 128 vertices per tile (x3 coordinates), N = 64 faces, K = kpad
 //
 // Per CTA (persistent, one per SM, 14 warps):
-//   warp 12  producer   cp.async.bulk of 8 KB basis chunks (16 k-columns x 128 rows, contiguous in the packed layout)
-//                       into an 8-stage shared-memory ring, completion on mbarriers
+//   warp 12  producer   cp.async.bulk (TMA engine): the resident B operand (pre-split coefficients of this batch tile) once,
+//                       then 8 KB basis chunks (16 k-columns x 128 rows, contiguous in the packed layout) into an
+//                       8-stage shared-memory ring, completion on mbarriers
 //   warps 0-7 converter two groups of 4 warps alternate chunks: shared memory -> registers, split every fp32 value into
-//                       hi = top 19 bits (exact tf32) and lo = x - hi, tcgen05.st both into a 4-stage TMEM ring as the
-//                       A operand (the basis never needs a second pass through shared memory)
+//                       hi = top 19 bits (exact tf32) and lo = x - hi, tcgen05.st both into a TMEM ring as the A operand
 //   warp 13  MMA issuer one thread: per k8 step  D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (tcgen05.mma kind::tf32, A from
 //                       TMEM, B = pre-split coefficients resident in shared memory in the canonical K-major layout)
 //   warps 8-11 epilogue tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices), (f.R).v + t, y flip,
@@ -28,11 +28,10 @@ namespace tc {
 constexpr int kN = 64;               // faces per batch tile (MMA N)
 constexpr int kChunkGroups = 4;      // float4 k-groups per chunk  -> 16 k columns, 8 KB of basis
 constexpr int kChunkK = kChunkGroups * 4;
-constexpr int kRawStages = 8;        // shared-memory ring (8 x 8 KB)
-constexpr int kAStages = 4;          // TMEM ring of split A chunks (4 x 32 columns)
+constexpr int kRawStages = 8;        // shared-memory ring of raw basis chunks (8 x 8 KB)
 constexpr int kDCols = 3 * kN;       // one accumulator set: x, y, z
-constexpr int kACol0 = 2 * kDCols;   // TMEM columns [0,384): two accumulator sets; [384,512): A ring
-constexpr int kTmemCols = 512;
+constexpr int kTmemCols = 512;       // [0, DBUFS*192): accumulator sets; the rest: ring of split A chunks (32 columns each)
+constexpr int kMaxAStages = 10;
 constexpr int kThreads = 14 * 32;
 constexpr int kConvWarps = 8, kEpiWarp0 = 8, kProducerWarp = 12, kMmaWarp = 13;
 constexpr uint32_t kChunkBytes = kChunkGroups * kTileVerts * 16;
@@ -44,13 +43,20 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN 
 struct Barriers {
   uint64_t raw_full[kRawStages];
   uint64_t raw_empty[kRawStages];
-  uint64_t a_full[kAStages];
-  uint64_t a_empty[kAStages];
+  uint64_t a_full[2];
+  uint64_t a_empty[2];
   uint64_t d_full[2];
   uint64_t d_empty[2];
+  uint64_t b_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
+
+// Optional per-role cycle accounting (developer diagnostics, FR_TC_DEBUG=1): [role][slot] accumulated clock64 deltas of
+// block 0.  role 0 = converter warp 0, 1 = MMA issuer, 2 = epilogue warp 8, 3 = producer.
+__device__ unsigned long long g_tc_dbg[4][8];
+#define TC_T(var) const long long var = dbg ? clock64() : 0
+#define TC_ACC(role, slot, t0, t1) do { if (dbg) g_tc_dbg[role][slot] += (unsigned long long)((t1) - (t0)); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +89,13 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// one lane of a fully converged warp (keeps tcgen05.mma / commit on the uniform datapath: a lane-0 branch makes the
+// compiler serialise every uniform-register operand through per-thread loops and triples the issue cost)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -140,33 +153,45 @@ __host__ __device__ inline SmemLayout smem_layout(int kg) {
   return L;
 }
 
+template <int DBUFS>
 __global__ void __launch_bounds__(kThreads, 1)
-recon_fwd_tc_kernel(const float4* __restrict__ packed, const float* __restrict__ coefT, const float* __restrict__ pose,
-                    float* __restrict__ vertex_proj, int batch, int bpad, int nver, int kg, int ntiles, float im_size,
-                    unsigned flags) {
+recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __restrict__ bsplit, const float* __restrict__ pose,
+                    float* __restrict__ vertex_proj, int batch, int nver, int kg, int ntiles, float im_size,
+                    unsigned flags, int debug) {
+  constexpr int kACol0 = DBUFS * kDCols;
+  constexpr int kAStages = (kTmemCols - kACol0) / (2 * kChunkK);
+  static_assert(kAStages % 2 == 0 && kAStages <= kMaxAStages, "the A ring is handed over in two halves");
+  // Hand-over granularity between the converters and the MMA issuer is HALF of the TMEM ring (kABatch chunks), in both
+  // directions.  Measured on B200 (tools/mma_bench2.cu): a satisfied mbarrier wait costs the issuing thread ~130 cycles
+  // and a tcgen05.commit ~200, while the six MMAs of one chunk execute in 192 cycles and the tensor pipe's queue is
+  // shallow -- per-chunk waits/commits leave the pipe idle most of the time.
+  constexpr int kABatch = kAStages / 2;
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemLayout L = smem_layout(kg);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + L.bars);
   float* s_pose = reinterpret_cast<float*>(smem + L.pose);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b0 = blockIdx.y * kN;
-  const int kpad = kg * 4;
   const int nchunks = (kg + kChunkGroups - 1) / kChunkGroups;
+  const uint32_t per_tile = 3u * (uint32_t)nchunks;
+  const uint32_t my_tiles = (blockIdx.x < (unsigned)ntiles) ? ((uint32_t)(ntiles - 1 - blockIdx.x) / gridDim.x + 1u) : 0u;
+  const uint32_t total = my_tiles * per_tile;                              // chunks this CTA processes
+  const uint32_t total_padded = (total + kABatch - 1) / kABatch * kABatch;
+  const bool dbg = debug != 0 && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0;
 
-  // ---- one-time setup: barriers, TMEM, resident B operand (split coefficients) and poses
+  // ---- one-time setup: barriers, TMEM, poses (the resident B operand arrives by bulk copy)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRawStages; ++i) {
       mbar_init(&bars->raw_full[i], 1);
       mbar_init(&bars->raw_empty[i], 4);       // one arrival per converter warp of the owning group
     }
-    for (int i = 0; i < kAStages; ++i) {
-      mbar_init(&bars->a_full[i], 4);
-      mbar_init(&bars->a_empty[i], 1);
-    }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a_full[i], 4 * kABatch);  // 4 converter warps per chunk
+      mbar_init(&bars->a_empty[i], 1);
       mbar_init(&bars->d_full[i], 1);
       mbar_init(&bars->d_empty[i], 4);
     }
+    mbar_init(&bars->b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kProducerWarp) {
@@ -175,25 +200,20 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const float* __restrict__
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < kpad * kN; i += kThreads) {
-    const int k = i / kN, n = i - k * kN;
-    const float c = coefT[(size_t)k * bpad + b0 + n];
-    const uint32_t hi = __float_as_uint(c) & 0xFFFFE000u;
-    const float lo = c - __uint_as_float(hi);
-    const uint32_t off = (uint32_t)(n >> 3) * L.sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
-    *reinterpret_cast<uint32_t*>(smem + L.b_hi + off) = hi;
-    *reinterpret_cast<float*>(smem + L.b_lo + off) = lo;
-  }
   for (int i = threadIdx.x; i < kN * kPoseStride; i += kThreads) s_pose[i] = pose[(size_t)b0 * kPoseStride + i];
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == kProducerWarp) {
-    // ================================================================== producer
+    // ================================================================== producer (TMA engine)
     if (lane == 0) {
+      // resident B operand: the pre-split coefficients of this batch tile, already in the canonical K-major layout
+      const uint32_t bbytes = 2u * (kN / 8) * L.sbo;
+      mbar_arrive_expect_tx(&bars->b_full, bbytes);
+      bulk_load(smem + L.b_hi, bsplit + (size_t)blockIdx.y * bbytes, bbytes / 2, &bars->b_full);
+      bulk_load(smem + L.b_lo, bsplit + (size_t)blockIdx.y * bbytes + bbytes / 2, bbytes / 2, &bars->b_full);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int c = 0; c < 3; ++c) {
@@ -210,88 +230,123 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const float* __restrict__
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        const uint32_t dbuf = tcount & 1u, dph = (tcount >> 1) & 1u;
-        mbar_wait(&bars->d_empty[dbuf], dph ^ 1u);     // epilogue has drained this accumulator set
-        tc_fence_after();
-        for (int c = 0; c < 3; ++c) {
-          const uint32_t d_addr = tmem + dbuf * kDCols + c * kN;
-          for (int ci = 0; ci < nchunks; ++ci, ++it) {
-            const uint32_t as = it % kAStages, aph = (it / kAStages) & 1u;
-            const int nk8 = min(kChunkGroups, kg - ci * kChunkGroups) / 2;
-            mbar_wait(&bars->a_full[as], aph);
+    // ================================================================== MMA issuer (whole warp converged, one elected lane issues)
+    mbar_wait(&bars->b_full, 0);
+    const uint64_t dhi0 = make_b_desc(smem_u32(smem + L.b_hi), 128u, L.sbo);
+    const uint64_t dlo0 = make_b_desc(smem_u32(smem + L.b_lo), 128u, L.sbo);
+    const int last_nk8 = (kg - (nchunks - 1) * kChunkGroups) / 2;
+    uint32_t it = 0, q = 0, c = 0, ci = 0, tcount = 0;
+    for (uint32_t bi = 0; bi * kABatch < total; ++bi) {
+      const uint32_t h = bi & 1u, ph = (bi >> 1) & 1u;
+      TC_T(t2);
+      mbar_wait(&bars->a_full[h], ph);                 // the converters have filled this half of the A ring
+      TC_T(t3);
+      TC_ACC(1, 1, t2, t3);
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < kABatch; ++s) {
+        if (it < total) {
+          const uint32_t dbuf = tcount % DBUFS;
+          if (q == 0) {
+            TC_T(t0);
+            mbar_wait(&bars->d_empty[dbuf], ((tcount / DBUFS) & 1u) ^ 1u);   // epilogue has drained this accumulator set
+            TC_T(t1);
+            TC_ACC(1, 0, t0, t1);
             tc_fence_after();
-            const uint32_t a_hi = tmem + kACol0 + as * (2 * kChunkK);
-            const uint32_t a_lo = a_hi + kChunkK;
-            for (int j = 0; j < nk8; ++j) {
-              const uint32_t kk = (uint32_t)(ci * (kChunkGroups / 2) + j);          // global k8 step
-              const uint64_t dhi = make_b_desc(smem_u32(smem + L.b_hi) + kk * 256u, 128u, L.sbo);
-              const uint64_t dlo = make_b_desc(smem_u32(smem + L.b_lo) + kk * 256u, 128u, L.sbo);
-              mma_tf32_ts(d_addr, a_lo + 8 * j, dhi, (ci | j) != 0);
-              mma_tf32_ts(d_addr, a_hi + 8 * j, dlo, true);
-              mma_tf32_ts(d_addr, a_hi + 8 * j, dhi, true);
-            }
-            tc_commit(&bars->a_empty[as]);               // A stage reusable once these MMAs have read it
           }
+          if (elect_one()) {
+            const uint32_t a_hi = tmem + kACol0 + (h * kABatch + s) * (2 * kChunkK);
+            const uint32_t a_lo = a_hi + kChunkK;
+            const uint32_t d_addr = tmem + dbuf * kDCols + c * kN;
+            const uint64_t koff = (uint64_t)ci * (kChunkGroups / 2) * 16u;   // 256 bytes per k8 step, in 16-byte units
+            const int nk8 = (ci == (uint32_t)nchunks - 1u) ? last_nk8 : kChunkGroups / 2;
+#pragma unroll
+            for (int j = 0; j < kChunkGroups / 2; ++j) {
+              if (j < nk8) {
+                const uint64_t dhi = dhi0 + koff + 16u * j, dlo = dlo0 + koff + 16u * j;
+                mma_tf32_ts(d_addr, a_lo + 8 * j, dhi, (ci | (uint32_t)j) != 0u);
+                mma_tf32_ts(d_addr, a_hi + 8 * j, dlo, true);
+                mma_tf32_ts(d_addr, a_hi + 8 * j, dhi, true);
+              }
+            }
+            if (s == kABatch - 1) tc_commit(&bars->a_empty[h]);             // this half of the A ring is reusable
+            if (q == per_tile - 1u) tc_commit(&bars->d_full[dbuf]);         // all three accumulators of the tile complete
+          }
+          __syncwarp();
+          ++it; ++q; ++ci;
+          if (ci == (uint32_t)nchunks) { ci = 0; ++c; }
+          if (q == per_tile) { q = 0; c = 0; ++tcount; }
         }
-        tc_commit(&bars->d_full[dbuf]);                  // all three accumulators of this tile are complete
       }
+      TC_T(t4);
+      TC_ACC(1, 2, t3, t4);
     }
   } else if (warp < kConvWarps) {
     // ================================================================== converters (two groups alternate chunks)
     const int group = warp >> 2;
     const int row = (warp & 3) * 32 + lane;                       // TMEM lane == vertex row of the tile
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int c = 0; c < 3; ++c) {
-        for (int ci = 0; ci < nchunks; ++ci, ++it) {
-          if ((int)(it & 1u) != group) continue;
-          const uint32_t s = it % kRawStages, ph = (it / kRawStages) & 1u;
-          const uint32_t as = it % kAStages, aph = (it / kAStages) & 1u;
-          const int ng = min(kChunkGroups, kg - ci * kChunkGroups);
-          mbar_wait(&bars->raw_full[s], ph);
-          const float4* src = reinterpret_cast<const float4*>(smem + L.raw + s * kChunkBytes) + row;
-          uint32_t hi[16], lo[16];
+    for (uint32_t it = (uint32_t)group; it < total_padded; it += 2u) {
+      const uint32_t as = it % kAStages, half = as / kABatch, aph = (it / kAStages) & 1u;
+      if (it >= total) {                                          // pad the last half-ring batch so the issuer's wait completes
+        mbar_wait(&bars->a_empty[half], aph ^ 1u);                // (in order: never ahead of the previous round's phase)
+        if (lane == 0) mbar_arrive(&bars->a_full[half]);
+        continue;
+      }
+      const uint32_t s = it % kRawStages, ph = (it / kRawStages) & 1u;
+      const uint32_t ci = (it % per_tile) % (uint32_t)nchunks;
+      const int ng = min(kChunkGroups, kg - (int)ci * kChunkGroups);
+      TC_T(c0);
+      mbar_wait(&bars->raw_full[s], ph);
+      TC_T(c1);
+      const float4* src = reinterpret_cast<const float4*>(smem + L.raw + s * kChunkBytes) + row;
+      uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int g = 0; g < kChunkGroups; ++g) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g < ng) v = src[g * kTileVerts];
-            const float f[4] = {v.x, v.y, v.z, v.w};
+      for (int g = 0; g < kChunkGroups; ++g) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < ng) v = src[g * kTileVerts];
+        const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
-              hi[4 * g + e] = h;
-              lo[4 * g + e] = __float_as_uint(f[e] - __uint_as_float(h));
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->raw_empty[s]);        // this warp's rows are in registers
-          mbar_wait(&bars->a_empty[as], aph ^ 1u);                // MMAs that read this TMEM stage have retired
-          tc_fence_after();
-          const uint32_t a_addr = tmem + lane_field + kACol0 + as * (2 * kChunkK);
-          tmem_st16(a_addr, hi);
-          tmem_st16(a_addr + kChunkK, lo);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->a_full[as]);
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t hbits = __float_as_uint(f[e]) & 0xFFFFE000u;
+          hi[4 * g + e] = hbits;
+          lo[4 * g + e] = __float_as_uint(f[e] - __uint_as_float(hbits));
         }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->raw_empty[s]);            // this warp's rows are in registers
+      TC_T(c2);
+      mbar_wait(&bars->a_empty[half], aph ^ 1u);                  // MMAs that read this half of the TMEM ring have retired
+      TC_T(c3);
+      tc_fence_after();
+      const uint32_t a_addr = tmem + lane_field + kACol0 + as * (2 * kChunkK);
+      tmem_st16(a_addr, hi);
+      tmem_st16(a_addr + kChunkK, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      TC_T(c4);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->a_full[half]);
+      if (warp == 0) {
+        TC_ACC(0, 0, c0, c1);   // wait raw_full
+        TC_ACC(0, 1, c1, c2);   // LDS + split
+        TC_ACC(0, 2, c2, c3);   // wait a_empty
+        TC_ACC(0, 3, c3, c4);   // STTM + wait::st
+        if (dbg) g_tc_dbg[0][7] += 1;
       }
     }
   } else {
     // ================================================================== epilogue (warps 8..11)
-    const int q = warp - kEpiWarp0;                               // TMEM lane quarter == warp % 4
-    const int v = q * 32 + lane;
-    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    const int qd = warp - kEpiWarp0;                              // TMEM lane quarter == warp % 4
+    const int v = qd * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(qd * 32) << 16;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-      const uint32_t dbuf = tcount & 1u, dph = (tcount >> 1) & 1u;
+      const uint32_t dbuf = tcount % DBUFS, dph = (tcount / DBUFS) & 1u;
       const int n = tile * kTileVerts + v;
+      TC_T(e0);
       mbar_wait(&bars->d_full[dbuf], dph);
+      TC_T(e1);
       tc_fence_after();
       const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
 #pragma unroll 1
@@ -305,15 +360,23 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const float* __restrict__
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int b = b0 + jb + j;
-            if (b < batch)
-              project_store(s_pose + (jb + j) * kPoseStride, x[j], y[j], z[j], im_size, flags,
-                            vertex_proj + (size_t)b * 3 * nver, (size_t)nver, (size_t)n);
+            if (b < batch) {
+              const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPoseStride);
+              const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+              const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+              project_store(P, x[j], y[j], z[j], im_size, flags, vertex_proj + (size_t)b * 3 * nver, (size_t)nver, (size_t)n);
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+      if (warp == kEpiWarp0) {
+        TC_T(e2);
+        TC_ACC(2, 0, e0, e1);   // wait d_full
+        TC_ACC(2, 1, e1, e2);   // drain + project + store
+      }
     }
   }
 
@@ -328,7 +391,33 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const float* __restrict__
 
 }  // namespace tc
 
-inline size_t recon_tc_workspace_bytes(int, const BasisGeom&) { return 0; }
+// split coefficients of every 64-face batch tile in the canonical layout: [tile][hi|lo][8 groups][kg][8 faces][4 k]
+inline size_t recon_tc_workspace_bytes(int batch, const BasisGeom& g) {
+  return (size_t)ceil_div(batch, tc::kN) * 2 * (tc::kN / 8) * (size_t)g.kg * 128;
+}
+
+// coefT [kpad][bpad] -> bsplit; element (face n, column k) of a tile lives at (n/8)*sbo + (k/4)*128 + (n%8)*16 + (k%4)*4
+__global__ void __launch_bounds__(256)
+recon_tc_split_kernel(const float* __restrict__ coefT, int bpad, int kpad, int kg, unsigned char* __restrict__ bsplit) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= kpad * bpad) return;
+  const int k = idx / bpad, b = idx - k * bpad;
+  const float c = coefT[idx];
+  const uint32_t hi = __float_as_uint(c) & 0xFFFFE000u;
+  const float lo = c - __uint_as_float(hi);
+  const uint32_t sbo = (uint32_t)kg * 128u;
+  const uint32_t half = (tc::kN / 8) * sbo;
+  const int n = b % tc::kN;
+  unsigned char* tile = bsplit + (size_t)(b / tc::kN) * 2 * half;
+  const uint32_t off = (uint32_t)(n >> 3) * sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
+  *reinterpret_cast<uint32_t*>(tile + off) = hi;
+  *reinterpret_cast<float*>(tile + half + off) = lo;
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
 
 // FR_RECON_PATH=simt|tc overrides the dispatch (debugging / A-B comparisons); default: tensor cores above 8 faces.
 inline int recon_path_override() {
@@ -349,21 +438,33 @@ inline bool recon_tc_applicable(int batch, const BasisGeom& g, unsigned) {
   return batch > 8;
 }
 
-inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const float* pose, void*, float* vertex_proj,
+inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const float* pose, void* tc_ws, float* vertex_proj,
                                int batch, int nver, const BasisGeom& g, float im_size, unsigned flags, int nsm,
                                cudaStream_t st) {
+  static const int dbufs = env_int("FR_TC_DBUFS", 2);
+  static const int debug = env_int("FR_TC_DEBUG", 0);
   const tc::SmemLayout L = tc::smem_layout(g.kg);
-  FR_CUDA(cudaFuncSetAttribute(tc::recon_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const int bpad = batch_padded(batch);
+  unsigned char* bsplit = static_cast<unsigned char*>(tc_ws);
+  recon_tc_split_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(coefT, bpad, g.kpad, g.kg, bsplit);
+  FR_LAUNCHED("recon_tc_split_kernel");
   const int nbt = ceil_div(batch, tc::kN);
   int ctas = nsm / nbt;
   if (ctas < 1) ctas = 1;
   if (ctas > g.ntiles) ctas = g.ntiles;
-  tc::recon_fwd_tc_kernel<<<dim3(ctas, nbt), tc::kThreads, L.total, st>>>(
-      reinterpret_cast<const float4*>(packed), coefT, pose, vertex_proj, batch, batch_padded(batch), nver, g.kg, g.ntiles,
-      im_size, flags);
+  if (dbufs == 1) {
+    FR_CUDA(cudaFuncSetAttribute(tc::recon_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    tc::recon_fwd_tc_kernel<1><<<dim3(ctas, nbt), tc::kThreads, L.total, st>>>(
+        reinterpret_cast<const float4*>(packed), bsplit, pose, vertex_proj, batch, nver, g.kg, g.ntiles, im_size, flags, debug);
+  } else {
+    FR_CUDA(cudaFuncSetAttribute(tc::recon_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    tc::recon_fwd_tc_kernel<2><<<dim3(ctas, nbt), tc::kThreads, L.total, st>>>(
+        reinterpret_cast<const float4*>(packed), bsplit, pose, vertex_proj, batch, nver, g.kg, g.ntiles, im_size, flags, debug);
+  }
   FR_LAUNCHED("recon_fwd_tc_kernel");
   return FR_OK;
 }
 
 }  // namespace fr
+
 #endif  // FR_RECON_TC_CUH_
