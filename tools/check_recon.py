@@ -65,3 +65,24 @@ if os.environ.get("FR_TC_DEBUG") == "1":
           % (nchunk, c[0, 0] / nchunk, c[0, 1] / nchunk, c[0, 2] / nchunk, c[0, 3] / nchunk, c[0, 4] / nchunk))
     print("mma thread per call: wait d_empty %.0f, wait a_full total %.0f, issue total %.0f" % (c[1, 0], c[1, 1], c[1, 2]))
     print("epilogue warp8 per call: wait d_full %.0f, drain %.0f" % (c[2, 0], c[2, 1]))
+
+if os.environ.get("FR_TC_DEBUG") in ("2", "3", "4"):
+    import ctypes
+    lib = fr._lib.lib()
+    p = synth.sample_params_constrained(64, seed=2)
+    pt = torch.from_numpy(p).cuda()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        flush.zero_()
+        net.recon_project(pt, dm, 200)
+    torch.cuda.synchronize()
+    tr = (ctypes.c_uint * (8 * 160))()
+    lib.fr_debug_tc_trace.argtypes = [ctypes.c_void_p]
+    lib.fr_debug_tc_trace(tr)
+    t = np.array(list(tr), dtype=np.int64).reshape(8, 160)
+    names = ["producer issue", "conv raw acquired", "conv a_empty acquired", "conv a_full arrived", "mma a_full acquired",
+             "mma issue done", "epi d_full acquired", "epi done"]
+    np.set_printoptions(linewidth=200)
+    for i, nme in enumerate(names):
+        n = 48 if i < 4 else (30 if i < 6 else 3)
+        print("%-24s" % nme, t[i, :n].tolist())
