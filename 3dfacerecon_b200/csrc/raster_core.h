@@ -73,11 +73,26 @@ FR_HD bool fr_tri_bbox(float x1, float y1, float x2, float y2, float x3, float y
   return true;
 }
 
+// IEEE x / 3.0f without the division sequence: q0 = x*c, q = fma(fma(-3,q0,x), c, q0) with c = RN(1/3) is the correctly
+// rounded quotient for every finite float (exhaustively verified over all 2^32 bit patterns, tools/div3_check.cu: the only
+// mismatches are +-inf, where the residual becomes NaN, and -0.0, which comes out as +0.0); zeros and huge / non-finite
+// inputs take the plain division.
+FR_HD float fr_div3(float x) {
+#if defined(__CUDA_ARCH__)
+  if (fabsf(x) < 1.0e30f && x != 0.0f) {                     // (-0.0 must stay -0.0: the residual trick turns it into +0.0)
+    const float c = 0.3333333432674407958984375f;
+    const float q0 = __fmul_rn(x, c);
+    return __fmaf_rn(__fmaf_rn(-3.0f, q0, x), c, q0);
+  }
+#endif
+  return FR_FDIV(x, 3.0f);
+}
+
 // Flat depth of a triangle (:217): float adds left to right, IEEE float divide by 3.0f.
-FR_HD float fr_tri_depth(float z1, float z2, float z3) { return FR_FDIV(FR_FADD(FR_FADD(z1, z2), z3), 3.0f); }
+FR_HD float fr_tri_depth(float z1, float z2, float z3) { return fr_div3(FR_FADD(FR_FADD(z1, z2), z3)); }
 
 // Mean of a per-vertex attribute (:223), same float arithmetic.
-FR_HD float fr_tri_mean(float a, float b, float c) { return FR_FDIV(FR_FADD(FR_FADD(a, b), c), 3.0f); }
+FR_HD float fr_tri_mean(float a, float b, float c) { return fr_div3(FR_FADD(FR_FADD(a, b), c)); }
 
 // Edge-function state of one triangle for PointInTri (:76-109): everything that does not depend on the pixel.
 struct FrTriEdge {

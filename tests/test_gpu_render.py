@@ -155,3 +155,30 @@ def test_full_batch_properties():
     for b in (0, 17, 63):
         want = oracle.oracle_render_depth_forward(vp[b:b + 1], m["tri"], m["vertex"], 200, 200)
         _assert_same([g[b:b + 1] for g in got], want, "face %d" % b)
+
+
+def test_unsure_queue_overflow():
+    """A large degenerate (collinear) triangle paints its whole bbox (render_depth_op.cc:105-109) and makes every pixel of it
+    'unsure' for the float pre-filter: > 1024 unsure pixels in one block overflow the deferred FP64 queue and exercise
+    the redo path of raster_keys_kernel; big slivers and pixel centres exactly on edges ride along."""
+    rng = np.random.default_rng(7)
+    nv = 40
+    v = np.empty((9, 3, nv), np.float32)                       # 9 faces: exercises the 8-faces-per-thread grouping + a tail
+    v[:, 0] = rng.uniform(2, 60, (9, nv))
+    v[:, 1] = rng.uniform(2, 60, (9, nv))
+    v[:, 2] = rng.uniform(-1, 1, (9, nv))
+    v[:, 0:2, 0] = [3.0, 3.0]
+    v[:, 0:2, 1] = [58.0, 58.0]
+    v[:, 0:2, 2] = [30.0, 30.0]                                 # collinear with vertices 0 and 1 -> 56x56 painted bbox
+    v[:, 2, 0:3] = 5.0                                          # ... nearest, so it survives the z-buffer
+    v[:, 0:2, 3] = [3.0, 50.0]
+    v[:, 0:2, 4] = [60.5, 50.000004]                            # long sliver
+    v[:, 0:2, 5] = [20.0, 50.00001]
+    v[:, 0:2, 6:12] = np.round(v[:, 0:2, 6:12])                 # integer vertices: edges through pixel centres
+    tri = rng.integers(0, nv, (3, 300)).astype(np.float32)
+    tri[:, 0] = [0, 1, 2]
+    tri[:, 1] = [3, 4, 5]
+    tex = rng.uniform(0, 1, (9, 3, nv)).astype(np.float32)
+    want = oracle.oracle_render_depth_forward(v, tri, tex, 64, 64)
+    assert (want[3][0] == 0).sum() > 1024                        # the degenerate triangle really covers > queue capacity
+    _assert_same(_gpu_render(v, tri, tex, 64, 64), want, "overflow")

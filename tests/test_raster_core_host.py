@@ -35,6 +35,7 @@ def emul():
                                         p(outs[0]), p(outs[1]), p(outs[2]), p(outs[3]))
         assert rc == 0, "emulation self-check %d failed" % rc
         return outs
+    run.lib = lib
     return run
 
 
