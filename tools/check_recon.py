@@ -66,7 +66,7 @@ if os.environ.get("FR_TC_DEBUG") == "1":
     print("mma thread per call: wait d_empty %.0f, wait a_full total %.0f, issue total %.0f" % (c[1, 0], c[1, 1], c[1, 2]))
     print("epilogue warp8 per call: wait d_full %.0f, drain %.0f" % (c[2, 0], c[2, 1]))
 
-if os.environ.get("FR_TC_DEBUG") in ("2", "3", "4"):
+if os.environ.get("FR_TC_DEBUG") in ("2", "3", "4") and hasattr(fr._lib.lib(), "fr_debug_tc_trace"):
     import ctypes
     lib = fr._lib.lib()
     p = synth.sample_params_constrained(64, seed=2)

@@ -1,0 +1,599 @@
+// Tensor-core flavour of the reconstruction + projection forward pass: tcgen05 (5th-gen tensor cores) with TMEM
+// accumulators, 3xTF32 operand splitting for fp32-level accuracy, bulk-async (TMA engine) streaming of the basis.
+//
+//   V[b, (c,n)] = sum_k P[(c,n), k] * coef[b, k]        M = 128 vertices per tile (x3 coordinates), N = 64 faces, K = kpad
+//
+// Per CTA (persistent, one per SM, 22 warps):
+//   warp 12  producer   cp.async.bulk (TMA engine): the resident B operand (pre-split coefficients of this batch tile) once,
+//                       then 8 KB basis chunks (16 k-columns x 128 rows, contiguous in the packed layout) into an
+//                       8-stage shared-memory ring, completion on mbarriers
+//   warps 0-7 converter two groups of 4 warps alternate chunks: shared memory -> registers, split every fp32 value into
+//                       hi = top 19 bits (exact tf32) and lo = x - hi, tcgen05.st both into a TMEM ring as the A operand
+//   warp 13  MMA issuer one thread: per k8 step  D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (tcgen05.mma kind::tf32, A from
+//                       TMEM, B = pre-split coefficients resident in shared memory in the canonical K-major layout)
+//   warps 8-11 epilogue tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices), (f.R).v + t, y flip,
+//                       coalesced stores of vertex_proj; double-buffered against the next tile's MMAs
+// The hi/lo split follows the 3xTF32 scheme (drop lo.lo): relative error ~2^-21 per product instead of 2^-11.
+#ifndef FR_RECON_TC_CUH_
+#define FR_RECON_TC_CUH_
+
+#include <cstdlib>
+
+#include "fr_common.cuh"
+#include "recon.cuh"
+
+namespace fr {
+namespace tc {
+
+constexpr int kN = 64;               // faces per batch tile (MMA N)
+constexpr int kChunkGroups = 4;      // float4 k-groups per chunk  -> 16 k columns, 8 KB of basis
+constexpr int kChunkK = kChunkGroups * 4;
+constexpr int kStageChunksDefault = 2;      // chunks per bulk copy / shared-memory stage (32 KB): one elected lane needs ~350 cycles per
+                                     // cp.async.bulk it issues (tools/bulk_bench.cu), too slow for 8 KB pieces
+constexpr int kRawBytes = 12 * 8192;  // shared-memory ring of raw basis stages (96 KB in flight per SM)
+constexpr int kL2Prefetch = 0;       // L2 prefetch ahead of the ring: measured to LOWER streaming bandwidth (tools/bulk_bench.cu)
+constexpr int kDCols = 3 * kN;       // one accumulator set: x, y, z
+constexpr int kTmemCols = 512;       // [0, DBUFS*192): accumulator sets; the rest: ring of split A chunks (32 columns each)
+constexpr int kMaxAStages = 10;
+constexpr int kConvGroups = 2, kEpiWarps = 8;          // role layout: [converters][epilogue][producer][MMA issuer]
+constexpr int kThreads = (4 * kConvGroups + kEpiWarps + 2) * 32;
+constexpr uint32_t kChunkBytes = kChunkGroups * kTileVerts * 16;
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), K-major A/B,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Barriers {
+  uint64_t raw_full[12];
+  uint64_t raw_empty[12];
+  uint64_t a_full[2];
+  uint64_t a_empty[2];
+  uint64_t d_full[2];
+  uint64_t d_empty[2];
+  uint64_t b_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+// Optional per-role cycle accounting (developer diagnostics, FR_TC_DEBUG=1): [role][slot] accumulated clock64 deltas of
+// block 0.  role 0 = converter warp 0, 1 = MMA issuer, 2 = epilogue warp 8, 3 = producer.
+__device__ unsigned long long g_tc_dbg[4][8];
+__device__ unsigned int g_tc_trace[8][160];   // [stream][event] cycles since kernel start (block 0), FR_TC_DEBUG=2
+#define TC_TRACE(stream, idx) do { if (trace && (idx) < 160) g_tc_trace[stream][idx] = (unsigned int)(clock64() - t_start); } while (0)
+#define TC_T(var) const long long var = dbg ? clock64() : 0
+#define TC_ACC(role, slot, t0, t1) do { if (dbg) g_tc_dbg[role][slot] += (unsigned long long)((t1) - (t0)); } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug traps (-> launch error the API reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// one lane of a fully converged warp (keeps tcgen05.mma / commit on the uniform datapath: a lane-0 branch makes the
+// compiler serialise every uniform-register operand through per-thread loops and triples the issue cost)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem_d] (+)= A[tmem_a] . B[smem desc]   (A: 128 lanes x 8 columns of tf32 in TMEM)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(kIdesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, no swizzle: 8-row x 16-byte core matrices,
+// LBO = bytes between the two 16-byte K chunks of one k8 step, SBO = bytes between 8-row groups; version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory carve-up (dynamic, 128-byte aligned base)
+struct SmemLayout {
+  uint32_t b_hi, b_lo, raw, pose, bars, total;
+  uint32_t sbo;  // bytes between 8-face groups of the coefficient operand
+};
+__host__ __device__ inline SmemLayout smem_layout(int kg) {
+  SmemLayout L;
+  L.sbo = (uint32_t)kg * 128u;                       // kg core matrices (8 faces x 4 k) per 8-face group
+  const uint32_t bsz = (kN / 8) * L.sbo;
+  L.b_hi = 0;
+  L.b_lo = bsz;
+  L.raw = 2 * bsz;
+  L.pose = L.raw + kRawBytes;
+  L.bars = L.pose + kN * kPoseStride * 4;
+  L.total = L.bars + (uint32_t)sizeof(Barriers);
+  return L;
+}
+
+// Issue the MMAs of one half-ring batch (BATCH chunks x 2 k8 steps x 3 products) with every operand a uniform base
+// plus a compile-time offset, so the elected lane emits back-to-back UTCHMMA without per-MMA address arithmetic.
+//   a_base : TMEM address of the first chunk of this half (hi columns; lo columns follow at +kChunkK)
+//   dhi/dlo: B descriptors of the batch's first k8 step;   tail_skip: k8 steps to skip at the end (short last chunk)
+template <int BATCH>
+__device__ __forceinline__ void issue_batch(uint32_t d_addr, uint32_t a_base, uint64_t dhi, uint64_t dlo, bool first,
+                                            int tail_skip) {
+#pragma unroll
+  for (int s = 0; s < BATCH; ++s) {
+#pragma unroll
+    for (int j = 0; j < kChunkGroups / 2; ++j) {
+      const int pos = s * (kChunkGroups / 2) + j;
+      if (pos >= BATCH * (kChunkGroups / 2) - tail_skip) continue;
+      const uint32_t a_hi = a_base + s * (2 * kChunkK) + 8 * j, a_lo = a_hi + kChunkK;
+      const uint64_t bh = dhi + 16u * pos, bl = dlo + 16u * pos;
+      mma_tf32_ts(d_addr, a_lo, bh, !(first && pos == 0));
+      mma_tf32_ts(d_addr, a_hi, bl, true);
+      mma_tf32_ts(d_addr, a_hi, bh, true);
+    }
+  }
+}
+
+template <int DBUFS, int kStageChunks>
+__global__ void __launch_bounds__(kThreads, 1)
+recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __restrict__ bsplit, const float* __restrict__ pose,
+                    float* __restrict__ vertex_proj, int batch, int nver, int kg, int ntiles, float im_size,
+                    unsigned flags, int debug) {
+  constexpr int kRawStages = kRawBytes / (kStageChunks * (int)kChunkBytes);
+  constexpr int kConvWarps = 4 * kConvGroups, kEpiWarp0 = kConvWarps, kProducerWarp = kEpiWarp0 + kEpiWarps, kMmaWarp = kProducerWarp + 1;
+  constexpr int kACol0 = DBUFS * kDCols;
+  constexpr int kAStages = (kTmemCols - kACol0) / (2 * kChunkK);
+  static_assert(kAStages % 2 == 0 && kAStages <= kMaxAStages, "the A ring is handed over in two halves");
+  // Hand-over granularity between the converters and the MMA issuer is HALF of the TMEM ring (kABatch chunks), in both
+  // directions.  Measured on B200 (tools/mma_bench2.cu): a satisfied mbarrier wait costs the issuing thread ~130 cycles
+  // and a tcgen05.commit ~200, while the six MMAs of one chunk execute in 192 cycles and the tensor pipe's queue is
+  // shallow -- per-chunk waits/commits leave the pipe idle most of the time.
+  constexpr int kABatch = kAStages / 2;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout L = smem_layout(kg);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + L.bars);
+  float* s_pose = reinterpret_cast<float*>(smem + L.pose);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * kN;
+  const int nchunks = (kg + kChunkGroups - 1) / kChunkGroups;
+  const uint32_t per_tile = 3u * (uint32_t)nchunks;
+  const uint32_t my_tiles = (blockIdx.x < (unsigned)ntiles) ? ((uint32_t)(ntiles - 1 - blockIdx.x) / gridDim.x + 1u) : 0u;
+  const uint32_t total = my_tiles * per_tile;                              // chunks this CTA processes
+  const uint32_t total_padded = (total + kABatch - 1) / kABatch * kABatch;
+  const bool dbg = debug == 1 && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0;
+  const bool trace = debug >= 2 && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0;
+  const long long t_start = clock64();
+
+  // ---- one-time setup: barriers, TMEM, poses (the resident B operand arrives by bulk copy)
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRawStages; ++i) {
+      mbar_init(&bars->raw_full[i], 1);
+      mbar_init(&bars->raw_empty[i], kConvWarps);   // every converter warp reads part of every stage
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a_full[i], 4 * kABatch);  // 4 converter warps per chunk
+      mbar_init(&bars->a_empty[i], 1);
+      mbar_init(&bars->d_full[i], 1);
+      mbar_init(&bars->d_empty[i], kEpiWarps);
+    }
+    mbar_init(&bars->b_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < kN * kPoseStride; i += blockDim.x) s_pose[i] = pose[(size_t)b0 * kPoseStride + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == kProducerWarp) {
+    // ================================================================== producer (TMA engine; whole warp converged, one elected lane issues)
+    {
+      // resident B operand: the pre-split coefficients of this batch tile, already in the canonical K-major layout
+      const uint32_t bbytes = 2u * (kN / 8) * L.sbo;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bars->b_full, bbytes);
+        bulk_load(smem + L.b_hi, bsplit + (size_t)blockIdx.y * bbytes, bbytes / 2, &bars->b_full);
+        bulk_load(smem + L.b_lo, bsplit + (size_t)blockIdx.y * bbytes + bbytes / 2, bbytes / 2, &bars->b_full);
+      }
+      __syncwarp();
+      // basis stream: one bulk copy per stage = kStageChunks consecutive chunks of one coordinate (contiguous in the
+      // packed layout); the last stage of a coordinate is shorter
+      const int stages_per_c = (nchunks + kStageChunks - 1) / kStageChunks;
+      uint32_t sc = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int c = 0; c < 3; ++c) {
+          const float4* cbase = packed + ((size_t)(tile * 3 + c) * kg) * kTileVerts;
+          for (int st = 0; st < stages_per_c; ++st, ++sc) {
+            const uint32_t slot = sc % kRawStages, ph = (sc / kRawStages) & 1u;
+            const int g0 = st * kStageChunks * kChunkGroups;
+            const uint32_t bytes = (uint32_t)min(kStageChunks * kChunkGroups, kg - g0) * kTileVerts * 16u;
+            mbar_wait(&bars->raw_empty[slot], ph ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars->raw_full[slot], bytes);
+              bulk_load(smem + L.raw + slot * (kStageChunks * kChunkBytes), cbase + (size_t)g0 * kTileVerts, bytes,
+                        &bars->raw_full[slot]);
+            }
+            __syncwarp();
+            TC_TRACE(0, sc);
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================== MMA issuer (whole warp converged, one elected lane issues)
+    mbar_wait(&bars->b_full, 0);
+    const uint64_t dhi0 = make_b_desc(smem_u32(smem + L.b_hi), 128u, L.sbo);
+    const uint64_t dlo0 = make_b_desc(smem_u32(smem + L.b_lo), 128u, L.sbo);
+    const int last_nk8 = (kg - (nchunks - 1) * kChunkGroups) / 2;
+    if (nchunks % kABatch == 0) {
+      // fast path: batches never straddle a coordinate, all per-MMA operands are base + immediate
+      const int batches_per_c = nchunks / kABatch;
+      const int tail_skip = kChunkGroups / 2 - last_nk8;
+      uint32_t bi = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const uint32_t dbuf = tcount % DBUFS;
+        TC_T(t0);
+        mbar_wait(&bars->d_empty[dbuf], ((tcount / DBUFS) & 1u) ^ 1u);       // epilogue has drained this accumulator set
+        TC_T(t1);
+        TC_ACC(1, 0, t0, t1);
+        tc_fence_after();
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t d_addr = tmem + dbuf * kDCols + c * kN;
+          uint64_t dhi = dhi0, dlo = dlo0;
+          for (int cb = 0; cb < batches_per_c; ++cb, ++bi) {
+            const uint32_t h = bi & 1u, ph = (bi >> 1) & 1u;
+            TC_T(t2);
+            mbar_wait(&bars->a_full[h], ph);                 // the converters have filled this half of the A ring
+            TC_T(t3);
+            TC_ACC(1, 1, t2, t3);
+            TC_TRACE(4, bi);
+            tc_fence_after();
+            if (elect_one()) {
+              const int skip = (cb == batches_per_c - 1) ? tail_skip : 0;
+              if (debug != 3) {                                                        // debug 3: measure the pipeline without MMAs
+                if (h == 0) issue_batch<kABatch>(d_addr, tmem + kACol0, dhi, dlo, cb == 0, skip);
+                else issue_batch<kABatch>(d_addr, tmem + kACol0 + kABatch * (2 * kChunkK), dhi, dlo, cb == 0, skip);
+              }
+              tc_commit(&bars->a_empty[h]);                                          // this half of the A ring is reusable
+              if (c == 2 && cb == batches_per_c - 1) tc_commit(&bars->d_full[dbuf]);  // the tile's accumulators are complete
+            }
+            __syncwarp();
+            dhi += (uint64_t)(kABatch * (kChunkGroups / 2)) * 16u;
+            dlo += (uint64_t)(kABatch * (kChunkGroups / 2)) * 16u;
+            TC_T(t4);
+            TC_ACC(1, 2, t3, t4);
+            TC_TRACE(5, bi);
+          }
+        }
+      }
+    } else {
+    uint32_t it = 0, q = 0, c = 0, ci = 0, tcount = 0;
+    for (uint32_t bi = 0; bi * kABatch < total; ++bi) {
+      const uint32_t h = bi & 1u, ph = (bi >> 1) & 1u;
+      TC_T(t2);
+      mbar_wait(&bars->a_full[h], ph);                 // the converters have filled this half of the A ring
+      TC_T(t3);
+      TC_ACC(1, 1, t2, t3);
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < kABatch; ++s) {
+        if (it < total) {
+          const uint32_t dbuf = tcount % DBUFS;
+          if (q == 0) {
+            TC_T(t0);
+            mbar_wait(&bars->d_empty[dbuf], ((tcount / DBUFS) & 1u) ^ 1u);   // epilogue has drained this accumulator set
+            TC_T(t1);
+            TC_ACC(1, 0, t0, t1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint32_t a_hi = tmem + kACol0 + (h * kABatch + s) * (2 * kChunkK);
+            const uint32_t a_lo = a_hi + kChunkK;
+            const uint32_t d_addr = tmem + dbuf * kDCols + c * kN;
+            const uint64_t koff = (uint64_t)ci * (kChunkGroups / 2) * 16u;   // 256 bytes per k8 step, in 16-byte units
+            const int nk8 = (ci == (uint32_t)nchunks - 1u) ? last_nk8 : kChunkGroups / 2;
+#pragma unroll
+            for (int j = 0; j < kChunkGroups / 2; ++j) {
+              if (j < nk8) {
+                const uint64_t dhi = dhi0 + koff + 16u * j, dlo = dlo0 + koff + 16u * j;
+                mma_tf32_ts(d_addr, a_lo + 8 * j, dhi, (ci | (uint32_t)j) != 0u);
+                mma_tf32_ts(d_addr, a_hi + 8 * j, dlo, true);
+                mma_tf32_ts(d_addr, a_hi + 8 * j, dhi, true);
+              }
+            }
+            if (s == kABatch - 1) tc_commit(&bars->a_empty[h]);             // this half of the A ring is reusable
+            if (q == per_tile - 1u) tc_commit(&bars->d_full[dbuf]);         // all three accumulators of the tile complete
+          }
+          __syncwarp();
+          ++it; ++q; ++ci;
+          if (ci == (uint32_t)nchunks) { ci = 0; ++c; }
+          if (q == per_tile) { q = 0; c = 0; ++tcount; }
+        }
+      }
+      TC_T(t4);
+      TC_ACC(1, 2, t3, t4);
+    }
+    }
+  } else if (warp < kConvWarps) {
+    // ================================================================== converters (two groups alternate chunks)
+    const int group = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;                       // TMEM lane == vertex row of the tile
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    // chunk ci of a coordinate belongs to group ci % kConvGroups; `it` is the CTA-wide chunk counter that names the A-ring stage
+    const int stages_per_c = (nchunks + kStageChunks - 1) / kStageChunks;
+    uint32_t it = 0, sc = 0;
+    uint32_t ready_round[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};       // last A-ring round seen released, per half
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int c = 0; c < 3; ++c) {
+        for (int st = 0; st < stages_per_c; ++st, ++sc) {
+          const uint32_t slot = sc % kRawStages, rph = (sc / kRawStages) & 1u;
+          const int ci_end = min(nchunks, (st + 1) * kStageChunks);
+          bool have = false;
+          uint32_t done_half[kStageChunks];   // (a group owns at most ceil(kStageChunks / groups) of them)
+          int ndone = 0;
+          for (int ci = st * kStageChunks; ci < ci_end; ++ci, ++it) {
+            if ((ci % kConvGroups) != group) continue;
+            const uint32_t as = it % kAStages, half = as / kABatch, aph = (it / kAStages) & 1u;
+            const int ng = min(kChunkGroups, kg - ci * kChunkGroups);
+            if (!have) {
+              mbar_wait(&bars->raw_full[slot], rph);              // the stage's bulk copy has landed
+              have = true;
+            }
+            if ((warp & 3) == 0) TC_TRACE(1, it);
+            const float4* src = reinterpret_cast<const float4*>(smem + L.raw + slot * (kStageChunks * kChunkBytes) +
+                                                                (ci - st * kStageChunks) * kChunkBytes) + row;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int g = 0; g < kChunkGroups; ++g) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (g < ng) v = src[g * kTileVerts];
+              const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t hbits = __float_as_uint(f[e]) & 0xFFFFE000u;
+                hi[4 * g + e] = hbits;
+                lo[4 * g + e] = __float_as_uint(f[e] - __uint_as_float(hbits));
+              }
+            }
+            if (ci + kConvGroups >= ci_end) {                     // this group's last chunk of the stage is in registers
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars->raw_empty[slot]);
+            }
+            if (ready_round[half] != it / kAStages) {            // a satisfied wait still costs ~130 cycles: ask once per round
+              mbar_wait(&bars->a_empty[half], aph ^ 1u);          // MMAs that read this half of the TMEM ring have retired
+              ready_round[half] = it / kAStages;
+            }
+            if ((warp & 3) == 0) TC_TRACE(2, it);
+            tc_fence_after();
+            const uint32_t a_addr = tmem + lane_field + kACol0 + as * (2 * kChunkK);
+            tmem_st16(a_addr, hi);
+            tmem_st16(a_addr + kChunkK, lo);
+            done_half[ndone++] = half;
+            if (warp == 0 && dbg) g_tc_dbg[0][7] += 1;
+          }
+          if (ndone > 0) {                                        // one completion wait + hand-over for the whole stage
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+              for (int i = 0; i < ndone; ++i) mbar_arrive(&bars->a_full[done_half[i]]);
+            if ((warp & 3) == 0) TC_TRACE(3, it - 1);
+          }
+          if (!have) {                                            // no chunk of this stage fell to this group: still release it
+            mbar_wait(&bars->raw_full[slot], rph);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->raw_empty[slot]);
+          }
+        }
+      }
+    }
+    // pad the last half-ring batch so the issuer's wait completes (in order: never ahead of the previous round's phase)
+    for (; it < total_padded; ++it) {
+      if ((int)(it % kConvGroups) != group) continue;
+      const uint32_t as = it % kAStages, half = as / kABatch, aph = (it / kAStages) & 1u;
+      mbar_wait(&bars->a_empty[half], aph ^ 1u);
+      if (lane == 0) mbar_arrive(&bars->a_full[half]);
+    }
+  } else {
+    // ================================================================== epilogue (warps 8..15: two per TMEM lane quarter,
+    // each draining half of the faces)
+    const int qd = (warp - kEpiWarp0) & 3;                        // TMEM lane quarter == warp % 4
+    const int fhalf = (warp - kEpiWarp0) >> 2;                    // this warp drains faces [fhalf, fhalf+1) * kN / (kEpiWarps/4)
+    const int v = qd * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(qd * 32) << 16;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const uint32_t dbuf = tcount % DBUFS, dph = (tcount / DBUFS) & 1u;
+      const int n = tile * kTileVerts + v;
+      TC_T(e0);
+      mbar_wait(&bars->d_full[dbuf], dph);
+      TC_T(e1);
+      if (warp == kEpiWarp0) TC_TRACE(6, tcount);
+      tc_fence_after();
+      const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
+      float* out = vertex_proj + (size_t)b0 * 3 * nver + n;        // face b0 + j lives 3*nver*j floats further
+      const size_t face_stride = (size_t)3 * nver;
+#pragma unroll 1
+      for (int jb = fhalf * (kN / (kEpiWarps / 4)); jb < (fhalf + 1) * (kN / (kEpiWarps / 4)); jb += 16) {
+        float x[16], y[16], z[16];
+        tmem_ld16(d_addr + 0 * kN + jb, x);
+        tmem_ld16(d_addr + 1 * kN + jb, y);
+        tmem_ld16(d_addr + 2 * kN + jb, z);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n < nver) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (b0 + jb + j < batch) {
+              const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPoseStride);
+              const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+              const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+              project_store(P, x[j], y[j], z[j], im_size, flags, out + (size_t)(jb + j) * face_stride, (size_t)nver, 0);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+      if (warp == kEpiWarp0) TC_TRACE(7, tcount);
+      if (warp == kEpiWarp0) {
+        TC_T(e2);
+        TC_ACC(2, 0, e0, e1);   // wait d_full
+        TC_ACC(2, 1, e1, e2);   // drain + project + store
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+  }
+}
+
+}  // namespace tc
+
+// split coefficients of every 64-face batch tile in the canonical layout: [tile][hi|lo][8 groups][kg][8 faces][4 k]
+inline size_t recon_tc_workspace_bytes(int batch, const BasisGeom& g) {
+  return (size_t)ceil_div(batch, tc::kN) * 2 * (tc::kN / 8) * (size_t)g.kg * 128;
+}
+
+// coefT [kpad][bpad] -> bsplit; element (face n, column k) of a tile lives at (n/8)*sbo + (k/4)*128 + (n%8)*16 + (k%4)*4
+__global__ void __launch_bounds__(256)
+recon_tc_split_kernel(const float* __restrict__ coefT, int bpad, int kpad, int kg, unsigned char* __restrict__ bsplit) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= kpad * bpad) return;
+  const int k = idx / bpad, b = idx - k * bpad;
+  const float c = coefT[idx];
+  const uint32_t hi = __float_as_uint(c) & 0xFFFFE000u;
+  const float lo = c - __uint_as_float(hi);
+  const uint32_t sbo = (uint32_t)kg * 128u;
+  const uint32_t half = (tc::kN / 8) * sbo;
+  const int n = b % tc::kN;
+  unsigned char* tile = bsplit + (size_t)(b / tc::kN) * 2 * half;
+  const uint32_t off = (uint32_t)(n >> 3) * sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
+  *reinterpret_cast<uint32_t*>(tile + off) = hi;
+  *reinterpret_cast<float*>(tile + half + off) = lo;
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
+// FR_RECON_PATH=simt|tc overrides the dispatch (debugging / A-B comparisons); default: tensor cores above 8 faces.
+inline int recon_path_override() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = std::getenv("FR_RECON_PATH");
+    cached = (e == nullptr) ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0));
+  }
+  return cached;
+}
+
+inline bool recon_tc_applicable(int batch, const BasisGeom& g, unsigned) {
+  const int ov = recon_path_override();
+  if (ov == 1) return false;
+  const tc::SmemLayout L = tc::smem_layout(g.kg);
+  if (L.total > 227u * 1024u) return false;          // K too large for a resident coefficient operand
+  if (ov == 2) return true;
+  return batch > 8;
+}
+
+inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const float* pose, void* tc_ws, float* vertex_proj,
+                               int batch, int nver, const BasisGeom& g, float im_size, unsigned flags, int nsm,
+                               cudaStream_t st) {
+  static const int dbufs = env_int("FR_TC_DBUFS", 1);
+  static const int debug = env_int("FR_TC_DEBUG", 0);
+  const tc::SmemLayout L = tc::smem_layout(g.kg);
+  const int bpad = batch_padded(batch);
+  unsigned char* bsplit = static_cast<unsigned char*>(tc_ws);
+  recon_tc_split_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(coefT, bpad, g.kpad, g.kg, bsplit);
+  FR_LAUNCHED("recon_tc_split_kernel");
+  const int nbt = ceil_div(batch, tc::kN);
+  int ctas = nsm / nbt;
+  if (ctas < 1) ctas = 1;
+  if (ctas > g.ntiles) ctas = g.ntiles;
+  static const int sc = env_int("FR_TC_STAGE_CHUNKS", 2);
+  FR_REQUIRE((sc == 1 || sc == 2 || sc == 4) && (dbufs == 1 || dbufs == 2), "bad FR_TC_* tuning override");
+  auto launch = [&](auto kern) -> int {
+    FR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    kern<<<dim3(ctas, nbt), tc::kThreads, L.total, st>>>(reinterpret_cast<const float4*>(packed), bsplit, pose, vertex_proj, batch, nver,
+                                                        g.kg, g.ntiles, im_size, flags, debug);
+    return FR_OK;
+  };
+  int rc = FR_OK;
+  if (dbufs == 1) {
+    if (sc == 1) rc = launch(tc::recon_fwd_tc_kernel<1, 1>);
+    else if (sc == 2) rc = launch(tc::recon_fwd_tc_kernel<1, 2>);
+    else rc = launch(tc::recon_fwd_tc_kernel<1, 4>);
+  } else {
+    if (sc == 1) rc = launch(tc::recon_fwd_tc_kernel<2, 1>);
+    else if (sc == 2) rc = launch(tc::recon_fwd_tc_kernel<2, 2>);
+    else rc = launch(tc::recon_fwd_tc_kernel<2, 4>);
+  }
+  if (rc != FR_OK) return rc;
+  FR_LAUNCHED("recon_fwd_tc_kernel");
+  return FR_OK;
+}
+
+}  // namespace fr
+
+#endif  // FR_RECON_TC_CUH_
