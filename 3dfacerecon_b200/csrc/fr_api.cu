@@ -139,11 +139,13 @@ int fr_recon_project_forward(const float* params, const float* packed, float* ve
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
 
+  const bool use_tc = recon_tc_applicable(batch, g, flags);
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
-                                                                 g.kpad, flags, w.coefT, w.pose);
+                                                                 g.kpad, flags, w.coefT, w.pose,
+                                                                 use_tc ? static_cast<unsigned char*>(w.tc) : nullptr);
   FR_LAUNCHED("recon_prep_kernel");
 
-  if (recon_tc_applicable(batch, g, flags))
+  if (use_tc)
     return launch_recon_fwd_tc(packed, w.coefT, w.pose, w.tc, vertex_proj, batch, nver, g, im_size, flags, sm_count(), st);
   if (batch <= 4) return launch_recon_fwd_simt<4>(packed, w, vertex_proj, batch, nver, g, im_size, flags, 1, st);
   if (batch <= 8) return launch_recon_fwd_simt<8>(packed, w, vertex_proj, batch, nver, g, im_size, flags, 1, st);
@@ -166,7 +168,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
 
   // recomputed rather than trusted from a previous forward: the workspace is the caller's scratch
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
-                                                                 g.kpad, flags, w.coefT, w.pose);
+                                                                 g.kpad, flags, w.coefT, w.pose, nullptr);
   FR_LAUNCHED("recon_prep_kernel");
   FR_CUDA(cudaMemsetAsync(w.G, 0, sizeof(float) * (size_t)bpad * g.kpad, st));
   recon_bwd_dt_kernel<<<dim3(batch, 3), 256, 0, st>>>(vertex_grad, nver, flags, w.dt);

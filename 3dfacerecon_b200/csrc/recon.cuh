@@ -17,7 +17,7 @@
 namespace fr {
 
 constexpr int kPoseStride = 24;  // floats per face: M = f.R [9] | t [3] | R [9] | f | pad[2]
-constexpr int kBatchPad = 64;    // coefficient matrix columns are padded to a multiple of this
+constexpr int kBatchPad = 64;    // coefficient matrix columns are padded to a multiple of this (== faces per tensor-core batch tile)
 
 __host__ __device__ inline int batch_padded(int batch) { return (batch + kBatchPad - 1) / kBatchPad * kBatchPad; }
 
@@ -95,7 +95,7 @@ __device__ inline void pose_matrices(const float* __restrict__ p, unsigned flags
 // column; beyond: 0; padded faces: 0).  pose [bpad][24].
 __global__ void __launch_bounds__(256)
 recon_prep_kernel(const float* __restrict__ params, int dparam, int batch, int bpad, int ks, int ke, int kpad,
-                  unsigned flags, float* __restrict__ coefT, float* __restrict__ pose) {
+                  unsigned flags, float* __restrict__ coefT, float* __restrict__ pose, unsigned char* __restrict__ bsplit) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx < kpad * bpad) {
     const int k = idx / bpad, b = idx - k * bpad;
@@ -105,6 +105,18 @@ recon_prep_kernel(const float* __restrict__ params, int dparam, int batch, int b
       else if (k == ks + ke) v = 1.0f;
     }
     coefT[idx] = v;
+    if (bsplit != nullptr) {
+      // tensor-core path: the same coefficient split into hi (exact tf32) + lo, stored per 64-face batch tile in the UMMA
+      // canonical K-major no-swizzle layout [hi|lo][8-face group][k/4][face%8][k%4] that recon_fwd_tc_kernel bulk-copies
+      const uint32_t hi = __float_as_uint(v) & 0xFFFFE000u;
+      const float lo = v - __uint_as_float(hi);
+      const uint32_t sbo = (uint32_t)(kpad / 4) * 128u, half = (kBatchPad / 8) * sbo;
+      const int n = b % kBatchPad;
+      unsigned char* tile = bsplit + (size_t)(b / kBatchPad) * 2 * half;
+      const uint32_t off = (uint32_t)(n >> 3) * sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
+      *reinterpret_cast<uint32_t*>(tile + off) = hi;
+      *reinterpret_cast<float*>(tile + half + off) = lo;
+    }
   }
   if (idx < bpad) {
     if (idx < batch) {

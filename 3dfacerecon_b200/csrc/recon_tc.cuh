@@ -396,24 +396,6 @@ inline size_t recon_tc_workspace_bytes(int batch, const BasisGeom& g) {
   return (size_t)ceil_div(batch, tc::kN) * 2 * (tc::kN / 8) * (size_t)g.kg * 128;
 }
 
-// coefT [kpad][bpad] -> bsplit; element (face n, column k) of a tile lives at (n/8)*sbo + (k/4)*128 + (n%8)*16 + (k%4)*4
-__global__ void __launch_bounds__(256)
-recon_tc_split_kernel(const float* __restrict__ coefT, int bpad, int kpad, int kg, unsigned char* __restrict__ bsplit) {
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= kpad * bpad) return;
-  const int k = idx / bpad, b = idx - k * bpad;
-  const float c = coefT[idx];
-  const uint32_t hi = __float_as_uint(c) & 0xFFFFE000u;
-  const float lo = c - __uint_as_float(hi);
-  const uint32_t sbo = (uint32_t)kg * 128u;
-  const uint32_t half = (tc::kN / 8) * sbo;
-  const int n = b % tc::kN;
-  unsigned char* tile = bsplit + (size_t)(b / tc::kN) * 2 * half;
-  const uint32_t off = (uint32_t)(n >> 3) * sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
-  *reinterpret_cast<uint32_t*>(tile + off) = hi;
-  *reinterpret_cast<float*>(tile + half + off) = lo;
-}
-
 inline int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   return e ? std::atoi(e) : dflt;
@@ -444,10 +426,8 @@ inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const fl
   static const int dbufs = env_int("FR_TC_DBUFS", 2);
   static const int debug = env_int("FR_TC_DEBUG", 0);
   const tc::SmemLayout L = tc::smem_layout(g.kg);
-  const int bpad = batch_padded(batch);
-  unsigned char* bsplit = static_cast<unsigned char*>(tc_ws);
-  recon_tc_split_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(coefT, bpad, g.kpad, g.kg, bsplit);
-  FR_LAUNCHED("recon_tc_split_kernel");
+  unsigned char* bsplit = static_cast<unsigned char*>(tc_ws);   // filled by recon_prep_kernel
+  static_assert(tc::kN == kBatchPad, "the prep kernel lays the split coefficients out per kBatchPad faces");
   const int nbt = ceil_div(batch, tc::kN);
   int ctas = nsm / nbt;
   if (ctas < 1) ctas = 1;

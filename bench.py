@@ -293,6 +293,58 @@ def run_ours(args):
                   "tri_ind_bit_exact": bool(tri_ind[:2].cpu().numpy().tobytes() == want[3].tobytes()),
                   "depth_bit_exact": bool(depth[:2].cpu().numpy().tobytes() == want[0].tobytes())}
 
+    # other BASELINE configs, reported as extras (not the headline): config 4 = batch-256 forward + backward of the whole
+    # path (d depth -> d params through render_depth's backward and the recon backward), config 1 = batch-1 forward latency
+    extras = None
+    if rank == 0 and not args.no_extras:
+        net = importlib.import_module(PKG + ".nets.network")
+        ops = importlib.import_module(PKG + ".rendering_layer.ops")
+
+        def time_torch(fn, reps):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / reps
+
+        B4 = 256
+        p4 = torch.from_numpy(synth.sample_params_constrained(B4, seed=4)).to(dev).requires_grad_(True)
+        img4 = torch.empty((B4, H, W, 3), device=dev)
+        tex4 = dm.vertex_code.unsqueeze(0).expand(B4, -1, -1)
+        gd4 = torch.randn((B4, H, W, 1), device=dev)
+
+        def fwd_bwd():
+            p4.grad = None
+            vp = net.recon_project(p4, dm, IM_SIZE)
+            d, _, _, ti = ops.render_depth(vp, dm.tri, tex4, img4)
+            (d * (gd4 * (ti >= 0))).sum().backward()
+
+        def fwd_only4():
+            with torch.no_grad():
+                vp = net.recon_project(p4, dm, IM_SIZE)
+                ops.render_depth(vp, dm.tri, tex4, img4)
+
+        ms_fb = time_torch(fwd_bwd, 10)
+        ms_f4 = time_torch(fwd_only4, 10)
+        p1 = torch.from_numpy(synth.sample_params_constrained(1, seed=1)).to(dev)
+        img1 = torch.empty((1, H, W, 3), device=dev)
+
+        def fwd1():
+            with torch.no_grad():
+                vp = net.recon_project(p1, dm, IM_SIZE)
+                ops.render_depth(vp, dm.tri, dm.vertex_code.unsqueeze(0), img1)
+
+        ms_1 = time_torch(fwd1, 20)
+        extras = {"config4_b256_fwd_bwd": {"ms": ms_fb, "faces_per_s": B4 / (ms_fb * 1e-3), "fwd_only_ms": ms_f4,
+                                           "api": "recon_project + render_depth (all four outputs) + autograd backward, torch API, L2 warm"},
+                  "config1_b1_fwd": {"ms": ms_1, "api": "recon_project + render_depth (all four outputs), torch API, L2 warm"}}
+        del p4, img4, gd4
+
     # end to end through the host-buffer C-ABI session: pinned params in, depth out, inside the timed region
     del ws, flush
     sess = pkg.Session(model, H, W, max_batch=B, device=local_rank)
@@ -349,7 +401,7 @@ def run_ours(args):
                                         "achieved": (rb + nb) / (ms_full_max * 1e-3) / 1e9,
                                         "frac": (rb + nb) / (ms_full_max * 1e-3) / 1e9 / peak},
                          "groups_ms": {"recon_project_forward": ms_recon_max, "render_depth_forward": ms_render_max}},
-            "cpu_baseline": cpu_baseline, "clocks": clocks, "parity": parity,
+            "cpu_baseline": cpu_baseline, "clocks": clocks, "parity": parity, "extras": extras,
         }
         print(json.dumps(line))
     dist.shutdown()
@@ -392,6 +444,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="faces per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
