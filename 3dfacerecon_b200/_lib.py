@@ -20,6 +20,7 @@ FR_YFLIP_S_Y_1, FR_YFLIP_S_Y, FR_YFLIP_NONE = 0x0, 0x2, 0x4
 FR_MEAN_PLANAR, FR_MEAN_INTERLEAVED = 0x0, 0x10
 FR_BASIS_PLANAR, FR_BASIS_INTERLEAVED = 0x0, 0x20
 FR_NDIM_POSE = 7
+FR_SESSION_SLOTS = 2
 
 _vp, _sz, _i, _f, _u, _ll = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, ctypes.c_uint, ctypes.c_longlong
 
@@ -41,6 +42,8 @@ SIGNATURES = {
     "fr_session_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u, _i, ctypes.POINTER(_vp)]),
     "fr_session_destroy": (None, [_vp]),
     "fr_session_forward": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),
+    "fr_session_submit": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp, _vp]),
+    "fr_session_wait": (_i, [_vp, _i]),
     "fr_session_backward": (_i, [_vp, _vp, _i, _vp]),
 }
 

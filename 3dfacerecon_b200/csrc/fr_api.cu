@@ -220,9 +220,10 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
   uint2* snap = reinterpret_cast<uint2*>(static_cast<char*>(workspace) +
                                          align_up(sizeof(unsigned long long) * (size_t)batch * npix, kAlign));
 
-  FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   if (ntri > 0) {
-    raster_snap_kernel<<<dim3(ceil_div(nver, kRasterThreads), batch), kRasterThreads, 0, st>>>(vertex, snap, nver, width, height);
+    // the snap pass also clears the visibility keys
+    raster_snap_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
+        vertex, snap, keys, nver, npix, width, height);
     FR_LAUNCHED("raster_snap_kernel");
     const unsigned gx = (unsigned)ceil_div(ntri, kRasterThreads);
     if (batch >= 8)
@@ -232,12 +233,15 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
     else
       raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(vertex, snap, tri, keys, batch, nver, ntri, height, width);
     FR_LAUNCHED("raster_keys_kernel");
+  } else {
+    FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   }
+  const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
   if (texture_image != nullptr || normal != nullptr)
-    raster_resolve_kernel<true><<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(
+    raster_resolve_kernel<true><<<rgrid, kRasterThreads, 0, st>>>(
         keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
   else
-    raster_resolve_kernel<false><<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(
+    raster_resolve_kernel<false><<<rgrid, kRasterThreads, 0, st>>>(
         keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
   FR_LAUNCHED("raster_resolve_kernel");
   return FR_OK;
@@ -281,24 +285,39 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ session
-struct fr_session {
-  int device, nver, ntri, ks, ke, height, width, max_batch, last_batch;
-  unsigned flags;
-  float last_im_size;
+// Device state of one in-flight batch.  Two slots let the device->host copy of one batch overlap the kernels of the
+// next (fr_session_submit / fr_session_wait); fr_session_forward is submit + wait on slot 0.
+struct fr_slot {
   cudaStream_t stream;
-  float *packed, *tri, *params, *vertex, *depth, *tri_ind, *depth_grad, *vgrad, *pgrad;
+  float *params, *vertex, *depth, *tri_ind;
   void* ws;
+  int batch;          // faces of the batch submitted last on this slot (0 = none)
+  float im_size;
+  bool pending;       // submitted and not yet waited for
+};
+
+struct fr_session {
+  int device, nver, ntri, ks, ke, height, width, max_batch;
+  unsigned flags;
+  float *packed, *tri, *depth_grad, *vgrad, *pgrad;
   size_t ws_bytes;
+  fr_slot slot[FR_SESSION_SLOTS];
 };
 
 static void session_free(fr_session* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  float* bufs[] = {s->packed, s->tri, s->params, s->vertex, s->depth, s->tri_ind, s->depth_grad, s->vgrad, s->pgrad};
+  for (fr_slot& sl : s->slot) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    float* bufs[] = {sl.params, sl.vertex, sl.depth, sl.tri_ind};
+    for (float* p : bufs)
+      if (p) cudaFree(p);
+    if (sl.ws) cudaFree(sl.ws);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
+  float* bufs[] = {s->packed, s->tri, s->depth_grad, s->vgrad, s->pgrad};
   for (float* p : bufs)
     if (p) cudaFree(p);
-  if (s->ws) cudaFree(s->ws);
-  if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
 
@@ -324,28 +343,29 @@ int fr_session_create(const float* mu, const float* pc_shape, const float* pc_ex
     return e == cudaSuccess;
   };
   s->ws_bytes = fr_pipeline_workspace_bytes(max_batch, nver, ndim_shape, ndim_exp, height, width);
-  chk(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
   chk(cudaMalloc(&s->packed, fr_packed_basis_bytes(nver, ndim_shape, ndim_exp)), "cudaMalloc(packed)");
   chk(cudaMalloc(&s->tri, sizeof(float) * 3 * (size_t)ntri), "cudaMalloc(tri)");
-  chk(cudaMalloc(&s->params, sizeof(float) * (size_t)max_batch * d), "cudaMalloc(params)");
-  chk(cudaMalloc(&s->vertex, sizeof(float) * (size_t)max_batch * n3), "cudaMalloc(vertex)");
-  chk(cudaMalloc(&s->depth, sizeof(float) * (size_t)max_batch * npix), "cudaMalloc(depth)");
-  chk(cudaMalloc(&s->tri_ind, sizeof(float) * (size_t)max_batch * npix), "cudaMalloc(tri_ind)");
-  chk(cudaMalloc(&s->depth_grad, sizeof(float) * (size_t)max_batch * npix), "cudaMalloc(depth_grad)");
-  chk(cudaMalloc(&s->vgrad, sizeof(float) * (size_t)max_batch * n3), "cudaMalloc(vertex_grad)");
-  chk(cudaMalloc(&s->pgrad, sizeof(float) * (size_t)max_batch * d), "cudaMalloc(params_grad)");
-  chk(cudaMalloc(&s->ws, s->ws_bytes), "cudaMalloc(workspace)");
+  for (fr_slot& sl : s->slot) {
+    chk(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    chk(cudaMalloc(&sl.params, sizeof(float) * (size_t)max_batch * d), "cudaMalloc(params)");
+    chk(cudaMalloc(&sl.vertex, sizeof(float) * (size_t)max_batch * n3), "cudaMalloc(vertex)");
+    chk(cudaMalloc(&sl.depth, sizeof(float) * (size_t)max_batch * npix), "cudaMalloc(depth)");
+    chk(cudaMalloc(&sl.tri_ind, sizeof(float) * (size_t)max_batch * npix), "cudaMalloc(tri_ind)");
+    chk(cudaMalloc(&sl.ws, s->ws_bytes), "cudaMalloc(workspace)");
+  }
+  // backward staging is allocated on first use (fr_session_backward): forward-only callers never pay for it
   chk(cudaMalloc(&d_mu, sizeof(float) * n3), "cudaMalloc(mu)");
   if (ndim_shape) chk(cudaMalloc(&d_ps, sizeof(float) * n3 * ndim_shape), "cudaMalloc(pc_shape)");
   if (ndim_exp) chk(cudaMalloc(&d_pe, sizeof(float) * n3 * ndim_exp), "cudaMalloc(pc_exp)");
+  cudaStream_t st = s->slot[0].stream;
   if (rc == FR_OK) {
-    chk(cudaMemcpyAsync(d_mu, mu, sizeof(float) * n3, cudaMemcpyHostToDevice, s->stream), "copy mu");
-    if (ndim_shape) chk(cudaMemcpyAsync(d_ps, pc_shape, sizeof(float) * n3 * ndim_shape, cudaMemcpyHostToDevice, s->stream), "copy pc_shape");
-    if (ndim_exp) chk(cudaMemcpyAsync(d_pe, pc_exp, sizeof(float) * n3 * ndim_exp, cudaMemcpyHostToDevice, s->stream), "copy pc_exp");
-    chk(cudaMemcpyAsync(s->tri, tri, sizeof(float) * 3 * (size_t)ntri, cudaMemcpyHostToDevice, s->stream), "copy tri");
+    chk(cudaMemcpyAsync(d_mu, mu, sizeof(float) * n3, cudaMemcpyHostToDevice, st), "copy mu");
+    if (ndim_shape) chk(cudaMemcpyAsync(d_ps, pc_shape, sizeof(float) * n3 * ndim_shape, cudaMemcpyHostToDevice, st), "copy pc_shape");
+    if (ndim_exp) chk(cudaMemcpyAsync(d_pe, pc_exp, sizeof(float) * n3 * ndim_exp, cudaMemcpyHostToDevice, st), "copy pc_exp");
+    chk(cudaMemcpyAsync(s->tri, tri, sizeof(float) * 3 * (size_t)ntri, cudaMemcpyHostToDevice, st), "copy tri");
   }
-  if (rc == FR_OK) rc = fr_pack_basis(d_mu, d_ps, d_pe, nver, ndim_shape, ndim_exp, flags, s->packed, s->stream);
-  if (rc == FR_OK) chk(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize");
+  if (rc == FR_OK) rc = fr_pack_basis(d_mu, d_ps, d_pe, nver, ndim_shape, ndim_exp, flags, s->packed, st);
+  if (rc == FR_OK) chk(cudaStreamSynchronize(st), "cudaStreamSynchronize");
   if (d_mu) cudaFree(d_mu);
   if (d_ps) cudaFree(d_ps);
   if (d_pe) cudaFree(d_pe);
@@ -359,42 +379,71 @@ int fr_session_create(const float* mu, const float* pc_shape, const float* pc_ex
 
 void fr_session_destroy(fr_session* s) { session_free(s); }
 
-int fr_session_forward(fr_session* s, const float* params, int batch, float im_size, float* depth, float* tri_ind,
-                       float* vertex_proj) {
+int fr_session_submit(fr_session* s, int slot, const float* params, int batch, float im_size, float* depth, float* tri_ind,
+                      float* vertex_proj) {
   FR_REQUIRE(s && params && depth, "null pointer argument");
+  FR_REQUIRE(slot >= 0 && slot < FR_SESSION_SLOTS, "slot %d outside [0, %d)", slot, FR_SESSION_SLOTS);
   FR_REQUIRE(batch > 0 && batch <= s->max_batch, "batch %d outside (0, %d]", batch, s->max_batch);
+  fr_slot& sl = s->slot[slot];
+  FR_REQUIRE(!sl.pending, "slot %d still has a batch in flight: call fr_session_wait first", slot);
   FR_CUDA(cudaSetDevice(s->device));
   const int d = FR_NDIM_POSE + s->ks + s->ke;
   const size_t npix = (size_t)s->height * s->width;
-  FR_CUDA(cudaMemcpyAsync(s->params, params, sizeof(float) * (size_t)batch * d, cudaMemcpyHostToDevice, s->stream));
-  if (int rc = fr_recon_render_forward(s->params, s->packed, s->tri, s->vertex, s->depth, s->tri_ind, batch, s->nver, s->ntri,
-                                       s->ks, s->ke, s->height, s->width, im_size, s->flags, s->ws, s->ws_bytes, s->stream))
+  FR_CUDA(cudaMemcpyAsync(sl.params, params, sizeof(float) * (size_t)batch * d, cudaMemcpyHostToDevice, sl.stream));
+  if (int rc = fr_recon_render_forward(sl.params, s->packed, s->tri, sl.vertex, sl.depth, sl.tri_ind, batch, s->nver, s->ntri,
+                                       s->ks, s->ke, s->height, s->width, im_size, s->flags, sl.ws, s->ws_bytes, sl.stream))
     return rc;
-  FR_CUDA(cudaMemcpyAsync(depth, s->depth, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, s->stream));
-  if (tri_ind) FR_CUDA(cudaMemcpyAsync(tri_ind, s->tri_ind, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, s->stream));
+  FR_CUDA(cudaMemcpyAsync(depth, sl.depth, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, sl.stream));
+  if (tri_ind) FR_CUDA(cudaMemcpyAsync(tri_ind, sl.tri_ind, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, sl.stream));
   if (vertex_proj)
-    FR_CUDA(cudaMemcpyAsync(vertex_proj, s->vertex, sizeof(float) * (size_t)batch * 3 * s->nver, cudaMemcpyDeviceToHost, s->stream));
-  FR_CUDA(cudaStreamSynchronize(s->stream));
-  s->last_batch = batch;
-  s->last_im_size = im_size;
+    FR_CUDA(cudaMemcpyAsync(vertex_proj, sl.vertex, sizeof(float) * (size_t)batch * 3 * s->nver, cudaMemcpyDeviceToHost, sl.stream));
+  sl.batch = batch;
+  sl.im_size = im_size;
+  sl.pending = true;
   return FR_OK;
+}
+
+int fr_session_wait(fr_session* s, int slot) {
+  FR_REQUIRE(s != nullptr, "null pointer argument");
+  FR_REQUIRE(slot >= 0 && slot < FR_SESSION_SLOTS, "slot %d outside [0, %d)", slot, FR_SESSION_SLOTS);
+  fr_slot& sl = s->slot[slot];
+  if (!sl.pending) return FR_OK;
+  sl.pending = false;
+  FR_CUDA(cudaSetDevice(s->device));
+  FR_CUDA(cudaStreamSynchronize(sl.stream));
+  return FR_OK;
+}
+
+int fr_session_forward(fr_session* s, const float* params, int batch, float im_size, float* depth, float* tri_ind,
+                       float* vertex_proj) {
+  FR_REQUIRE(s != nullptr, "null pointer argument");
+  if (int rc = fr_session_wait(s, 0)) return rc;
+  if (int rc = fr_session_submit(s, 0, params, batch, im_size, depth, tri_ind, vertex_proj)) return rc;
+  return fr_session_wait(s, 0);
 }
 
 int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float* params_grad) {
   FR_REQUIRE(s && depth_grad && params_grad, "null pointer argument");
-  FR_REQUIRE(batch > 0 && batch == s->last_batch, "batch %d does not match the last forward (%d)", batch, s->last_batch);
+  fr_slot& sl = s->slot[0];
+  FR_REQUIRE(!sl.pending, "slot 0 still has a batch in flight: call fr_session_wait first");
+  FR_REQUIRE(batch > 0 && batch == sl.batch, "batch %d does not match the last forward on slot 0 (%d)", batch, sl.batch);
   FR_CUDA(cudaSetDevice(s->device));
   const int d = FR_NDIM_POSE + s->ks + s->ke;
   const size_t npix = (size_t)s->height * s->width;
-  FR_CUDA(cudaMemcpyAsync(s->depth_grad, depth_grad, sizeof(float) * batch * npix, cudaMemcpyHostToDevice, s->stream));
-  if (int rc = fr_render_depth_backward(s->depth_grad, s->tri, s->tri_ind, s->vgrad, batch, s->nver, s->ntri, s->height,
-                                        s->width, s->stream))
+  if (s->depth_grad == nullptr) {
+    FR_CUDA(cudaMalloc(&s->depth_grad, sizeof(float) * (size_t)s->max_batch * npix));
+    FR_CUDA(cudaMalloc(&s->vgrad, sizeof(float) * (size_t)s->max_batch * 3 * s->nver));
+    FR_CUDA(cudaMalloc(&s->pgrad, sizeof(float) * (size_t)s->max_batch * d));
+  }
+  FR_CUDA(cudaMemcpyAsync(s->depth_grad, depth_grad, sizeof(float) * batch * npix, cudaMemcpyHostToDevice, sl.stream));
+  if (int rc = fr_render_depth_backward(s->depth_grad, s->tri, sl.tri_ind, s->vgrad, batch, s->nver, s->ntri, s->height,
+                                        s->width, sl.stream))
     return rc;
-  if (int rc = fr_recon_project_backward(s->params, s->packed, s->vgrad, s->pgrad, batch, s->nver, s->ks, s->ke, s->flags,
-                                         s->ws, s->ws_bytes, s->stream))
+  if (int rc = fr_recon_project_backward(sl.params, s->packed, s->vgrad, s->pgrad, batch, s->nver, s->ks, s->ke, s->flags,
+                                         sl.ws, s->ws_bytes, sl.stream))
     return rc;
-  FR_CUDA(cudaMemcpyAsync(params_grad, s->pgrad, sizeof(float) * (size_t)batch * d, cudaMemcpyDeviceToHost, s->stream));
-  FR_CUDA(cudaStreamSynchronize(s->stream));
+  FR_CUDA(cudaMemcpyAsync(params_grad, s->pgrad, sizeof(float) * (size_t)batch * d, cudaMemcpyDeviceToHost, sl.stream));
+  FR_CUDA(cudaStreamSynchronize(sl.stream));
   return FR_OK;
 }
 

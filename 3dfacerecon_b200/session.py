@@ -32,6 +32,7 @@ class Session:
         self.d = _lib.FR_NDIM_POSE + self.ks + self.ke
         self.height, self.width, self.max_batch = int(height), int(width), int(max_batch)
         self._h = ctypes.c_void_p()
+        self._inflight = {}
         check(lib().fr_session_create(_fptr(mu), _fptr(ps), _fptr(pe), _fptr(tri), self.nver, self.ntri, self.ks, self.ke,
                                       self.height, self.width, self.max_batch, _CONV[convention], int(device),
                                       ctypes.byref(self._h)))
@@ -47,6 +48,23 @@ class Session:
             tri_ind = np.empty((B, self.height, self.width, 1), np.float32)
         check(lib().fr_session_forward(self._h, _fptr(params), B, float(im_size), _fptr(depth), _fptr(tri_ind), _fptr(vertex_proj)))
         return depth, tri_ind
+
+    def submit(self, slot, params, im_size=200.0, depth=None, tri_ind=None, vertex_proj=None):
+        """Enqueue one batch on ``slot`` (0 .. FR_SESSION_SLOTS-1) and return immediately; ``wait(slot)`` blocks until
+        ``depth`` (and the optional outputs) are filled.  ``params`` and the output arrays must be C-contiguous float32
+        and stay alive and untouched until the wait -- pass pinned memory so that the copies really overlap."""
+        for a in (params, depth, tri_ind, vertex_proj):
+            if a is not None and not (a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("submit() needs C-contiguous float32 arrays (no hidden copies on the pipelined path)")
+        if depth is None:
+            raise ValueError("submit() needs the output array `depth`")
+        self._inflight[slot] = (params, depth, tri_ind, vertex_proj)       # keep the buffers alive until wait()
+        check(lib().fr_session_submit(self._h, int(slot), _fptr(params), params.shape[0], float(im_size), _fptr(depth),
+                                      _fptr(tri_ind), _fptr(vertex_proj)))
+
+    def wait(self, slot):
+        check(lib().fr_session_wait(self._h, int(slot)))
+        return self._inflight.pop(slot, None)
 
     def backward(self, depth_grad, params_grad=None):
         depth_grad = np.ascontiguousarray(depth_grad, np.float32)

@@ -119,7 +119,16 @@ void fr_session_destroy(fr_session* s);
  * Copies in, runs recon + projection + render, copies out, and waits for completion. */
 int fr_session_forward(fr_session* s, const float* params, int batch, float im_size, float* depth, float* tri_ind,
                        float* vertex_proj);
-/* depth_grad [batch,H,W,1] for the faces of the last fr_session_forward -> params_grad [batch,d]. */
+/* Pipelined flavour: a session has FR_SESSION_SLOTS independent slots (device staging + stream each).
+ * fr_session_submit enqueues copy-in, recon + projection + render and the copies out of one batch on `slot` and returns
+ * without waiting; fr_session_wait blocks until that batch's outputs are in the host buffers.  Alternating the slots
+ * overlaps the device->host copy of one batch with the kernels of the next (pinned host buffers required for the
+ * overlap; the host buffers of a slot must stay untouched until its wait).  fr_session_forward == submit + wait on slot 0. */
+#define FR_SESSION_SLOTS 2
+int fr_session_submit(fr_session* s, int slot, const float* params, int batch, float im_size, float* depth, float* tri_ind,
+                      float* vertex_proj);
+int fr_session_wait(fr_session* s, int slot);
+/* depth_grad [batch,H,W,1] for the faces of the last batch run on slot 0 (fr_session_forward) -> params_grad [batch,d]. */
 int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float* params_grad);
 /* counters: kernels launched by this library since load (for bench.py's gpu_launches) */
 unsigned long long fr_launch_count(void);

@@ -146,6 +146,29 @@ def test_session_host_buffers_match_tensor_path(bfm):
     sess.close()
 
 
+def test_session_pipelined_slots_match_synchronous(bfm):
+    """fr_session_submit / fr_session_wait: batches alternating over the two slots (different sizes, outputs in pinned
+    memory) give bit-identical results to the synchronous call, and a busy slot refuses a second submit."""
+    sess = fr("session").Session(bfm, 200, 200, max_batch=6, device=0)
+    batches = [fr("synth").sample_params_constrained(b, seed=40 + i) for i, b in enumerate((6, 3, 5, 1))]
+    want = [sess.forward(p, 200.0)[0].copy() for p in batches]
+    pins = [torch.empty((p.shape[0], 200, 200, 1), dtype=torch.float32).pin_memory() for p in batches]
+    pps = [torch.from_numpy(p.copy()).pin_memory() for p in batches]
+    for i, p in enumerate(pps):
+        slot = i % 2
+        if i >= 2:
+            sess.wait(slot)
+        sess.submit(slot, p.numpy(), 200.0, depth=pins[i].numpy())
+    with pytest.raises(ValueError):
+        sess.submit(0, pps[0].numpy(), 200.0, depth=pins[0].numpy())      # slot 0 is still in flight
+    sess.wait(0)
+    sess.wait(1)
+    sess.wait(1)                                                          # waiting on an idle slot is a no-op
+    for i in range(len(batches)):
+        assert pins[i].numpy().tobytes() == want[i].tobytes(), i
+    sess.close()
+
+
 def test_facerecnet_mirror(bfm):
     """The FaceRecNet geometry slice end to end: default pred_params -> depth_rendering_layer (network.py:300-308)."""
     net = fr("nets.network").FaceRecNet(mesh_data=bfm, batch_size=2, im_size=200, device=DEV)
