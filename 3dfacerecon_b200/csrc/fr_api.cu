@@ -195,7 +195,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
 size_t fr_render_workspace_bytes(int batch, int nver, int height, int width) {
   if (batch <= 0 || nver <= 0 || height <= 0 || width <= 0) return 0;
   return align_up(sizeof(unsigned long long) * (size_t)batch * height * width, kAlign) +   // visibility keys
-         align_up(sizeof(uint2) * (size_t)batch * nver, kAlign);                             // snapped vertices
+         align_up(sizeof(float4) * (size_t)batch * nver, kAlign);                            // vertex records
 }
 
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
@@ -217,21 +217,21 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* keys = static_cast<unsigned long long*>(workspace);
   const int npix = height * width;
-  uint2* snap = reinterpret_cast<uint2*>(static_cast<char*>(workspace) +
-                                         align_up(sizeof(unsigned long long) * (size_t)batch * npix, kAlign));
+  float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) +
+                                          align_up(sizeof(unsigned long long) * (size_t)batch * npix, kAlign));
 
   if (ntri > 0) {
-    // the snap pass also clears the visibility keys
-    raster_snap_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
-        vertex, snap, keys, nver, npix, width, height);
-    FR_LAUNCHED("raster_snap_kernel");
+    // the pack pass also clears the visibility keys
+    raster_pack_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
+        vertex, rec, keys, nver, npix, width, height);
+    FR_LAUNCHED("raster_pack_kernel");
     const unsigned gx = (unsigned)ceil_div(ntri, kRasterThreads);
     if (batch >= 8)
-      raster_keys_kernel<8><<<dim3(gx, ceil_div(batch, 8)), kRasterThreads, 0, st>>>(vertex, snap, tri, keys, batch, nver, ntri, height, width);
+      raster_keys_kernel<8><<<dim3(gx, ceil_div(batch, 8)), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
     else if (batch >= 3)
-      raster_keys_kernel<4><<<dim3(gx, ceil_div(batch, 4)), kRasterThreads, 0, st>>>(vertex, snap, tri, keys, batch, nver, ntri, height, width);
+      raster_keys_kernel<4><<<dim3(gx, ceil_div(batch, 4)), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
     else
-      raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(vertex, snap, tri, keys, batch, nver, ntri, height, width);
+      raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
     FR_LAUNCHED("raster_keys_kernel");
   } else {
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));

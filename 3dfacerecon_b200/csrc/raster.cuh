@@ -2,9 +2,9 @@
 //
 // Replaces the reference's CUDA op (render_depth_op.cu.cc:35-381, four kernels + 13 doubles of scratch
 // per triangle per face) and reproduces its CPU op (render_depth_op.cc:132-368) bit for bit:
-//   0. raster_snap_kernel    one thread per (vertex, face): biased ceil/floor pixel coordinates, 8 bytes.
-//   1. raster_keys_kernel    one thread per (triangle, face group): exact integer bbox cull on the snapped
-//                            vertices, survivors compacted in shared memory, then FP64 inside tests;
+//   0. raster_pack_kernel    (vertex, face) -> 16-byte record {x, y, z, snap code}; clears the visibility keys.
+//   1. raster_keys_kernel    one thread per (triangle, face group): exact integer bbox cull on the snap
+//                            codes, survivors compacted in shared memory, then FP64 inside tests;
 //                            visibility resolved with a packed (depth, ~index) u64 atomicMax -- order
 //                            independent, so no race (the reference's kernel 3 has one, .cu.cc:217-231).
 //   2. raster_resolve_kernel one thread per pixel: depth and index decoded from the key; normal and mean
@@ -29,24 +29,27 @@ __device__ __forceinline__ bool tri_vertex_index(float f, int nver, int* out) {
   return true;
 }
 
-// Snap every vertex of every face to its biased ceil/floor pixel coordinates once (raster_core.h "per-vertex pixel
-// snapping"): 8 bytes per vertex replace the 6 float gathers + min/max/ceil/floor per (triangle, face) of the cull.
-// The same pass clears the face's visibility keys (saves a separate memset pass over the key buffer).  Each thread
-// handles kSnapPerThread vertices, all loads issued before the first use: with one vertex per thread the kernel is
-// bound by CTA turnover (one DRAM/L2 latency per 256 vertices), not by bandwidth.
+// Vertex records: every (vertex, face) is repacked ONCE into 16 bytes  { x, y, z, snap code }  (raster_core.h "one-word
+// snap code").  The cull of a (triangle, face) pair then needs three 4-byte gathers of the code words, and a surviving
+// pair gets everything else with three 16-byte gathers of the very sectors the cull just pulled into L1 -- instead of
+// nine 4-byte gathers from the three coordinate planes.  The same pass clears the face's visibility keys.  Each thread
+// handles kSnapPerThread vertices with all loads issued before the first use (one vertex per thread is bound by CTA
+// turnover, not by bandwidth).
 constexpr int kSnapPerThread = 4;
 __global__ void __launch_bounds__(kRasterThreads)
-raster_snap_kernel(const float* __restrict__ vertex, uint2* __restrict__ snap, unsigned long long* __restrict__ keys,
+raster_pack_kernel(const float* __restrict__ vertex, float4* __restrict__ rec, unsigned long long* __restrict__ keys,
                    int nver, int npix, int width, int height) {
   const int b = blockIdx.y;
   const int base = blockIdx.x * (kRasterThreads * kSnapPerThread) + threadIdx.x;
   const float* vx = vertex + (size_t)b * 3 * nver;
-  float x[kSnapPerThread], y[kSnapPerThread];
+  float x[kSnapPerThread], y[kSnapPerThread], z[kSnapPerThread];
 #pragma unroll
   for (int j = 0; j < kSnapPerThread; ++j) {
     const int n = base + j * kRasterThreads;
-    x[j] = (n < nver) ? __ldg(vx + n) : 0.0f;
-    y[j] = (n < nver) ? __ldg(vx + nver + n) : 0.0f;
+    const bool ok = n < nver;
+    x[j] = ok ? __ldg(vx + n) : 0.0f;
+    y[j] = ok ? __ldg(vx + nver + n) : 0.0f;
+    z[j] = ok ? __ldg(vx + 2 * (size_t)nver + n) : 0.0f;
   }
   unsigned long long* kb = keys + (size_t)b * npix;
   for (int p = base; p < npix; p += gridDim.x * (kRasterThreads * kSnapPerThread)) {
@@ -57,25 +60,45 @@ raster_snap_kernel(const float* __restrict__ vertex, uint2* __restrict__ snap, u
 #pragma unroll
   for (int j = 0; j < kSnapPerThread; ++j) {
     const int n = base + j * kRasterThreads;
-    if (n < nver) {
-      const FrSnap s = fr_snap_vertex(x[j], y[j], width, height);
-      snap[(size_t)b * nver + n] = make_uint2(s.lo, s.hi);
-    }
+    if (n < nver)
+      rec[(size_t)b * nver + n] = make_float4(x[j], y[j], z[j], __uint_as_float(fr_snap_code(x[j], y[j], width, height)));
   }
 }
 
-// Phase A: one thread per (triangle, FPT faces): three 8-byte gathers of snapped vertices and a handful of packed
-// integer ops decide the reference's bounding-box cull exactly.  ~70 % of the sub-pixel BFM triangles contain no
-// pixel centre and stop here; the survivors are compacted into a shared-memory queue so that
-// Phase B gathers the float vertices and runs the FP64 edge setup + inside tests + atomicMax with every lane busy.
+// Phase B body shared by the single-pixel and multi-pixel queues: depth, FP64 edge setup, inside tests over the bbox,
+// packed (depth, ~index) atomicMax.
+__device__ __forceinline__ void raster_draw(const float4& r1, const float4& r2, const float4& r3, uint2 box, int tri_index,
+                                            unsigned long long* __restrict__ kb, int width, bool single) {
+  const float h = fr_tri_depth(r1.z, r2.z, r3.z);
+  if (!fr_depth_draws(h)) return;
+  FrTriEdge e;
+  fr_tri_edge_setup(r1.x, r1.y, r2.x, r2.y, r3.x, r3.y, &e);
+  const unsigned long long key = fr_pack_key(h, tri_index);
+  const int x0 = (int)(box.x & 0xFFFFu) - 1, y0 = (int)(box.x >> 16) - 1;
+  if (single) {
+    if (fr_point_in_tri(&e, x0, y0)) atomicMax(kb + (y0 * width + x0), key);
+  } else {
+    const int x1 = (int)(box.y & 0xFFFFu) - 1, y1 = (int)(box.y >> 16) - 1;
+    for (int y = y0; y <= y1; ++y)
+      for (int x = x0; x <= x1; ++x)
+        if (fr_point_in_tri(&e, x, y)) atomicMax(kb + (y * width + x), key);
+  }
+}
+
+// Phase A: one thread per (triangle, FPT faces): three 4-byte gathers of snap codes and a handful of packed integer ops
+// decide the reference's bounding-box cull exactly.  ~55 % of the sub-pixel BFM triangles contain no pixel centre and
+// stop here; the survivors are compacted into a shared-memory queue (single-pixel boxes from the front, the others from
+// the back) so that Phase B gathers the records and runs the FP64 edge setup + inside tests + atomicMax with every lane
+// busy and without a divergent pixel loop in the single-pixel warps.
+// All record indices are 32-bit: the API guarantees batch * 3 * nver < 2^31.
 template <int FPT>
 __global__ void __launch_bounds__(kRasterThreads)
-raster_keys_kernel(const float* __restrict__ vertex, const uint2* __restrict__ snap, const float* __restrict__ tri,
-                   unsigned long long* __restrict__ keys, int batch, int nver, int ntri, int height, int width) {
+raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri, unsigned long long* __restrict__ keys,
+                   int batch, int nver, int ntri, int height, int width) {
   __shared__ uint2 q_box[kRasterThreads * FPT];           // biased bbox (lo_min, hi_max)
   __shared__ unsigned short q_id[kRasterThreads * FPT];   // (local triangle << 3) | face slot
   __shared__ int s_idx[3][kRasterThreads];
-  __shared__ unsigned q_count;                           // single-pixel survivors | multi-pixel survivors << 16
+  __shared__ unsigned q_count;                            // single-pixel survivors | multi-pixel survivors << 16
   static_assert(FPT <= 8, "face slot is packed into 3 bits");
 
   const int tid = threadIdx.x;
@@ -94,34 +117,25 @@ raster_keys_kernel(const float* __restrict__ vertex, const uint2* __restrict__ s
   s_idx[2][tid] = p3;
 
   const uint32_t limit = (uint32_t)width | ((uint32_t)height << 16);
-  uint2 sa[FPT], sb[FPT], sc[FPT];
+  uint32_t e1[FPT], e2[FPT], e3[FPT];
 #pragma unroll
   for (int f = 0; f < FPT; ++f) {  // all gathers in flight before the first use
-    const uint2* sp = snap + (size_t)min(b0 + f, batch - 1) * nver;
-    sa[f] = __ldg(sp + p1);
-    sb[f] = __ldg(sp + p2);
-    sc[f] = __ldg(sp + p3);
+    const unsigned fb = (unsigned)min(b0 + f, batch - 1) * (unsigned)nver;
+    e1[f] = __float_as_uint(__ldg(&rec[fb + (unsigned)p1].w));
+    e2[f] = __float_as_uint(__ldg(&rec[fb + (unsigned)p2].w));
+    e3[f] = __float_as_uint(__ldg(&rec[fb + (unsigned)p3].w));
   }
   uint2 box[FPT];
-  unsigned keepmask = 0u;
+  unsigned keepmask = 0u, singlemask = 0u;
 #pragma unroll
   for (int f = 0; f < FPT; ++f) {
-    FrSnap a, b, c;
-    a.lo = sa[f].x; a.hi = sa[f].y;
-    b.lo = sb[f].x; b.hi = sb[f].y;
-    c.lo = sc[f].x; c.hi = sc[f].y;
-    const bool keep = fr_snap_keep(a, b, c, limit, &box[f].x, &box[f].y) && valid && (b0 + f < batch);
+    const bool keep = fr_code_keep(e1[f], e2[f], e3[f], limit, &box[f].x, &box[f].y) && valid && (b0 + f < batch);
     keepmask |= (keep ? 1u : 0u) << f;
+    singlemask |= ((box[f].x == box[f].y) ? 1u : 0u) << f;
   }
-  // Survivors whose bbox is a single pixel (about 60 % on the BFM mesh) are queued from the front, the others from the
-  // back: phase B then runs warps of single-pixel work without a pixel loop and confines the divergent bbox loops to the
-  // multi-pixel warps.  One packed shared atomic reserves both ranges.
-  unsigned singlemask = 0u;
-#pragma unroll
-  for (int f = 0; f < FPT; ++f) singlemask |= ((box[f].x == box[f].y) ? 1u : 0u) << f;
   singlemask &= keepmask;
   const unsigned multimask = keepmask & ~singlemask;
-  if (keepmask != 0u) {
+  if (keepmask != 0u) {     // one packed shared atomic reserves both queue ranges
     const unsigned got = atomicAdd(&q_count, (unsigned)__popc(singlemask) | ((unsigned)__popc(multimask) << 16));
     int ps = (int)(got & 0xFFFFu), pm = kRasterThreads * FPT - 1 - (int)(got >> 16);
 #pragma unroll
@@ -137,47 +151,24 @@ raster_keys_kernel(const float* __restrict__ vertex, const uint2* __restrict__ s
 
   const unsigned counts = q_count;
   const int n_single = (int)(counts & 0xFFFFu), n_multi = (int)(counts >> 16);
-  const size_t npix = (size_t)height * width;
-  // ---- phase B1: one pixel per survivor, two survivors per thread and trip so that 18 gathers are in flight at once
+  const int npix = height * width;
+  const int tri0 = blockIdx.x * kRasterThreads;
+  // ---- phase B1: one pixel per survivor; two survivors per thread and trip keep six 16-byte gathers in flight
   for (int i0 = tid; i0 < n_single; i0 += 2 * kRasterThreads) {
-    const int i1e = i0 + kRasterThreads;
-    const bool two = i1e < n_single;
-    const int ia = i0, ib = two ? i1e : i0;
-    const uint2 bxa = q_box[ia], bxb = q_box[ib];
-    const int ida = q_id[ia], idb = q_id[ib];
+    const int i1 = i0 + kRasterThreads;
+    const bool two = i1 < n_single;
+    const int ib = two ? i1 : i0;
+    const uint2 bxa = q_box[i0], bxb = q_box[ib];
+    const int ida = q_id[i0], idb = q_id[ib];
     const int tla = ida >> 3, tlb = idb >> 3;
-    const int ba = b0 + (ida & 7), bb_ = b0 + (idb & 7);
-    const float* vxa = vertex + (size_t)ba * 3 * nver;
-    const float* vxb = vertex + (size_t)bb_ * 3 * nver;
-    const int a1 = s_idx[0][tla], a2 = s_idx[1][tla], a3 = s_idx[2][tla];
-    const int c1 = s_idx[0][tlb], c2 = s_idx[1][tlb], c3 = s_idx[2][tlb];
-    float xa[3], ya[3], za[3], xb[3], yb[3], zb[3];
-    xa[0] = __ldg(vxa + a1); xa[1] = __ldg(vxa + a2); xa[2] = __ldg(vxa + a3);
-    ya[0] = __ldg(vxa + nver + a1); ya[1] = __ldg(vxa + nver + a2); ya[2] = __ldg(vxa + nver + a3);
-    za[0] = __ldg(vxa + 2 * (size_t)nver + a1); za[1] = __ldg(vxa + 2 * (size_t)nver + a2); za[2] = __ldg(vxa + 2 * (size_t)nver + a3);
-    xb[0] = __ldg(vxb + c1); xb[1] = __ldg(vxb + c2); xb[2] = __ldg(vxb + c3);
-    yb[0] = __ldg(vxb + nver + c1); yb[1] = __ldg(vxb + nver + c2); yb[2] = __ldg(vxb + nver + c3);
-    zb[0] = __ldg(vxb + 2 * (size_t)nver + c1); zb[1] = __ldg(vxb + 2 * (size_t)nver + c2); zb[2] = __ldg(vxb + 2 * (size_t)nver + c3);
-    {
-      const float h = fr_tri_depth(za[0], za[1], za[2]);
-      if (fr_depth_draws(h)) {
-        FrTriEdge e;
-        fr_tri_edge_setup(xa[0], ya[0], xa[1], ya[1], xa[2], ya[2], &e);
-        const int x = (int)(bxa.x & 0xFFFFu) - 1, y = (int)(bxa.x >> 16) - 1;
-        if (fr_point_in_tri(&e, x, y))
-          atomicMax(keys + ((size_t)ba * npix + (size_t)y * width + x), fr_pack_key(h, blockIdx.x * kRasterThreads + tla));
-      }
-    }
-    if (two) {
-      const float h = fr_tri_depth(zb[0], zb[1], zb[2]);
-      if (fr_depth_draws(h)) {
-        FrTriEdge e;
-        fr_tri_edge_setup(xb[0], yb[0], xb[1], yb[1], xb[2], yb[2], &e);
-        const int x = (int)(bxb.x & 0xFFFFu) - 1, y = (int)(bxb.x >> 16) - 1;
-        if (fr_point_in_tri(&e, x, y))
-          atomicMax(keys + ((size_t)bb_ * npix + (size_t)y * width + x), fr_pack_key(h, blockIdx.x * kRasterThreads + tlb));
-      }
-    }
+    const int ba = b0 + (ida & 7), bb = b0 + (idb & 7);
+    const unsigned fa = (unsigned)ba * (unsigned)nver, fb = (unsigned)bb * (unsigned)nver;
+    const float4 a1 = __ldg(rec + (fa + (unsigned)s_idx[0][tla])), a2 = __ldg(rec + (fa + (unsigned)s_idx[1][tla])),
+                 a3 = __ldg(rec + (fa + (unsigned)s_idx[2][tla]));
+    const float4 c1 = __ldg(rec + (fb + (unsigned)s_idx[0][tlb])), c2 = __ldg(rec + (fb + (unsigned)s_idx[1][tlb])),
+                 c3 = __ldg(rec + (fb + (unsigned)s_idx[2][tlb]));
+    raster_draw(a1, a2, a3, bxa, tri0 + tla, keys + (size_t)ba * npix, width, true);
+    if (two) raster_draw(c1, c2, c3, bxb, tri0 + tlb, keys + (size_t)bb * npix, width, true);
   }
   // ---- phase B2: survivors with several candidate pixels
   for (int j = tid; j < n_multi; j += kRasterThreads) {
@@ -186,23 +177,10 @@ raster_keys_kernel(const float* __restrict__ vertex, const uint2* __restrict__ s
     const int id = q_id[i];
     const int tl = id >> 3;
     const int b = b0 + (id & 7);
-    const int i1 = s_idx[0][tl], i2 = s_idx[1][tl], i3 = s_idx[2][tl];
-    const float* vx = vertex + (size_t)b * 3 * nver;
-    const float* vy = vx + nver;
-    const float* vz = vy + nver;
-    const float x1 = __ldg(vx + i1), x2 = __ldg(vx + i2), x3 = __ldg(vx + i3);
-    const float y1 = __ldg(vy + i1), y2 = __ldg(vy + i2), y3 = __ldg(vy + i3);
-    const float h = fr_tri_depth(__ldg(vz + i1), __ldg(vz + i2), __ldg(vz + i3));
-    if (!fr_depth_draws(h)) continue;
-    FrBBox bb;
-    fr_snap_bbox(bx.x, bx.y, &bb);
-    FrTriEdge e;
-    fr_tri_edge_setup(x1, y1, x2, y2, x3, y3, &e);
-    const unsigned long long key = fr_pack_key(h, blockIdx.x * kRasterThreads + tl);
-    unsigned long long* kb = keys + (size_t)b * npix;
-    for (int y = bb.y_min; y <= bb.y_max; ++y)
-      for (int x = bb.x_min; x <= bb.x_max; ++x)
-        if (fr_point_in_tri(&e, x, y)) atomicMax(kb + (size_t)y * width + x, key);
+    const unsigned fb = (unsigned)b * (unsigned)nver;
+    const float4 r1 = __ldg(rec + (fb + (unsigned)s_idx[0][tl])), r2 = __ldg(rec + (fb + (unsigned)s_idx[1][tl])),
+                 r3 = __ldg(rec + (fb + (unsigned)s_idx[2][tl]));
+    raster_draw(r1, r2, r3, bx, tri0 + tl, keys + (size_t)b * npix, width, false);
   }
 }
 

@@ -258,6 +258,35 @@ FR_HD bool fr_snap_keep(FrSnap a, FrSnap b, FrSnap c, uint32_t limit, uint32_t* 
   return (nonempty & inside_lo & inside_hi & G) == G;
 }
 
+// ---- one-word snap code --------------------------------------------------------------------------
+// floor-biased is always ceil-biased or ceil-biased - 1 (also after the clamp), so one 16-bit field per axis carries
+// both:  e = 2 * ceil_biased + (floor_biased == ceil_biased).  e is monotone in the pair (ceil, floor), hence
+//   min_i ceil_i = (min_i e_i) >> 1      and      max_i floor_i = floor of (max_i e_i),
+// so the cull needs one packed min3 and one packed max3 on the raw codes and a single decode per triangle.
+// Fields stay below 2^16 because biased values are < 2^15.  The code is the 4th word of the 16-byte vertex record the
+// rasterizer gathers (x, y, z, code).
+FR_HD uint32_t fr_snap_code(float x, float y, int width, int height) {
+  const FrSnap s = fr_snap_vertex(x, y, width, height);
+  const uint32_t same = ~(s.lo ^ s.hi);                                        // per field: all ones iff equal
+  const uint32_t fx = ((same & 0xFFFFu) == 0xFFFFu) ? 1u : 0u, fy = ((same >> 16) == 0xFFFFu) ? 1u : 0u;
+  return (s.lo << 1) | fx | (fy << 16);
+}
+
+// fr_snap_keep on snap codes: same decision, same biased bounding box.
+FR_HD bool fr_code_keep(uint32_t e1, uint32_t e2, uint32_t e3, uint32_t limit, uint32_t* lo_min, uint32_t* hi_max) {
+  const uint32_t G = 0x80008000u;
+  const uint32_t mn = fr_min3_u16x2(e1, e2, e3);
+  const uint32_t mx = fr_max3_u16x2(e1, e2, e3);
+  const uint32_t lo = (mn >> 1) & 0x7FFF7FFFu;
+  const uint32_t hi = ((mx >> 1) & 0x7FFF7FFFu) - 0x00010001u + (mx & 0x00010001u);  // flag clear => ceil_biased >= 1: no borrow
+  const uint32_t nonempty = (hi | G) - lo;
+  const uint32_t inside_lo = (lo | G) - 0x00010001u;
+  const uint32_t inside_hi = (limit | G) - hi;
+  *lo_min = lo;
+  *hi_max = hi;
+  return (nonempty & inside_lo & inside_hi & G) == G;
+}
+
 FR_HD void fr_snap_bbox(uint32_t lo_min, uint32_t hi_max, FrBBox* bb) {
   bb->x_min = (int)(lo_min & 0xFFFFu) - 1;
   bb->y_min = (int)(lo_min >> 16) - 1;

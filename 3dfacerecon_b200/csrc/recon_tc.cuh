@@ -55,8 +55,13 @@ struct Barriers {
 // Optional per-role cycle accounting (developer diagnostics, FR_TC_DEBUG=1): [role][slot] accumulated clock64 deltas of
 // block 0.  role 0 = converter warp 0, 1 = MMA issuer, 2 = epilogue warp 8, 3 = producer.
 __device__ unsigned long long g_tc_dbg[4][8];
+#ifdef FR_TC_INSTRUMENT   // compile with -DFR_TC_INSTRUMENT for the per-role cycle counters (costs issue slots in every role)
 #define TC_T(var) const long long var = dbg ? clock64() : 0
 #define TC_ACC(role, slot, t0, t1) do { if (dbg) g_tc_dbg[role][slot] += (unsigned long long)((t1) - (t0)); } while (0)
+#else
+#define TC_T(var) do { } while (0)
+#define TC_ACC(role, slot, t0, t1) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -161,6 +166,7 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __re
   constexpr int kACol0 = DBUFS * kDCols;
   constexpr int kAStages = (kTmemCols - kACol0) / (2 * kChunkK);
   static_assert(kAStages % 2 == 0 && kAStages <= kMaxAStages, "the A ring is handed over in two halves");
+  static_assert(kChunkGroups == 4, "the issuer spells out the two k8 steps of a chunk");
   // Hand-over granularity between the converters and the MMA issuer is HALF of the TMEM ring (kABatch chunks), in both
   // directions.  Measured on B200 (tools/mma_bench2.cu): a satisfied mbarrier wait costs the issuing thread ~130 cycles
   // and a tcgen05.commit ~200, while the six MMAs of one chunk execute in 192 cycles and the tensor pipe's queue is
@@ -170,14 +176,20 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __re
   const SmemLayout L = smem_layout(kg);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + L.bars);
   float* s_pose = reinterpret_cast<float*>(smem + L.pose);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast through a shuffle so the compiler treats the warp index (and every role branch on it) as warp-uniform:
+  // the MMA issuer's addresses and descriptors then live in uniform registers instead of being moved there per use
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int b0 = blockIdx.y * kN;
   const int nchunks = (kg + kChunkGroups - 1) / kChunkGroups;
   const uint32_t per_tile = 3u * (uint32_t)nchunks;
   const uint32_t my_tiles = (blockIdx.x < (unsigned)ntiles) ? ((uint32_t)(ntiles - 1 - blockIdx.x) / gridDim.x + 1u) : 0u;
   const uint32_t total = my_tiles * per_tile;                              // chunks this CTA processes
   const uint32_t total_padded = (total + kABatch - 1) / kABatch * kABatch;
+#ifdef FR_TC_INSTRUMENT
   const bool dbg = debug != 0 && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0;
+#else
+  (void)debug;
+#endif
 
   // ---- one-time setup: barriers, TMEM, poses (the resident B operand arrives by bulk copy)
   if (threadIdx.x == 0) {
@@ -231,55 +243,54 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __re
     }
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer (whole warp converged, one elected lane issues)
+    // The tensor pipe's queue is shallow and an M128 N64 K8 MMA executes in 32 cycles, so every instruction this warp
+    // spends between two MMAs shows up as an idle pipe: the loop nest is the static tile / coordinate / chunk order, the
+    // only running state is the chunk counter `it` (ring stage = it % kAStages), and the operands are plain sums of
+    // warp-uniform values.
     mbar_wait(&bars->b_full, 0);
     const uint64_t dhi0 = make_b_desc(smem_u32(smem + L.b_hi), 128u, L.sbo);
     const uint64_t dlo0 = make_b_desc(smem_u32(smem + L.b_lo), 128u, L.sbo);
     const int last_nk8 = (kg - (nchunks - 1) * kChunkGroups) / 2;
-    uint32_t it = 0, q = 0, c = 0, ci = 0, tcount = 0;
-    for (uint32_t bi = 0; bi * kABatch < total; ++bi) {
-      const uint32_t h = bi & 1u, ph = (bi >> 1) & 1u;
-      TC_T(t2);
-      mbar_wait(&bars->a_full[h], ph);                 // the converters have filled this half of the A ring
-      TC_T(t3);
-      TC_ACC(1, 1, t2, t3);
+    const uint32_t a_ring = tmem + kACol0;
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const uint32_t dbuf = tcount % DBUFS;
+      TC_T(t0);
+      mbar_wait(&bars->d_empty[dbuf], ((tcount / DBUFS) & 1u) ^ 1u);          // epilogue has drained this accumulator set
+      TC_T(t1);
+      TC_ACC(1, 0, t0, t1);
       tc_fence_after();
-#pragma unroll
-      for (int s = 0; s < kABatch; ++s) {
-        if (it < total) {
-          const uint32_t dbuf = tcount % DBUFS;
-          if (q == 0) {
-            TC_T(t0);
-            mbar_wait(&bars->d_empty[dbuf], ((tcount / DBUFS) & 1u) ^ 1u);   // epilogue has drained this accumulator set
-            TC_T(t1);
-            TC_ACC(1, 0, t0, t1);
+#pragma unroll 1
+      for (uint32_t c = 0; c < 3u; ++c) {
+        const uint32_t d_addr = tmem + dbuf * kDCols + c * kN;
+#pragma unroll 1
+        for (uint32_t ci = 0; ci < (uint32_t)nchunks; ++ci, ++it) {
+          const uint32_t s = it % kAStages, h = s / kABatch;
+          if (s % kABatch == 0u) {
+            TC_T(t2);
+            mbar_wait(&bars->a_full[h], (it / kAStages) & 1u);                 // the converters have filled this half of the A ring
+            TC_T(t3);
+            TC_ACC(1, 1, t2, t3);
             tc_fence_after();
           }
           if (elect_one()) {
-            const uint32_t a_hi = tmem + kACol0 + (h * kABatch + s) * (2 * kChunkK);
-            const uint32_t a_lo = a_hi + kChunkK;
-            const uint32_t d_addr = tmem + dbuf * kDCols + c * kN;
-            const uint64_t koff = (uint64_t)ci * (kChunkGroups / 2) * 16u;   // 256 bytes per k8 step, in 16-byte units
-            const int nk8 = (ci == (uint32_t)nchunks - 1u) ? last_nk8 : kChunkGroups / 2;
-#pragma unroll
-            for (int j = 0; j < kChunkGroups / 2; ++j) {
-              if (j < nk8) {
-                const uint64_t dhi = dhi0 + koff + 16u * j, dlo = dlo0 + koff + 16u * j;
-                mma_tf32_ts(d_addr, a_lo + 8 * j, dhi, (ci | (uint32_t)j) != 0u);
-                mma_tf32_ts(d_addr, a_hi + 8 * j, dlo, true);
-                mma_tf32_ts(d_addr, a_hi + 8 * j, dhi, true);
-              }
+            const uint32_t a_hi = a_ring + s * (2 * kChunkK), a_lo = a_hi + kChunkK;
+            const uint64_t koff = (uint64_t)(ci * ((kChunkGroups / 2) * 16u));  // 256 bytes per k8 step, in 16-byte units
+            const uint64_t dhi = dhi0 + koff, dlo = dlo0 + koff;
+            mma_tf32_ts(d_addr, a_lo, dhi, ci != 0u);
+            mma_tf32_ts(d_addr, a_hi, dlo, true);
+            mma_tf32_ts(d_addr, a_hi, dhi, true);
+            if (ci != (uint32_t)nchunks - 1u || last_nk8 == 2) {
+              mma_tf32_ts(d_addr, a_lo + 8, dhi + 16u, true);
+              mma_tf32_ts(d_addr, a_hi + 8, dlo + 16u, true);
+              mma_tf32_ts(d_addr, a_hi + 8, dhi + 16u, true);
             }
-            if (s == kABatch - 1) tc_commit(&bars->a_empty[h]);             // this half of the A ring is reusable
-            if (q == per_tile - 1u) tc_commit(&bars->d_full[dbuf]);         // all three accumulators of the tile complete
+            if (s % kABatch == kABatch - 1u) tc_commit(&bars->a_empty[h]);     // this half of the A ring is reusable
+            if (c == 2u && ci == (uint32_t)nchunks - 1u) tc_commit(&bars->d_full[dbuf]);   // all three accumulators complete
           }
           __syncwarp();
-          ++it; ++q; ++ci;
-          if (ci == (uint32_t)nchunks) { ci = 0; ++c; }
-          if (q == per_tile) { q = 0; c = 0; ++tcount; }
         }
       }
-      TC_T(t4);
-      TC_ACC(1, 2, t3, t4);
     }
   } else if (warp < kConvWarps) {
     // ================================================================== converters (two groups alternate chunks)
@@ -332,7 +343,9 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __re
         TC_ACC(0, 1, c1, c2);   // LDS + split
         TC_ACC(0, 2, c2, c3);   // wait a_empty
         TC_ACC(0, 3, c3, c4);   // STTM + wait::st
+#ifdef FR_TC_INSTRUMENT
         if (dbg) g_tc_dbg[0][7] += 1;
+#endif
       }
     }
   } else {

@@ -44,6 +44,13 @@ extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, con
         uint32_t lo_min, hi_max;
         const bool keep_snap = fr_snap_keep(fr_snap_vertex(vx[p1], vy[p1], width, height), fr_snap_vertex(vx[p2], vy[p2], width, height),
                                             fr_snap_vertex(vx[p3], vy[p3], width, height), limit, &lo_min, &hi_max);
+        {  // the one-word snap codes (4th word of the vertex record) must reproduce fr_snap_keep exactly
+          uint32_t lo2, hi2;
+          const bool keep_code = fr_code_keep(fr_snap_code(vx[p1], vy[p1], width, height), fr_snap_code(vx[p2], vy[p2], width, height),
+                                              fr_snap_code(vx[p3], vy[p3], width, height), limit, &lo2, &hi2);
+          if (keep_code != keep_snap) return 107;
+          if (keep_code && (lo2 != lo_min || hi2 != hi_max)) return 108;
+        }
         const bool has_nan = vx[p1] != vx[p1] || vx[p2] != vx[p2] || vx[p3] != vx[p3] || vy[p1] != vy[p1] || vy[p2] != vy[p2] || vy[p3] != vy[p3];
         if (has_nan) {
           if (keep_snap) return 103;
