@@ -71,15 +71,98 @@ int sm_count() {
 }
 
 template <int FB>
-int launch_recon_fwd_simt(const float* packed, const ReconWorkspace& w, float* vertex_proj, int batch, int nver,
+int launch_recon_fwd_simt(const float* packed, const ReconWorkspace& w, ReconOut out, int batch, int nver,
                           const BasisGeom& g, float im_size, unsigned flags, int gy, cudaStream_t st) {
   const int fbt = FB * gy;
   const size_t smem = sizeof(float) * (size_t)g.kpad * fbt;
   FR_CUDA(cudaFuncSetAttribute(recon_fwd_simt_kernel<FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(g.ntiles, ceil_div(batch, fbt)), block(kTileVerts, gy);
   recon_fwd_simt_kernel<FB><<<grid, block, smem, st>>>(reinterpret_cast<const float4*>(packed), w.coefT, w.pose,
-                                                       vertex_proj, batch, batch_padded(batch), nver, g.kg, im_size, flags);
+                                                       out, batch, batch_padded(batch), nver, g.kg, im_size, flags);
   FR_LAUNCHED("recon_fwd_simt_kernel");
+  return FR_OK;
+}
+
+// fr_recon_project_forward with a choice of outputs (planar tensor and / or rasterizer records, recon.cuh ReconOut)
+int recon_project_forward_impl(const float* params, const float* packed, const ReconOut& out, int batch, int nver,
+                               int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
+  if (batch == 0) return FR_OK;
+  FR_REQUIRE(params && packed && (out.planar || out.rec), "null pointer argument");
+  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp);
+  const ReconWorkspace w = carve_recon(workspace, batch, g);
+  if (int rc = check_workspace(workspace, workspace_bytes, w.bytes)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int bpad = batch_padded(batch);
+  const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
+
+  const bool use_tc = recon_tc_applicable(batch, g, flags);
+  recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
+                                                                 g.kpad, flags, w.coefT, w.pose,
+                                                                 use_tc ? static_cast<unsigned char*>(w.tc) : nullptr);
+  FR_LAUNCHED("recon_prep_kernel");
+
+  if (use_tc)
+    return launch_recon_fwd_tc(packed, w.coefT, w.pose, w.tc, out, batch, nver, g, im_size, flags, sm_count(), st);
+  if (batch <= 4) return launch_recon_fwd_simt<4>(packed, w, out, batch, nver, g, im_size, flags, 1, st);
+  if (batch <= 8) return launch_recon_fwd_simt<8>(packed, w, out, batch, nver, g, im_size, flags, 1, st);
+  const int gy = batch <= 16 ? 1 : (batch <= 32 ? 2 : 4);
+  return launch_recon_fwd_simt<16>(packed, w, out, batch, nver, g, im_size, flags, gy, st);
+}
+
+// fr_render_depth_forward; with records_ready the workspace already holds this batch's vertex records and cleared
+// visibility keys (written by the fused call's reconstruction epilogue), `vertex` may then be null unless normals or
+// texture are requested.
+int render_depth_forward_impl(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
+                              float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
+                              int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream,
+                              bool records_ready) {
+  FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
+             "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
+  // render_depth_op.cc:161-166: the reference refuses ntri >= 10M (its static scratch); nver < 2^24 keeps float indices exact
+  FR_REQUIRE(ntri < 10 * 1000 * 1000, "Too many triangular %d >= %d", ntri, 10 * 1000 * 1000);
+  FR_REQUIRE(nver <= (1 << 24), "nver %d exceeds the exact range of float triangle indices", nver);
+  FR_REQUIRE(height <= 32000 && width <= 32000 && (long long)height * width < (1ll << 31), "image too large");
+  FR_REQUIRE((long long)batch * 3 * nver < (1ll << 31), "batch * 3 * nver must stay below 2^31: split the batch");
+  if (batch == 0) return FR_OK;
+  FR_REQUIRE((vertex || records_ready) && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
+  FR_REQUIRE(vertex || (texture_image == nullptr && normal == nullptr), "normals / texture need the planar vertex tensor");
+  FR_REQUIRE(texture_image == nullptr || texture != nullptr, "texture_image requested without a texture");
+  FR_REQUIRE(texture_batch_stride == 0 || texture_batch_stride >= 3ll * nver, "texture_batch_stride must be 0 or >= 3*nver");
+  const size_t need = fr_render_workspace_bytes(batch, nver, height, width);
+  if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* keys = static_cast<unsigned long long*>(workspace);
+  const int npix = height * width;
+  float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) +
+                                          align_up(sizeof(unsigned long long) * (size_t)batch * npix, kAlign));
+
+  if (ntri > 0) {
+    if (!records_ready) {   // the pack pass also clears the visibility keys
+      raster_pack_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
+          vertex, rec, keys, nver, npix, width, height);
+      FR_LAUNCHED("raster_pack_kernel");
+    }
+    const unsigned gx = (unsigned)ceil_div(ntri, kRasterThreads);
+    if (batch >= 8)
+      raster_keys_kernel<8><<<dim3(gx, ceil_div(batch, 8)), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
+    else if (batch >= 3)
+      raster_keys_kernel<4><<<dim3(gx, ceil_div(batch, 4)), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
+    else
+      raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
+    FR_LAUNCHED("raster_keys_kernel");
+  } else if (!records_ready) {
+    FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
+  }
+  const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
+  if (texture_image != nullptr || normal != nullptr)
+    raster_resolve_kernel<true><<<rgrid, kRasterThreads, 0, st>>>(
+        keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
+  else
+    raster_resolve_kernel<false><<<rgrid, kRasterThreads, 0, st>>>(
+        keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
+  FR_LAUNCHED("raster_resolve_kernel");
   return FR_OK;
 }
 
@@ -129,28 +212,10 @@ size_t fr_recon_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_ex
 int fr_recon_project_forward(const float* params, const float* packed, float* vertex_proj, int batch, int nver,
                              int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                              size_t workspace_bytes, void* stream) {
-  if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
-  if (batch == 0) return FR_OK;
-  FR_REQUIRE(params && packed && vertex_proj, "null pointer argument");
-  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp);
-  const ReconWorkspace w = carve_recon(workspace, batch, g);
-  if (int rc = check_workspace(workspace, workspace_bytes, w.bytes)) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int bpad = batch_padded(batch);
-  const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
-
-  const bool use_tc = recon_tc_applicable(batch, g, flags);
-  recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
-                                                                 g.kpad, flags, w.coefT, w.pose,
-                                                                 use_tc ? static_cast<unsigned char*>(w.tc) : nullptr);
-  FR_LAUNCHED("recon_prep_kernel");
-
-  if (use_tc)
-    return launch_recon_fwd_tc(packed, w.coefT, w.pose, w.tc, vertex_proj, batch, nver, g, im_size, flags, sm_count(), st);
-  if (batch <= 4) return launch_recon_fwd_simt<4>(packed, w, vertex_proj, batch, nver, g, im_size, flags, 1, st);
-  if (batch <= 8) return launch_recon_fwd_simt<8>(packed, w, vertex_proj, batch, nver, g, im_size, flags, 1, st);
-  const int gy = batch <= 16 ? 1 : (batch <= 32 ? 2 : 4);
-  return launch_recon_fwd_simt<16>(packed, w, vertex_proj, batch, nver, g, im_size, flags, gy, st);
+  FR_REQUIRE(batch == 0 || vertex_proj != nullptr, "null pointer argument");
+  const ReconOut out = {vertex_proj, nullptr, 0, 0};
+  return recon_project_forward_impl(params, packed, out, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace,
+                                    workspace_bytes, stream);
 }
 
 int fr_recon_project_backward(const float* params, const float* packed, const float* vertex_grad, float* params_grad,
@@ -201,50 +266,8 @@ size_t fr_render_workspace_bytes(int batch, int nver, int height, int width) {
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                             float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
                             int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream) {
-  FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
-             "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
-  // render_depth_op.cc:161-166: the reference refuses ntri >= 10M (its static scratch); nver < 2^24 keeps float indices exact
-  FR_REQUIRE(ntri < 10 * 1000 * 1000, "Too many triangular %d >= %d", ntri, 10 * 1000 * 1000);
-  FR_REQUIRE(nver <= (1 << 24), "nver %d exceeds the exact range of float triangle indices", nver);
-  FR_REQUIRE(height <= 32000 && width <= 32000 && (long long)height * width < (1ll << 31), "image too large");
-  FR_REQUIRE((long long)batch * 3 * nver < (1ll << 31), "batch * 3 * nver must stay below 2^31: split the batch");
-  if (batch == 0) return FR_OK;
-  FR_REQUIRE(vertex && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
-  FR_REQUIRE(texture_image == nullptr || texture != nullptr, "texture_image requested without a texture");
-  FR_REQUIRE(texture_batch_stride == 0 || texture_batch_stride >= 3ll * nver, "texture_batch_stride must be 0 or >= 3*nver");
-  const size_t need = fr_render_workspace_bytes(batch, nver, height, width);
-  if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  unsigned long long* keys = static_cast<unsigned long long*>(workspace);
-  const int npix = height * width;
-  float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) +
-                                          align_up(sizeof(unsigned long long) * (size_t)batch * npix, kAlign));
-
-  if (ntri > 0) {
-    // the pack pass also clears the visibility keys
-    raster_pack_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
-        vertex, rec, keys, nver, npix, width, height);
-    FR_LAUNCHED("raster_pack_kernel");
-    const unsigned gx = (unsigned)ceil_div(ntri, kRasterThreads);
-    if (batch >= 8)
-      raster_keys_kernel<8><<<dim3(gx, ceil_div(batch, 8)), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
-    else if (batch >= 3)
-      raster_keys_kernel<4><<<dim3(gx, ceil_div(batch, 4)), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
-    else
-      raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
-    FR_LAUNCHED("raster_keys_kernel");
-  } else {
-    FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
-  }
-  const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
-  if (texture_image != nullptr || normal != nullptr)
-    raster_resolve_kernel<true><<<rgrid, kRasterThreads, 0, st>>>(
-        keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
-  else
-    raster_resolve_kernel<false><<<rgrid, kRasterThreads, 0, st>>>(
-        keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
-  FR_LAUNCHED("raster_resolve_kernel");
-  return FR_OK;
+  return render_depth_forward_impl(vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver,
+                                   ntri, height, width, workspace, workspace_bytes, stream, false);
 }
 
 int fr_render_depth_backward(const float* depth_grad, const float* tri, const float* tri_ind, float* vertex_grad,
@@ -272,16 +295,25 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
                             float* tri_ind, int batch, int nver, int ntri, int ndim_shape, int ndim_exp, int height,
                             int width, float im_size, unsigned flags, void* workspace, size_t workspace_bytes,
                             void* stream) {
+  FR_REQUIRE(batch >= 0 && nver > 0 && height > 0 && width > 0 && height <= 32000 && width <= 32000 &&
+                 (long long)height * width < (1ll << 31),
+             "bad dimensions batch=%d nver=%d height=%d width=%d", batch, nver, height, width);
+  if (batch == 0) return FR_OK;
   const size_t rb = fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp);
   const size_t need = rb + fr_render_workspace_bytes(batch, nver, height, width);
-  if (batch > 0) {
-    if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
-  }
-  if (int rc = fr_recon_project_forward(params, packed, vertex_proj, batch, nver, ndim_shape, ndim_exp, im_size, flags,
-                                        workspace, rb, stream))
+  if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
+  // The reconstruction epilogue writes the rasterizer's vertex records straight into the render workspace (same carve-up
+  // as render_depth_forward_impl: keys first, records after), so the repack pass over vertex_proj disappears;
+  // vertex_proj itself is optional here.
+  char* rws = static_cast<char*>(workspace) + rb;
+  const size_t key_bytes = sizeof(unsigned long long) * (size_t)batch * height * width;
+  FR_CUDA(cudaMemsetAsync(rws, 0, key_bytes, static_cast<cudaStream_t>(stream)));
+  const ReconOut out = {vertex_proj, reinterpret_cast<float4*>(rws + align_up(key_bytes, kAlign)), width, height};
+  if (int rc = recon_project_forward_impl(params, packed, out, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace, rb,
+                                          stream))
     return rc;
-  return fr_render_depth_forward(vertex_proj, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height,
-                                 width, workspace ? static_cast<char*>(workspace) + rb : nullptr, workspace_bytes - rb, stream);
+  return render_depth_forward_impl(vertex_proj, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height,
+                                   width, rws, workspace_bytes - rb, stream, true);
 }
 
 // ------------------------------------------------------------------------------------------------ session
@@ -390,7 +422,7 @@ int fr_session_submit(fr_session* s, int slot, const float* params, int batch, f
   const int d = FR_NDIM_POSE + s->ks + s->ke;
   const size_t npix = (size_t)s->height * s->width;
   FR_CUDA(cudaMemcpyAsync(sl.params, params, sizeof(float) * (size_t)batch * d, cudaMemcpyHostToDevice, sl.stream));
-  if (int rc = fr_recon_render_forward(sl.params, s->packed, s->tri, sl.vertex, sl.depth, sl.tri_ind, batch, s->nver, s->ntri,
+  if (int rc = fr_recon_render_forward(sl.params, s->packed, s->tri, vertex_proj ? sl.vertex : nullptr, sl.depth, sl.tri_ind, batch, s->nver, s->ntri,
                                        s->ks, s->ke, s->height, s->width, im_size, s->flags, sl.ws, s->ws_bytes, sl.stream))
     return rc;
   FR_CUDA(cudaMemcpyAsync(depth, sl.depth, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, sl.stream));

@@ -265,11 +265,27 @@ FR_HD bool fr_snap_keep(FrSnap a, FrSnap b, FrSnap c, uint32_t limit, uint32_t* 
 // so the cull needs one packed min3 and one packed max3 on the raw codes and a single decode per triangle.
 // Fields stay below 2^16 because biased values are < 2^15.  The code is the 4th word of the 16-byte vertex record the
 // rasterizer gathers (x, y, z, code).
-FR_HD uint32_t fr_snap_code(float x, float y, int width, int height) {
+FR_HD uint32_t fr_snap_code_literal(float x, float y, int width, int height) {   // the definition, spelled out
   const FrSnap s = fr_snap_vertex(x, y, width, height);
   const uint32_t same = ~(s.lo ^ s.hi);                                        // per field: all ones iff equal
   const uint32_t fx = ((same & 0xFFFFu) == 0xFFFFu) ? 1u : 0u, fy = ((same >> 16) == 0xFFFFu) ? 1u : 0u;
   return (s.lo << 1) | fx | (fy << 16);
+}
+
+// The same code in a handful of operations per axis.  Inside (-1, extent): floor_biased = floor(v) + 1 and
+// ceil_biased = floor_biased + (v is not an integer), so e = 2 floor(v) + 4 - (v is an integer); at or below -1 (and for
+// NaN) both clamp to 0 -> e = 1; at or above extent both clamp to extent + 1 -> e = 2 extent + 3.
+// tests/host_emul checks it against fr_snap_code_literal over a sweep of float bit patterns.
+FR_HD uint32_t fr_snap_code_axis(float v, int extent) {
+  const float t = floorf(v);
+  uint32_t e = (uint32_t)(2 * (int)t + 4) - ((t == v) ? 1u : 0u);
+  if (!(v > -1.0f)) e = 1u;
+  if (v >= (float)extent) e = 2u * (uint32_t)extent + 3u;
+  return e;
+}
+
+FR_HD uint32_t fr_snap_code(float x, float y, int width, int height) {
+  return fr_snap_code_axis(x, width) | (fr_snap_code_axis(y, height) << 16);
 }
 
 // fr_snap_keep on snap codes: same decision, same biased bounding box.

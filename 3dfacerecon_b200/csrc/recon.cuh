@@ -13,6 +13,7 @@
 #define FR_RECON_CUH_
 
 #include "fr_common.cuh"
+#include "raster_core.h"
 
 namespace fr {
 
@@ -127,9 +128,19 @@ recon_prep_kernel(const float* __restrict__ params, int dparam, int batch, int b
   }
 }
 
+// Where the forward kernels put a projected vertex.  `planar` is the reference's vertex_proj [B,3,N] tensor
+// (nets/network.py:171); `rec` is the rasterizer's 16-byte vertex record array [B][N] {x, y, z, snap code}
+// (raster.cuh): the fused params -> depth-map call has the reconstruction epilogue write the records directly, which
+// saves the rasterizer's repack pass over the vertex tensor.  Either may be null.
+struct ReconOut {
+  float* planar;
+  float4* rec;
+  int width, height;   // image size the snap codes refer to (rec != nullptr)
+};
+
 // Projection + y flip of one reconstructed vertex (nets/network.py:163-169).
 __device__ __forceinline__ void project_store(const float* __restrict__ P, float x, float y, float z, float im_size,
-                                              unsigned flags, float* __restrict__ out, size_t nver, size_t n) {
+                                              unsigned flags, const ReconOut& out, int b, int nver, int n) {
   const float X = fmaf(P[2], z, fmaf(P[1], y, P[0] * x)) + P[9];
   float Y = fmaf(P[5], z, fmaf(P[4], y, P[3] * x)) + P[10];
   const float Z = fmaf(P[8], z, fmaf(P[7], y, P[6] * x)) + P[11];
@@ -137,9 +148,14 @@ __device__ __forceinline__ void project_store(const float* __restrict__ P, float
     Y = __fsub_rn(im_size, Y);                        // S - y
     if (!(flags & FR_YFLIP_S_Y)) Y = __fsub_rn(Y, 1.0f);  // ... - 1
   }
-  out[n] = X;
-  out[nver + n] = Y;
-  out[2 * nver + n] = Z;
+  if (out.planar != nullptr) {
+    float* o = out.planar + (size_t)b * 3 * nver;
+    o[n] = X;
+    o[(size_t)nver + n] = Y;
+    o[2 * (size_t)nver + n] = Z;
+  }
+  if (out.rec != nullptr)
+    out.rec[(size_t)b * nver + n] = make_float4(X, Y, Z, __uint_as_float(fr_snap_code(X, Y, out.width, out.height)));
 }
 
 // ---------------------------------------------------------------------------------------------- forward (SIMT)
@@ -149,7 +165,7 @@ __device__ __forceinline__ void project_store(const float* __restrict__ P, float
 template <int FB>
 __global__ void __launch_bounds__(512)
 recon_fwd_simt_kernel(const float4* __restrict__ packed, const float* __restrict__ coefT, const float* __restrict__ pose,
-                      float* __restrict__ vertex_proj, int batch, int bpad, int nver, int kg, float im_size,
+                      ReconOut out, int batch, int bpad, int nver, int kg, float im_size,
                       unsigned flags) {
   extern __shared__ __align__(16) float fr_smem[];
   const int gy = blockDim.y;
@@ -219,8 +235,7 @@ recon_fwd_simt_kernel(const float4* __restrict__ packed, const float* __restrict
     for (int j = 0; j < FB; ++j) {
       const int b = b0 + threadIdx.y * FB + j;
       if (b < batch)
-        project_store(pose + (size_t)b * kPoseStride, acc[0][j], acc[1][j], acc[2][j], im_size, flags,
-                      vertex_proj + (size_t)b * 3 * nver, (size_t)nver, (size_t)n);
+        project_store(pose + (size_t)b * kPoseStride, acc[0][j], acc[1][j], acc[2][j], im_size, flags, out, b, nver, n);
     }
   }
 }

@@ -3,15 +3,15 @@
 //
 //   V[b, (c,n)] = sum_k P[(c,n), k] * coef[b, k]        M = 128 vertices per tile (x3 coordinates), N = 64 faces, K = kpad
 //
-// Per CTA (persistent, one per SM, 14 warps):
-//   warp 12  producer   cp.async.bulk (TMA engine): the resident B operand (pre-split coefficients of this batch tile) once,
+// Per CTA (persistent, one per SM, 18 warps):
+//   warp 16  producer   cp.async.bulk (TMA engine): the resident B operand (pre-split coefficients of this batch tile) once,
 //                       then 8 KB basis chunks (16 k-columns x 128 rows, contiguous in the packed layout) into an
 //                       8-stage shared-memory ring, completion on mbarriers
 //   warps 0-7 converter two groups of 4 warps alternate chunks: shared memory -> registers, split every fp32 value into
 //                       hi = top 19 bits (exact tf32) and lo = x - hi, tcgen05.st both into a TMEM ring as the A operand
-//   warp 13  MMA issuer one thread: per k8 step  D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (tcgen05.mma kind::tf32, A from
+//   warp 17  MMA issuer one thread: per k8 step  D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (tcgen05.mma kind::tf32, A from
 //                       TMEM, B = pre-split coefficients resident in shared memory in the canonical K-major layout)
-//   warps 8-11 epilogue tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices), (f.R).v + t, y flip,
+//   warps 8-15 epilogue tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices), (f.R).v + t, y flip,
 //                       coalesced stores of vertex_proj; double-buffered against the next tile's MMAs
 // The hi/lo split follows the 3xTF32 scheme (drop lo.lo): relative error ~2^-21 per product instead of 2^-11.
 #ifndef FR_RECON_TC_CUH_
@@ -32,8 +32,9 @@ constexpr int kRawStages = 8;        // shared-memory ring of raw basis chunks (
 constexpr int kDCols = 3 * kN;       // one accumulator set: x, y, z
 constexpr int kTmemCols = 512;       // [0, DBUFS*192): accumulator sets; the rest: ring of split A chunks (32 columns each)
 constexpr int kMaxAStages = 10;
-constexpr int kThreads = 14 * 32;
-constexpr int kConvWarps = 8, kEpiWarp0 = 8, kProducerWarp = 12, kMmaWarp = 13;
+constexpr int kEpiWarps = 8;         // two per TMEM lane quarter, each draining half of the tile's faces
+constexpr int kConvWarps = 8, kEpiWarp0 = 8, kProducerWarp = kEpiWarp0 + kEpiWarps, kMmaWarp = kProducerWarp + 1;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
 constexpr uint32_t kChunkBytes = kChunkGroups * kTileVerts * 16;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), K-major A/B,
@@ -161,7 +162,7 @@ __host__ __device__ inline SmemLayout smem_layout(int kg) {
 template <int DBUFS>
 __global__ void __launch_bounds__(kThreads, 1)
 recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __restrict__ bsplit, const float* __restrict__ pose,
-                    float* __restrict__ vertex_proj, int batch, int nver, int kg, int ntiles, float im_size,
+                    ReconOut out, int batch, int nver, int kg, int ntiles, float im_size,
                     unsigned flags, int debug) {
   constexpr int kACol0 = DBUFS * kDCols;
   constexpr int kAStages = (kTmemCols - kACol0) / (2 * kChunkK);
@@ -201,7 +202,7 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __re
       mbar_init(&bars->a_full[i], 4 * kABatch);  // 4 converter warps per chunk
       mbar_init(&bars->a_empty[i], 1);
       mbar_init(&bars->d_full[i], 1);
-      mbar_init(&bars->d_empty[i], 4);
+      mbar_init(&bars->d_empty[i], kEpiWarps);
     }
     mbar_init(&bars->b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -350,7 +351,8 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __re
     }
   } else {
     // ================================================================== epilogue (warps 8..11)
-    const int qd = warp - kEpiWarp0;                              // TMEM lane quarter == warp % 4
+    const int qd = (warp - kEpiWarp0) & 3;                        // TMEM lane quarter == warp % 4
+    const int jb0 = ((warp - kEpiWarp0) >> 2) * (kN / (kEpiWarps / 4)), jb1 = jb0 + kN / (kEpiWarps / 4);   // this warp's faces
     const int v = qd * 32 + lane;
     const uint32_t lane_field = (uint32_t)(qd * 32) << 16;
     uint32_t tcount = 0;
@@ -363,7 +365,7 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __re
       tc_fence_after();
       const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
 #pragma unroll 1
-      for (int jb = 0; jb < kN; jb += 16) {
+      for (int jb = jb0; jb < jb1; jb += 16) {
         float x[16], y[16], z[16];
         tmem_ld16(d_addr + 0 * kN + jb, x);
         tmem_ld16(d_addr + 1 * kN + jb, y);
@@ -377,7 +379,7 @@ recon_fwd_tc_kernel(const float4* __restrict__ packed, const unsigned char* __re
               const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPoseStride);
               const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
               const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
-              project_store(P, x[j], y[j], z[j], im_size, flags, vertex_proj + (size_t)b * 3 * nver, (size_t)nver, (size_t)n);
+              project_store(P, x[j], y[j], z[j], im_size, flags, out, b, nver, n);
             }
           }
         }
@@ -433,7 +435,7 @@ inline bool recon_tc_applicable(int batch, const BasisGeom& g, unsigned) {
   return batch > 8;
 }
 
-inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const float* pose, void* tc_ws, float* vertex_proj,
+inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const float* pose, void* tc_ws, ReconOut out,
                                int batch, int nver, const BasisGeom& g, float im_size, unsigned flags, int nsm,
                                cudaStream_t st) {
   static const int dbufs = env_int("FR_TC_DBUFS", 2);
@@ -448,11 +450,11 @@ inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const fl
   if (dbufs == 1) {
     FR_CUDA(cudaFuncSetAttribute(tc::recon_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     tc::recon_fwd_tc_kernel<1><<<dim3(ctas, nbt), tc::kThreads, L.total, st>>>(
-        reinterpret_cast<const float4*>(packed), bsplit, pose, vertex_proj, batch, nver, g.kg, g.ntiles, im_size, flags, debug);
+        reinterpret_cast<const float4*>(packed), bsplit, pose, out, batch, nver, g.kg, g.ntiles, im_size, flags, debug);
   } else {
     FR_CUDA(cudaFuncSetAttribute(tc::recon_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     tc::recon_fwd_tc_kernel<2><<<dim3(ctas, nbt), tc::kThreads, L.total, st>>>(
-        reinterpret_cast<const float4*>(packed), bsplit, pose, vertex_proj, batch, nver, g.kg, g.ntiles, im_size, flags, debug);
+        reinterpret_cast<const float4*>(packed), bsplit, pose, out, batch, nver, g.kg, g.ntiles, im_size, flags, debug);
   }
   FR_LAUNCHED("recon_fwd_tc_kernel");
   return FR_OK;

@@ -100,7 +100,10 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
 int fr_render_depth_backward(const float* depth_grad, const float* tri, const float* tri_ind, float* vertex_grad,
                              int batch, int nver, int ntri, int height, int width, void* stream);
 
-/* ---- fused convenience: params -> depth map (the north-star path in one call) ------------------- */
+/* ---- fused: params -> depth map (the north-star path in one call) -------------------------------
+ * Same results as fr_recon_project_forward followed by fr_render_depth_forward (depth + tri_ind only), but the
+ * reconstruction epilogue writes the rasterizer's vertex records directly, so the rasterizer's repack pass over the
+ * vertex tensor is skipped.  vertex_proj [batch,3,nver] is optional here (NULL = do not materialise it). */
 size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width);
 int fr_recon_render_forward(const float* params, const float* packed, const float* tri, float* vertex_proj, float* depth,
                             float* tri_ind, int batch, int nver, int ntri, int ndim_shape, int ndim_exp, int height,

@@ -111,3 +111,30 @@ extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, con
   }
   return 0;
 }
+
+// fr_snap_code (the short form the kernels run) against its literal definition: every `stride`-th float bit pattern
+// plus the neighbourhood of every integer in [-3, extent + 3].  Returns the number of mismatches.
+extern "C" long long fr_emul_check_snap_code(int width, int height, unsigned stride) {
+  long long bad = 0;
+  auto one = [&](float v) {
+    if (fr_snap_code(v, v, width, height) != fr_snap_code_literal(v, v, width, height)) ++bad;
+    if (fr_snap_code(v, 0.5f, width, height) != fr_snap_code_literal(v, 0.5f, width, height)) ++bad;
+  };
+  for (unsigned long long u = 0; u < (1ull << 32); u += stride) {
+    union { uint32_t u; float f; } c;
+    c.u = (uint32_t)u;
+    one(c.f);
+  }
+  const int top = (width > height ? width : height) + 3;
+  for (int i = -3; i <= top; ++i) {
+    union { uint32_t u; float f; } c;
+    c.f = (float)i;
+    for (int d = -2; d <= 2; ++d) {
+      union { uint32_t u; float f; } e;
+      e.u = c.u + (uint32_t)d;
+      one(e.f);
+    }
+    one((float)i + 0.5f);
+  }
+  return bad;
+}

@@ -146,6 +146,36 @@ def test_session_host_buffers_match_tensor_path(bfm):
     sess.close()
 
 
+@pytest.mark.parametrize("B", [3, 20])
+def test_fused_call_matches_separate_calls(bfm, B):
+    """fr_recon_render_forward (records written by the reconstruction epilogue, SIMT path at B=3 and tcgen05 path at
+    B=20) == fr_recon_project_forward + fr_render_depth_forward bit for bit, with and without the vertex tensor."""
+    lib, check = fr("_lib").lib(), fr("_lib").check
+    p = fr("synth").sample_params_constrained(B, seed=60 + B)
+    dm, vp = _gpu_vertices(bfm, p, 200)
+    image = torch.empty((B, 200, 200, 3), device=DEV)
+    want = fr("rendering_layer.ops").render_depth(torch.from_numpy(vp).to(DEV), dm.tri, dm.vertex_code.unsqueeze(0).expand(B, -1, -1), image)
+    pt = torch.from_numpy(p).to(DEV)
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, dm.ndim_shape, dm.ndim_exp, 200, 200), dtype=torch.uint8, device=DEV)
+    sp = torch.cuda.current_stream().cuda_stream
+    for with_vertex in (True, False):
+        ws.fill_(0xAB)                                                    # stale workspace contents must not matter
+        vertex = torch.full((B, 3, dm.nver), float("nan"), device=DEV)
+        depth = torch.empty((B, 200, 200, 1), device=DEV)
+        tri_ind = torch.empty((B, 200, 200, 1), device=DEV)
+        check(lib.fr_recon_render_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(),
+                                          vertex.data_ptr() if with_vertex else None, depth.data_ptr(), tri_ind.data_ptr(), B,
+                                          dm.nver, dm.ntri, dm.ndim_shape, dm.ndim_exp, 200, 200, 200.0, dm.run_flags,
+                                          ws.data_ptr(), ws.numel(), sp))
+        torch.cuda.synchronize()
+        assert depth.cpu().numpy().tobytes() == want[0].cpu().numpy().tobytes(), with_vertex
+        assert tri_ind.cpu().numpy().tobytes() == want[3].cpu().numpy().tobytes(), with_vertex
+        if with_vertex:
+            assert vertex.cpu().numpy().tobytes() == vp.tobytes()
+        else:
+            assert bool(torch.isnan(vertex).all())                         # untouched
+
+
 def test_session_pipelined_slots_match_synchronous(bfm):
     """fr_session_submit / fr_session_wait: batches alternating over the two slots (different sizes, outputs in pinned
     memory) give bit-identical results to the synchronous call, and a busy slot refuses a second submit."""

@@ -92,3 +92,13 @@ def test_emulation_extreme_coordinates(emul):
         got = emul(v, t, tex, 8, 8, seed)
         for g, w in zip(got, want):
             assert g.tobytes() == w.tobytes()
+
+
+def test_snap_code_short_form_matches_definition(emul):
+    """The few-instruction snap code the kernels compute == its literal definition (per-vertex biased ceil/floor, clamped),
+    over every 509-th float bit pattern (NaNs, infinities, denormals, huge values included) and around every integer."""
+    lib = emul.lib
+    lib.fr_emul_check_snap_code.restype = ctypes.c_longlong
+    lib.fr_emul_check_snap_code.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint]
+    for w, h in ((200, 200), (1, 7), (31999, 640)):
+        assert lib.fr_emul_check_snap_code(w, h, 509) == 0, (w, h)
