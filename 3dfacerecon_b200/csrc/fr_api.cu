@@ -9,6 +9,7 @@
 #include "raster.cuh"
 #include "recon.cuh"
 #include "recon_tc.cuh"
+#include "recon_f16.cuh"
 
 using namespace fr;
 
@@ -21,7 +22,9 @@ struct ReconWorkspace {
   float* pose;    // [bpad][24]
   float* G;       // [bpad][kpad]
   float* dt;      // [bpad][4]
-  void* tc;       // tensor-core path scratch (split coefficients)
+  void* tc;       // 3xTF32 tensor-core path scratch (split coefficients)
+  void* bsplit16; // fp16-pair tensor-core path: coefficient operands per 64-face batch tile
+  float* pose16;  // ... and [bpad][16] scaled pose
   size_t bytes;
 };
 
@@ -39,6 +42,8 @@ ReconWorkspace carve_recon(void* base, int batch, const BasisGeom& g) {
   w.G = static_cast<float*>(take(sizeof(float) * (size_t)bpad * g.kpad));
   w.dt = static_cast<float*>(take(sizeof(float) * (size_t)bpad * 4));
   w.tc = take(recon_tc_workspace_bytes(batch, g));
+  w.bsplit16 = take(recon_f16_bsplit_bytes(batch, g));
+  w.pose16 = static_cast<float*>(take(recon_f16_pose_bytes(batch)));
   w.bytes = off;
   return w;
 }
@@ -97,7 +102,17 @@ int recon_project_forward_impl(const float* params, const float* packed, const R
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
 
-  const bool use_tc = recon_tc_applicable(batch, g, flags);
+  // dispatch: fp16-pair tcgen05 kernel above 8 faces (FR_RECON_PATH = simt | tf32 | f16 overrides it, for A/B comparisons)
+  const int ov = recon_path_override();
+  const size_t key_bytes_face = out.keys ? sizeof(unsigned long long) * (size_t)out.width * out.height : 0;
+  if (recon_f16_fits(g) && (ov == 3 || (ov == 0 && batch > 8))) {
+    const bool fold = out.keys != nullptr && key_bytes_face % 16 == 0;     // the kernel clears the keys itself, 16 bytes at a time
+    if (out.keys != nullptr && !fold) FR_CUDA(cudaMemsetAsync(out.keys, 0, key_bytes_face * batch, st));
+    return launch_recon_fwd_f16(params, packed, w.bsplit16, w.pose16, out, batch, nver, g, im_size, flags, sm_count(), st,
+                                fold ? out.keys : nullptr, fold ? (int)(key_bytes_face / 16) : 0);
+  }
+  if (out.keys != nullptr) FR_CUDA(cudaMemsetAsync(out.keys, 0, key_bytes_face * batch, st));
+  const bool use_tc = ov == 2 && recon_tc_applicable(batch, g, flags);
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
                                                                  g.kpad, flags, w.coefT, w.pose,
                                                                  use_tc ? static_cast<unsigned char*>(w.tc) : nullptr);
@@ -200,6 +215,21 @@ int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, i
   pack_basis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       mu, pc_shape, pc_exp, nver, ndim_shape, ndim_exp, g.kg, g.ntiles, layout_flags, reinterpret_cast<float4*>(packed));
   FR_LAUNCHED("pack_basis_kernel");
+  // fp16-pair section: column maxima -> power-of-two column scales -> hi/lo operand tiles
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* base = reinterpret_cast<unsigned char*>(packed);
+  float* scale = reinterpret_cast<float*>(base + g.scale_offset());
+  FR_CUDA(cudaMemsetAsync(scale, 0, sizeof(float) * g.kpad16, st));
+  f16::basis_colmax_kernel<<<(unsigned)(((size_t)3 * nver + 511) / 512), 256, 0, st>>>(mu, pc_shape, pc_exp, nver, ndim_shape, ndim_exp,
+                                                                                     reinterpret_cast<unsigned*>(scale));
+  FR_LAUNCHED("basis_colmax_kernel");
+  f16::basis_colscale_kernel<<<ceil_div(g.kpad16, 256), 256, 0, st>>>(scale, g.kreal, g.kpad16);
+  FR_LAUNCHED("basis_colscale_kernel");
+  const size_t pieces = (size_t)g.ntiles * 3 * g.nch16 * 2 * kTileVerts;
+  f16::pack_basis_f16_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(mu, pc_shape, pc_exp, scale, nver, ndim_shape, ndim_exp,
+                                                                              g.nch16, g.ntiles, layout_flags,
+                                                                              reinterpret_cast<uint4*>(base + g.f16_offset()));
+  FR_LAUNCHED("pack_basis_f16_kernel");
   return FR_OK;
 }
 
@@ -213,7 +243,7 @@ int fr_recon_project_forward(const float* params, const float* packed, float* ve
                              int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                              size_t workspace_bytes, void* stream) {
   FR_REQUIRE(batch == 0 || vertex_proj != nullptr, "null pointer argument");
-  const ReconOut out = {vertex_proj, nullptr, 0, 0};
+  const ReconOut out = {vertex_proj, nullptr, 0, 0, nullptr};
   return recon_project_forward_impl(params, packed, out, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace,
                                     workspace_bytes, stream);
 }
@@ -307,8 +337,8 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
   // vertex_proj itself is optional here.
   char* rws = static_cast<char*>(workspace) + rb;
   const size_t key_bytes = sizeof(unsigned long long) * (size_t)batch * height * width;
-  FR_CUDA(cudaMemsetAsync(rws, 0, key_bytes, static_cast<cudaStream_t>(stream)));
-  const ReconOut out = {vertex_proj, reinterpret_cast<float4*>(rws + align_up(key_bytes, kAlign)), width, height};
+  const ReconOut out = {vertex_proj, reinterpret_cast<float4*>(rws + align_up(key_bytes, kAlign)), width, height,
+                        reinterpret_cast<unsigned long long*>(rws)};
   if (int rc = recon_project_forward_impl(params, packed, out, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace, rb,
                                           stream))
     return rc;

@@ -60,11 +60,21 @@ constexpr int kTileVerts = 128;  // vertices per tile == TMEM lanes == threads o
 struct BasisGeom {
   int nver, ks, ke;
   int kreal;   // ks + ke + 1 (the extra column is the mean, coefficient 1)
-  int kpad;    // kreal rounded up to 8 (one tf32 MMA K step)
+  int kpad;    // kreal rounded up to 8 (fp32 section: float4 groups, one tf32 MMA K step)
   int kg;      // kpad / 4 float4 groups
+  int kpad16;  // kreal rounded up to 16 (fp16-pair section: one f16 MMA K step per chunk)
+  int nch16;   // kpad16 / 16 chunks per (tile, coordinate) row
   int ntiles;  // ceil(nver / 128)
+  // The packed basis has three sections (DESIGN.md "Packed basis"):
+  //   [0, f32_bytes)                  fp32, float4-tiled: SIMT forward (small batches) and the backward pass
+  //   [f16_offset, +f16_bytes)        fp16 hi/lo pairs of the column-scaled basis in tcgen05 operand tiles: tensor-core forward
+  //   [scale_offset, +4 kpad16)       2^-s_k per column (what a coefficient is multiplied by to undo the column scale)
   size_t tile_floats() const { return (size_t)3 * kg * kTileVerts * 4; }
-  size_t bytes() const { return (size_t)ntiles * tile_floats() * sizeof(float); }
+  size_t f32_bytes() const { return (size_t)ntiles * tile_floats() * sizeof(float); }
+  size_t f16_offset() const { return (f32_bytes() + 1023) / 1024 * 1024; }
+  size_t f16_bytes() const { return (size_t)ntiles * 3 * nch16 * 8192; }
+  size_t scale_offset() const { return f16_offset() + f16_bytes(); }
+  size_t bytes() const { return scale_offset() + ((size_t)kpad16 * sizeof(float) + 255) / 256 * 256; }
 };
 inline BasisGeom basis_geom(int nver, int ks, int ke) {
   BasisGeom g;
@@ -74,6 +84,8 @@ inline BasisGeom basis_geom(int nver, int ks, int ke) {
   g.kreal = ks + ke + 1;
   g.kpad = (g.kreal + 7) / 8 * 8;
   g.kg = g.kpad / 4;
+  g.kpad16 = (g.kreal + 15) / 16 * 16;
+  g.nch16 = g.kpad16 / 16;
   g.ntiles = (nver + kTileVerts - 1) / kTileVerts;
   return g;
 }

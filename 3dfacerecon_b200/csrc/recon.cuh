@@ -136,6 +136,7 @@ struct ReconOut {
   float* planar;
   float4* rec;
   int width, height;   // image size the snap codes refer to (rec != nullptr)
+  unsigned long long* keys;   // fused call: the rasterizer's visibility keys [B][height*width], to be cleared before it runs
 };
 
 // Projection + y flip of one reconstructed vertex (nets/network.py:163-169).

@@ -1,0 +1,428 @@
+// Tensor-core reconstruction + projection forward, second generation: the basis is split ONCE, at pack time, into an
+// fp16 hi/lo pair per element (22 significant bits after a per-column power-of-two scale), laid out as ready-made
+// tcgen05 operand tiles.  The kernel then has no conversion stage at all:
+//
+//   V[b, (c,n)] = sum_k P[(c,n), k] * coef[b, k]
+//              ~= 2^-t_b * sum_k (Phi + Plo)[(c,n), k] * (b0 + b1)[b, k]          (dropping Plo*b1, 2^-22 relative)
+//   P 2^s_k = Phi + Plo (fp16 each),  coef 2^-s_k 2^t_b = b0 + b1 (fp16 each),  products accumulated in fp32 (TMEM)
+//
+// Per CTA (persistent, one per SM, 10 warps):
+//   warp 8   producer    cp.async.bulk (TMA engine): the two resident coefficient operands of this 64-face batch tile
+//                        once, then 24 KB stages (3 chunks of 16 k: hi tile + lo tile each) of the basis into a
+//                        shared-memory ring -- a tile's 3 coordinate rows are one contiguous run of the packed file
+//   warp 9   MMA issuer  whole warp converged, one elected lane: per chunk  D += Phi.b0 + Plo.b0 + Phi.b1
+//                        (tcgen05.mma kind::f16, M128 N64 K16, BOTH operands from shared memory); a tcgen05.commit per
+//                        stage hands the shared-memory stage back to the producer when its MMAs have retired
+//   warps 0-7 epilogue   tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices), (2^-t f.R).v + t,
+//                        y flip, coalesced stores (planar vertex_proj and / or rasterizer records); double-buffered
+//                        against the next tile's MMAs
+// Measured on B200 (tools/mma_bench3.cu): an SS-form M128 N64 MMA takes 48 cycles (operand reads at 128 B/clk), K8 tf32
+// and K16 f16 alike, so a 16-k chunk costs 144 tensor cycles here against 192 for the 3xTF32 TS-form kernel
+// (recon_tc.cuh) -- and that kernel also needs 8 converter warps and a TMEM operand ring only 4 chunks deep.
+#ifndef FR_RECON_F16_CUH_
+#define FR_RECON_F16_CUH_
+
+#include <cuda_fp16.h>
+
+#include "recon_tc.cuh"
+
+namespace fr {
+namespace f16 {
+
+using tc::bulk_load;
+using tc::elect_one;
+using tc::mbar_arrive;
+using tc::mbar_arrive_expect_tx;
+using tc::mbar_init;
+using tc::mbar_wait;
+using tc::smem_u32;
+using tc::tc_commit;
+using tc::tc_fence_after;
+using tc::tc_fence_before;
+using tc::tmem_ld16;
+
+constexpr int kN = 64;                 // faces per batch tile (MMA N)
+constexpr int kChunkK = 16;            // k columns per chunk == one f16 MMA K step
+constexpr uint32_t kHalfBytes = kTileVerts * kChunkK * 2;   // one operand tile (hi or lo): 128 rows x 16 k fp16 = 4 KB
+constexpr uint32_t kChunkBytes = 2 * kHalfBytes;            // hi tile + lo tile
+constexpr int kStageChunks = 3;        // chunks per bulk copy: a tile has 3 * nch16 chunks, always a multiple of 3
+constexpr uint32_t kStageBytes = kStageChunks * kChunkBytes;
+constexpr int kStages = 4;             // 96 KB of basis in flight per SM
+constexpr int kDBufs = 2;
+constexpr int kDCols = 3 * kN;
+constexpr int kTmemCols = 512;
+constexpr int kEpiWarps = 8, kProducerWarp = 8, kMmaWarp = 9;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
+constexpr int kPose16Stride = 16;      // floats per face: 2^-t f.R [9] | t [3] | pad
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 at [4,6), a = b = F16 (0) at [7,10) / [10,13), K-major
+// A and B, n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Barriers {
+  uint64_t raw_full[kStages];
+  uint64_t raw_empty[kStages];
+  uint64_t d_full[kDBufs];
+  uint64_t d_empty[kDBufs];
+  uint64_t b_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct SmemLayout {
+  uint32_t b0, b1, raw, pose, bars, total;
+  uint32_t sbo;  // bytes between 8-face groups of a coefficient operand
+};
+__host__ __device__ inline SmemLayout smem_layout(int nch16) {
+  SmemLayout L;
+  L.sbo = (uint32_t)nch16 * 2u * 128u;            // 2 core matrices (8 faces x 8 k fp16 = 128 B) per chunk
+  const uint32_t bsz = (kN / 8) * L.sbo;
+  L.b0 = 0;
+  L.b1 = bsz;
+  L.raw = (2 * bsz + 1023u) / 1024u * 1024u;
+  L.pose = L.raw + kStages * kStageBytes;
+  L.bars = L.pose + kN * kPose16Stride * 4;
+  L.total = L.bars + (uint32_t)sizeof(Barriers);
+  return L;
+}
+
+// D[tmem_d] (+)= A[smem desc] . B[smem desc]   (M128 N64 K16, fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- packing
+// Column scale: s_k with max_n |P[n,k]| 2^s_k in [2^14, 2^15) (fp16 overflows at 2^16); the scale region first collects
+// the column maxima as float bit patterns (non-negative floats order like unsigned integers), then holds 2^-s_k.
+__global__ void __launch_bounds__(256)
+basis_colmax_kernel(const float* __restrict__ mu, const float* __restrict__ pc_shape, const float* __restrict__ pc_exp,
+                    int nver, int ks, int ke, unsigned* __restrict__ colmax_bits) {
+  const int kreal = ks + ke + 1;
+  const size_t rows = (size_t)3 * nver;
+  const size_t r0 = (size_t)blockIdx.x * 512, r1 = min(rows, r0 + 512);
+  for (int k = threadIdx.x; k < kreal; k += 256) {
+    float m = 0.0f;
+    for (size_t r = r0; r < r1; ++r) {
+      const float v = (k < ks) ? pc_shape[r * ks + k] : (k < ks + ke ? pc_exp[r * ke + (k - ks)] : mu[r]);
+      m = fmaxf(m, fabsf(v));          // NaN entries are ignored here and stay NaN in the packed tiles
+    }
+    atomicMax(colmax_bits + k, __float_as_uint(m));
+  }
+}
+
+__global__ void basis_colscale_kernel(float* __restrict__ scale, int kreal, int kpad16) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kpad16) return;
+  float inv = 1.0f;
+  if (k < kreal) {
+    const float m = __uint_as_float(reinterpret_cast<unsigned*>(scale)[k]);
+    if (m > 0.0f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);                   // m = f 2^e, f in [0.5, 1)  =>  m 2^(15-e) in [2^14, 2^15)
+      const int s = max(-100, min(100, 15 - e));
+      inv = ldexpf(1.0f, -s);
+    }
+  }
+  scale[k] = inv;
+}
+
+// fp16 operand tiles: for every (tile, coordinate) row, nch16 chunks of [hi tile | lo tile]; a tile is the canonical
+// K-major no-swizzle layout of a 128 x 16 fp16 operand: [k / 8][row][k % 8], i.e. 8-row x 16-byte core matrices, 128 B
+// between 8-row groups (SBO) and 2048 B between the two K halves (LBO).  One thread writes one 16-byte row piece.
+__global__ void __launch_bounds__(256)
+pack_basis_f16_kernel(const float* __restrict__ mu, const float* __restrict__ pc_shape, const float* __restrict__ pc_exp,
+                      const float* __restrict__ inv_scale, int nver, int ks, int ke, int nch16, int ntiles, unsigned flags,
+                      uint4* __restrict__ tiles) {
+  const size_t total = (size_t)ntiles * 3 * nch16 * 2 * kTileVerts;      // (tile, c, chunk, k half, row)
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int v = (int)(idx % kTileVerts);
+  const int kh = (int)((idx / kTileVerts) % 2);
+  const int ci = (int)((idx / (2 * kTileVerts)) % nch16);
+  const int c = (int)((idx / ((size_t)2 * kTileVerts * nch16)) % 3);
+  const int tile = (int)(idx / ((size_t)2 * kTileVerts * nch16 * 3));
+  const int n = tile * kTileVerts + v;
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = ci * kChunkK + kh * 8 + j;
+    float x = 0.0f;
+    if (n < nver) {
+      const size_t row_b = (flags & FR_BASIS_INTERLEAVED) ? (size_t)3 * n + c : (size_t)c * nver + n;
+      const size_t row_m = (flags & FR_MEAN_INTERLEAVED) ? (size_t)3 * n + c : (size_t)c * nver + n;
+      if (k < ks) x = pc_shape[row_b * ks + k];
+      else if (k < ks + ke) x = pc_exp[row_b * ke + (k - ks)];
+      else if (k == ks + ke) x = mu[row_m];
+    }
+    const float xs = x * (1.0f / inv_scale[k]);            // power of two: exact
+    hi[j] = __float2half_rn(xs);
+    lo[j] = __float2half_rn(xs - __half2float(hi[j]));     // the difference is exact in fp32
+  }
+  uint4 whi, wlo;
+  memcpy(&whi, hi, 16);
+  memcpy(&wlo, lo, 16);
+  const size_t chunk = ((size_t)(tile * 3 + c) * nch16 + ci) * (kChunkBytes / 16);
+  const size_t piece = (size_t)kh * kTileVerts + v;
+  tiles[chunk + piece] = whi;
+  tiles[chunk + kHalfBytes / 16 + piece] = wlo;
+}
+
+// ---------------------------------------------------------------------------------------------- prep
+// One CTA per (padded) face: coefficients with the column scale undone, a per-face power-of-two scale 2^t that brings the
+// largest of them into [2^13, 2^14), split into fp16 b0 + b1 and stored per 64-face batch tile in the canonical K-major
+// layout [b0|b1][8-face group][k / 8][face % 8][k % 8] the kernel bulk-copies; pose16 = 2^-t f.R | t3d.
+__global__ void __launch_bounds__(256)
+recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict__ inv_scale, int dparam, int batch, int ks,
+                      int ke, int kpad16, unsigned flags, unsigned char* __restrict__ bsplit, float* __restrict__ pose16) {
+  __shared__ float red[8];
+  __shared__ float s_pose[kPoseStride];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bool live = b < batch;
+  float cmax = 0.0f;
+  for (int k = tid; k < kpad16; k += 256) {
+    float v = 0.0f;
+    if (live) {
+      if (k < ks + ke) v = params[(size_t)b * dparam + FR_NDIM_POSE + k];
+      else if (k == ks + ke) v = 1.0f;
+    }
+    cmax = fmaxf(cmax, fabsf(v * inv_scale[k]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
+  if ((tid & 31) == 0) red[tid >> 5] = cmax;
+  if (tid == 0 && live) pose_matrices(params + (size_t)b * dparam, flags, s_pose);
+  __syncthreads();
+  cmax = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) cmax = fmaxf(cmax, red[w]);
+  int t = 0;
+  if (cmax > 0.0f && cmax < 3.0e38f) {
+    int e;
+    frexpf(cmax, &e);                  // cmax 2^(14-e) in [2^13, 2^14)
+    t = max(-60, min(60, 14 - e));
+  }
+  const float up = ldexpf(1.0f, t), down = ldexpf(1.0f, -t);
+  const uint32_t sbo = (uint32_t)(kpad16 / 8) * 128u, half = (kN / 8) * sbo;
+  const int n = b % kN;
+  unsigned char* tile = bsplit + (size_t)(b / kN) * 2 * half;
+  for (int k = tid; k < kpad16; k += 256) {
+    float v = 0.0f;
+    if (live) {
+      if (k < ks + ke) v = params[(size_t)b * dparam + FR_NDIM_POSE + k];
+      else if (k == ks + ke) v = 1.0f;
+    }
+    const float c = v * inv_scale[k] * up;
+    const __half b0 = __float2half_rn(c);
+    const __half b1 = __float2half_rn(c - __half2float(b0));
+    const uint32_t off = (uint32_t)(n >> 3) * sbo + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<__half*>(tile + off) = b0;
+    *reinterpret_cast<__half*>(tile + half + off) = b1;
+  }
+  if (tid < kPose16Stride) {
+    float v = 0.0f;
+    if (live) {
+      if (tid < 9) v = s_pose[tid] * down;
+      else if (tid < 12) v = s_pose[tid];
+    }
+    pose16[(size_t)b * kPose16Stride + tid] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(kThreads, 1)
+recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned char* __restrict__ bsplit,
+                     const float* __restrict__ pose16, ReconOut out, int batch, int nver, int nch16, int ntiles,
+                     float im_size, unsigned flags, int key_vec_per_face) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const SmemLayout L = smem_layout(nch16);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + L.bars);
+  float* s_pose = reinterpret_cast<float*>(smem + L.pose);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * kN;
+  const size_t tile_bytes = (size_t)3 * nch16 * kChunkBytes;
+
+  // ---- one-time setup: barriers, TMEM, poses
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars->raw_full[i], 1);
+      mbar_init(&bars->raw_empty[i], 1);         // released by a tcgen05.commit
+    }
+    for (int i = 0; i < kDBufs; ++i) {
+      mbar_init(&bars->d_full[i], 1);
+      mbar_init(&bars->d_empty[i], kEpiWarps);
+    }
+    mbar_init(&bars->b_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < kN * kPose16Stride; i += kThreads) s_pose[i] = pose16[(size_t)b0 * kPose16Stride + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == kProducerWarp) {
+    // ================================================================== producer (TMA engine)
+    if (lane == 0) {
+      const uint32_t bbytes = (kN / 8) * L.sbo;
+      mbar_arrive_expect_tx(&bars->b_full, 2u * bbytes);
+      bulk_load(smem + L.b0, bsplit + (size_t)blockIdx.y * 2 * bbytes, bbytes, &bars->b_full);
+      bulk_load(smem + L.b1, bsplit + (size_t)blockIdx.y * 2 * bbytes + bbytes, bbytes, &bars->b_full);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const unsigned char* src = tiles + (size_t)tile * tile_bytes;
+        for (int sg = 0; sg < nch16; ++sg, ++it) {             // nch16 stages of 3 chunks per tile
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(&bars->raw_empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&bars->raw_full[s], kStageBytes);
+          bulk_load(smem + L.raw + s * kStageBytes, src + (size_t)sg * kStageBytes, kStageBytes, &bars->raw_full[s]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================== MMA issuer (whole warp converged, one elected lane issues)
+    mbar_wait(&bars->b_full, 0);
+    tc_fence_after();
+    const uint64_t db0 = tc::make_b_desc(smem_u32(smem + L.b0), 128u, L.sbo);
+    const uint64_t db1 = tc::make_b_desc(smem_u32(smem + L.b1), 128u, L.sbo);
+    const uint64_t da0 = tc::make_b_desc(smem_u32(smem + L.raw), 2048u, 128u);   // same descriptor format for A
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const uint32_t dbuf = tcount % kDBufs;
+      mbar_wait(&bars->d_empty[dbuf], ((tcount / kDBufs) & 1u) ^ 1u);          // epilogue has drained this accumulator set
+      tc_fence_after();
+      uint32_t c = 0, ci = 0;                                                  // coordinate and chunk-in-row of the next chunk
+#pragma unroll 1
+      for (int sg = 0; sg < nch16; ++sg, ++it) {
+        const uint32_t s = it % kStages;
+        mbar_wait(&bars->raw_full[s], (it / kStages) & 1u);
+        tc_fence_after();
+        uint32_t cj[kStageChunks], cij[kStageChunks];                          // (coordinate, chunk-in-row) of the stage's chunks
+#pragma unroll
+        for (int j = 0; j < kStageChunks; ++j) {
+          cj[j] = c;
+          cij[j] = ci;
+          if (++ci == (uint32_t)nch16) { ci = 0; ++c; }
+        }
+        if (elect_one()) {
+          const uint64_t da = da0 + (uint64_t)((s * kStageBytes) >> 4);
+#pragma unroll
+          for (int j = 0; j < kStageChunks; ++j) {
+            const uint32_t d_addr = tmem + dbuf * kDCols + cj[j] * kN;
+            const uint64_t a_hi = da + (uint64_t)((j * kChunkBytes) >> 4), a_lo = a_hi + (uint64_t)(kHalfBytes >> 4);
+            const uint64_t kb = (uint64_t)(cij[j] * (256u >> 4));              // two 128-byte core matrices per chunk
+            mma_f16_ss(d_addr, a_hi, db0 + kb, cij[j] != 0u);
+            mma_f16_ss(d_addr, a_lo, db0 + kb, true);
+            mma_f16_ss(d_addr, a_hi, db1 + kb, true);
+          }
+          tc_commit(&bars->raw_empty[s]);                                      // stage reusable once these MMAs have retired
+          if (sg == nch16 - 1) tc_commit(&bars->d_full[dbuf]);                 // all three accumulators of the tile complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================================================== epilogue (warps 0..7)
+    const int qd = warp & 3;                                      // TMEM lane quarter == warp % 4
+    const int jb0 = (warp >> 2) * (kN / (kEpiWarps / 4)), jb1 = jb0 + kN / (kEpiWarps / 4);   // this warp's faces
+    const int v = qd * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(qd * 32) << 16;
+    // fused call: while the first tile's MMAs run these warps have nothing to drain -- clear this batch tile's visibility keys
+    // for the rasterizer that follows (16-byte vectors; the CTAs of the batch tile share the range)
+    if (key_vec_per_face > 0) {
+      uint4* kv = reinterpret_cast<uint4*>(out.keys) + (size_t)b0 * key_vec_per_face;
+      const size_t nvec = (size_t)min(kN, batch - b0) * key_vec_per_face;
+      for (size_t i = (size_t)blockIdx.x * (kEpiWarps * 32) + threadIdx.x; i < nvec; i += (size_t)gridDim.x * (kEpiWarps * 32))
+        kv[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
+      const int n = tile * kTileVerts + v;
+      mbar_wait(&bars->d_full[dbuf], dph);
+      tc_fence_after();
+      const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
+#pragma unroll 1
+      for (int jb = jb0; jb < jb1; jb += 16) {
+        float x[16], y[16], z[16];
+        tmem_ld16(d_addr + 0 * kN + jb, x);
+        tmem_ld16(d_addr + 1 * kN + jb, y);
+        tmem_ld16(d_addr + 2 * kN + jb, z);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n < nver) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int b = b0 + jb + j;
+            if (b < batch) {
+              const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPose16Stride);
+              const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+              const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+              project_store(P, x[j], y[j], z[j], im_size, flags, out, b, nver, n);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+  }
+}
+
+}  // namespace f16
+
+// fp16 coefficient operands of every 64-face batch tile + pose16
+inline size_t recon_f16_bsplit_bytes(int batch, const BasisGeom& g) {
+  return (size_t)ceil_div(batch, f16::kN) * 2 * (f16::kN / 8) * (size_t)(g.kpad16 / 8) * 128;
+}
+inline size_t recon_f16_pose_bytes(int batch) { return sizeof(float) * (size_t)batch_padded(batch) * f16::kPose16Stride; }
+
+inline bool recon_f16_fits(const BasisGeom& g) { return f16::smem_layout(g.nch16).total <= 227u * 1024u; }
+
+// keys / key_vec_per_face: when the visibility keys of the fused call can be cleared by the kernel's idle epilogue warps
+// (16-byte vectors per face), else nullptr / 0.
+inline int launch_recon_fwd_f16(const float* params, const float* packed, void* bsplit, float* pose16, ReconOut out, int batch,
+                                int nver, const BasisGeom& g, float im_size, unsigned flags, int nsm, cudaStream_t st,
+                                void* keys, int key_vec_per_face) {
+  static_assert(f16::kN == kBatchPad, "batch tiles are kBatchPad faces");
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(packed);
+  const float* inv_scale = reinterpret_cast<const float*>(base + g.scale_offset());
+  const int bpad = batch_padded(batch);
+  const int dparam = FR_NDIM_POSE + g.ks + g.ke;
+  f16::recon_prep_f16_kernel<<<bpad, 256, 0, st>>>(params, inv_scale, dparam, batch, g.ks, g.ke, g.kpad16, flags,
+                                                  static_cast<unsigned char*>(bsplit), pose16);
+  FR_LAUNCHED("recon_prep_f16_kernel");
+  const f16::SmemLayout L = f16::smem_layout(g.nch16);
+  const int nbt = ceil_div(batch, f16::kN);
+  int ctas = nsm / nbt;
+  if (ctas < 1) ctas = 1;
+  if (ctas > g.ntiles) ctas = g.ntiles;
+  FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  f16::recon_fwd_f16_kernel<<<dim3(ctas, nbt), f16::kThreads, L.total, st>>>(
+      base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), pose16, out, batch, nver, g.nch16, g.ntiles, im_size, flags,
+      keys != nullptr ? key_vec_per_face : 0);
+  FR_LAUNCHED("recon_fwd_f16_kernel");
+  return FR_OK;
+}
+
+}  // namespace fr
+
+#endif  // FR_RECON_F16_CUH_

@@ -416,23 +416,18 @@ inline int env_int(const char* name, int dflt) {
   return e ? std::atoi(e) : dflt;
 }
 
-// FR_RECON_PATH=simt|tc overrides the dispatch (debugging / A-B comparisons); default: tensor cores above 8 faces.
+// FR_RECON_PATH = simt | tf32 | f16 overrides the forward dispatch (debugging / A-B comparisons): 1, 2, 3; 0 = default.
 inline int recon_path_override() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = std::getenv("FR_RECON_PATH");
-    cached = (e == nullptr) ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0));
+    cached = (e == nullptr) ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : (e[0] == 'f' ? 3 : 0)));
   }
   return cached;
 }
 
-inline bool recon_tc_applicable(int batch, const BasisGeom& g, unsigned) {
-  const int ov = recon_path_override();
-  if (ov == 1) return false;
-  const tc::SmemLayout L = tc::smem_layout(g.kg);
-  if (L.total > 227u * 1024u) return false;          // K too large for a resident coefficient operand
-  if (ov == 2) return true;
-  return batch > 8;
+inline bool recon_tc_applicable(int, const BasisGeom& g, unsigned) {
+  return tc::smem_layout(g.kg).total <= 227u * 1024u;   // K too large for a resident coefficient operand otherwise
 }
 
 inline int launch_recon_fwd_tc(const float* packed, const float* coefT, const float* pose, void* tc_ws, ReconOut out,

@@ -226,8 +226,10 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
-    def step_full():
-        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), vertex.data_ptr(),
+    def step_full(vertex_ptr=None):
+        """The north-star call: params -> depth + tri_ind.  The intermediate vertex tensor is an optional output of the fused
+        call (the reconstruction epilogue feeds the rasterizer's vertex records directly); the timed loop does not ask for it."""
+        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), vertex_ptr,
                                           depth.data_ptr(), tri_ind.data_ptr(), B, nver, ntri, ks, ke, H, W, IM_SIZE,
                                           dm.run_flags, ws.data_ptr(), ws.numel(), sp))
 
@@ -285,6 +287,10 @@ def run_ours(args):
         import oracle
         from oracle import recon as orecon
         torch.cuda.synchronize(dev)
+        depth_timed = depth.clone()
+        step_full(vertex.data_ptr())                                      # same call, this time materialising vertex_proj
+        torch.cuda.synchronize(dev)
+        assert depth_timed.cpu().numpy().tobytes() == depth.cpu().numpy().tobytes()
         vp = vertex[:2].cpu().numpy()
         want_vp = orecon.vertices_transform(params_host[:2], model, IM_SIZE)
         want = oracle.oracle_render_depth_forward(vp, model["tri"], model["vertex"], H, W)
@@ -409,6 +415,9 @@ def run_ours(args):
                                    "200x200 depth render (depth + tri_ind), forward only, per GPU",
                        "batch_per_gpu": B, "nver": nver, "ntri": ntri, "ndim_shape": ks, "ndim_exp": ke, "image": [H, W],
                        "l2": "flushed before every timed step (512 MiB write, outside the events)",
+                       "call": "fr_recon_render_forward, depth + tri_ind out; the optional vertex_proj output is not requested in "
+                               "the timed loop (the parity check re-runs the call with it); groups_ms times the two separate "
+                               "entry points, which do materialise and re-read it",
                        "parallelism": "batch-sharded x%d, basis replicated, no collective" % world},
             "e2e": {"value": faces_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                     "h2d_bytes_per_step": int(pin_params[0].numel() * 4), "d2h_bytes_per_step": int(pin_depth[0].numel() * 4),
