@@ -11,7 +11,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib3dfacerecon_b200.so")
+# FR_LIB_PATH: developer switch for A/B runs of differently built libraries (tools/); the product always loads the in-tree one
+LIB_PATH = os.environ.get("FR_LIB_PATH") or os.path.join(_HERE, "lib3dfacerecon_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "facerecon_b200.h")
 
 FR_OK, FR_ERR_INVALID_ARGUMENT, FR_ERR_CUDA, FR_ERR_WORKSPACE, FR_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
