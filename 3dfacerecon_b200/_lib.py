@@ -30,6 +30,7 @@ SIGNATURES = {
     "fr_last_error": (ctypes.c_char_p, []),
     "fr_version": (_i, []),
     "fr_launch_count": (ctypes.c_ulonglong, []),
+    "fr_debug_set_mid_event": (_i, [_vp]),
     "fr_packed_basis_bytes": (_sz, [_i, _i, _i]),
     "fr_pack_basis": (_i, [_vp, _vp, _vp, _i, _i, _i, _u, _vp, _vp]),
     "fr_recon_workspace_bytes": (_sz, [_i, _i, _i, _i]),

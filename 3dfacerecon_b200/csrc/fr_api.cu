@@ -189,6 +189,14 @@ const char* fr_last_error(void) { return error_buffer(); }
 int fr_version(void) { return FR_VERSION; }
 unsigned long long fr_launch_count(void) { return launch_counter().load(); }
 
+// measurement hook: a CUDA event the fused call records between its reconstruction and its rasterizer kernels, so that a
+// benchmark can time the two parts of ONE real step (bench.py "roofline"); null disables it.  Not thread-safe.
+static cudaEvent_t g_mid_event = nullptr;
+int fr_debug_set_mid_event(void* cuda_event) {
+  g_mid_event = static_cast<cudaEvent_t>(cuda_event);
+  return FR_OK;
+}
+
 // developer diagnostics (not part of the public header): per-role cycle counters of the tensor-core kernel's block 0
 int fr_debug_tc_counters(unsigned long long* out32, int reset) {
   if (out32 && cudaMemcpyFromSymbol(out32, fr::tc::g_tc_dbg, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
@@ -342,6 +350,7 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
   if (int rc = recon_project_forward_impl(params, packed, out, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace, rb,
                                           stream))
     return rc;
+  if (g_mid_event != nullptr) FR_CUDA(cudaEventRecord(g_mid_event, static_cast<cudaStream_t>(stream)));
   return render_depth_forward_impl(vertex_proj, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height,
                                    width, rws, workspace_bytes - rb, stream, true);
 }

@@ -135,6 +135,9 @@ int fr_session_wait(fr_session* s, int slot);
 int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float* params_grad);
 /* counters: kernels launched by this library since load (for bench.py's gpu_launches) */
 unsigned long long fr_launch_count(void);
+/* measurement hook: a cudaEvent_t that fr_recon_render_forward records between its reconstruction and its rasterizer
+ * kernels (NULL = off), so a benchmark can split the device time of one real step; process-global, not thread-safe. */
+int fr_debug_set_mid_event(void* cuda_event);
 
 #ifdef __cplusplus
 }
