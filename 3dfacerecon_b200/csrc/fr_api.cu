@@ -10,6 +10,7 @@
 #include "recon.cuh"
 #include "recon_tc.cuh"
 #include "recon_f16.cuh"
+#include "recon_bwd_f16.cuh"
 
 using namespace fr;
 
@@ -25,6 +26,9 @@ struct ReconWorkspace {
   void* tc;       // 3xTF32 tensor-core path scratch (split coefficients)
   void* bsplit16; // fp16-pair tensor-core path: coefficient operands per 64-face batch tile
   float* pose16;  // ... and [bpad][16] scaled pose
+  unsigned char* gtiles;  // tensor-core backward: fp16 operand tiles of the rotated vertex gradient
+  float* gmax;            // ... [bpad][4] per-face, per-row gradient maxima
+  float* gscale;          // ... [bpad] 2^-u_b
   size_t bytes;
 };
 
@@ -44,6 +48,9 @@ ReconWorkspace carve_recon(void* base, int batch, const BasisGeom& g) {
   w.tc = take(recon_tc_workspace_bytes(batch, g));
   w.bsplit16 = take(recon_f16_bsplit_bytes(batch, g));
   w.pose16 = static_cast<float*>(take(recon_f16_pose_bytes(batch)));
+  w.gtiles = static_cast<unsigned char*>(take(recon_bwd_f16_fits(g) ? b16::grad_tiles_bytes(batch, g) : 0));
+  w.gmax = static_cast<float*>(take(sizeof(float) * (size_t)bpad * 4));
+  w.gscale = static_cast<float*>(take(sizeof(float) * (size_t)bpad));
   w.bytes = off;
   return w;
 }
@@ -238,6 +245,12 @@ int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, i
                                                                               g.nch16, g.ntiles, layout_flags,
                                                                               reinterpret_cast<uint4*>(base + g.f16_offset()));
   FR_LAUNCHED("pack_basis_f16_kernel");
+  // ... and the same pairs transposed for the backward contraction over the vertices
+  const size_t bpieces = (size_t)g.ntiles * 3 * (kTileVerts / 16) * g.mtiles() * 2 * kTileVerts;
+  b16::pack_basis_bwd_kernel<<<(unsigned)((bpieces + 255) / 256), 256, 0, st>>>(pc_shape, pc_exp, scale, nver, ndim_shape, ndim_exp,
+                                                                               g.mtiles(), g.ntiles, layout_flags,
+                                                                               reinterpret_cast<uint4*>(base + g.bwd_offset()));
+  FR_LAUNCHED("pack_basis_bwd_kernel");
   return FR_OK;
 }
 
@@ -274,8 +287,31 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
                                                                  g.kpad, flags, w.coefT, w.pose, nullptr);
   FR_LAUNCHED("recon_prep_kernel");
   FR_CUDA(cudaMemsetAsync(w.G, 0, sizeof(float) * (size_t)bpad * g.kpad, st));
-  recon_bwd_dt_kernel<<<dim3(batch, 3), 256, 0, st>>>(vertex_grad, nver, flags, w.dt);
+  // dispatch: tcgen05 contraction above 8 faces (FR_RECON_PATH=simt forces the FFMA kernel)
+  const uint32_t bwd_smem = b16::smem_bytes(g.mtiles(), b16::faces_per_tile(batch));
+  const bool use_tc = recon_bwd_f16_fits(g) && bwd_smem <= 227u * 1024u && batch > 8 && recon_path_override() != 1;
+  recon_bwd_dt_kernel<<<dim3(batch, 3), 256, 0, st>>>(vertex_grad, nver, flags, w.dt, use_tc ? w.gmax : nullptr);
   FR_LAUNCHED("recon_bwd_dt_kernel");
+  if (use_tc) {
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(packed);
+    const float* inv_scale = reinterpret_cast<const float*>(base + g.scale_offset());
+    const int nb = b16::faces_per_tile(batch), nbt = ceil_div(batch, nb);
+    b16::recon_bwd_pack_grad_kernel<<<dim3(ceil_div(g.ntiles * (kTileVerts / 8), 4 * b16::kGroupsPerThread), ceil_div(batch, 64)), 256, 0,
+                                      st>>>(vertex_grad, w.pose, w.gmax, reinterpret_cast<const float4*>(packed), g.kg, g.ks + g.ke, g.kpad,
+                                            batch, nver, g.ntiles, nb, flags, w.gtiles, w.gscale, w.G);
+    FR_LAUNCHED("recon_bwd_pack_grad_kernel");
+    int ctas = sm_count() / nbt;
+    if (ctas < 1) ctas = 1;
+    if (ctas > g.ntiles) ctas = g.ntiles;
+    FR_CUDA(cudaFuncSetAttribute(b16::recon_bwd_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
+    b16::recon_bwd_f16_kernel<<<dim3(ctas, nbt), b16::kThreads, bwd_smem, st>>>(base + g.bwd_offset(), w.gtiles, inv_scale, w.gscale,
+                                                                              w.G, batch, nb, g.mtiles(), g.ntiles, g.kpad);
+    FR_LAUNCHED("recon_bwd_f16_kernel");
+    recon_bwd_finalize_kernel<<<batch, 256, 0, st>>>(w.G, w.coefT, w.pose, w.dt, bpad, ndim_shape, ndim_exp, g.kpad, dparam,
+                                                    params_grad);
+    FR_LAUNCHED("recon_bwd_finalize_kernel");
+    return FR_OK;
+  }
 
   const int gy = batch <= 16 ? 1 : (batch <= 32 ? 2 : 4);
   const int fbt = kBwdFB * gy;

@@ -74,7 +74,12 @@ struct BasisGeom {
   size_t f16_offset() const { return (f32_bytes() + 1023) / 1024 * 1024; }
   size_t f16_bytes() const { return (size_t)ntiles * 3 * nch16 * 8192; }
   size_t scale_offset() const { return f16_offset() + f16_bytes(); }
-  size_t bytes() const { return scale_offset() + ((size_t)kpad16 * sizeof(float) + 255) / 256 * 256; }
+  //   [bwd_offset, +bwd_bytes)        the same fp16 hi/lo pairs once more, transposed for the backward contraction over the
+  //                                   vertices: per (tile, coordinate, 16-vertex chunk)  [hi m0 | hi m1 | lo m0 | lo m1]  with 128 k rows each
+  int mtiles() const { return (kpad16 + 127) / 128; }
+  size_t bwd_offset() const { return scale_offset() + ((size_t)kpad16 * sizeof(float) + 1023) / 1024 * 1024; }
+  size_t bwd_bytes() const { return (size_t)ntiles * 3 * (kTileVerts / 16) * 2 * mtiles() * 4096; }
+  size_t bytes() const { return bwd_offset() + bwd_bytes(); }
 };
 inline BasisGeom basis_geom(int nver, int ks, int ke) {
   BasisGeom g;

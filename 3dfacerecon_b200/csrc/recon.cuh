@@ -242,23 +242,39 @@ recon_fwd_simt_kernel(const float4* __restrict__ packed, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-// d t3d[b][r] = sum_n g'[b][r][n]  (g' = upstream gradient with the y row negated when a flip is active).
+// d t3d[b][r] = sum_n g'[b][r][n]  (g' = upstream gradient with the y row negated when a flip is active); optionally also
+// gmax[b*4 + r] = max_n |g[b][r][n]| (the tensor-core backward scales its fp16 operand by it).
 __global__ void __launch_bounds__(256)
-recon_bwd_dt_kernel(const float* __restrict__ vertex_grad, int nver, unsigned flags, float* __restrict__ dt) {
+recon_bwd_dt_kernel(const float* __restrict__ vertex_grad, int nver, unsigned flags, float* __restrict__ dt,
+                    float* __restrict__ gmax) {
   const int b = blockIdx.x, r = blockIdx.y;
   const float* g = vertex_grad + ((size_t)b * 3 + r) * nver;
-  float s = 0.0f;
-  for (int n = threadIdx.x; n < nver; n += 256) s += g[n];
-  __shared__ float red[8];
+  float s = 0.0f, m = 0.0f;
+  for (int n = threadIdx.x; n < nver; n += 256) {
+    const float v = g[n];
+    s += v;
+    m = fmaxf(m, fabsf(v));
+  }
+  __shared__ float red[8], redm[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = s;
+    redm[threadIdx.x >> 5] = m;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float tot = 0.0f;
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    float tot = 0.0f, mx = 0.0f;
+    for (int w = 0; w < 8; ++w) {
+      tot += red[w];
+      mx = fmaxf(mx, redm[w]);
+    }
     if (r == 1 && !(flags & FR_YFLIP_NONE)) tot = -tot;
     dt[b * 4 + r] = tot;
+    if (gmax != nullptr) gmax[b * 4 + r] = mx;
   }
 }
 

@@ -66,7 +66,7 @@ def test_other_conventions(small_model, convention, conv):
     assert np.abs(got - want).max() <= VERT_TOL * np.abs(want).max()
 
 
-@pytest.mark.parametrize("B", [2, 20, 64])
+@pytest.mark.parametrize("B", [2, 20, 64, 300])
 def test_bfm_size_backward(bfm, B):
     """d params of sum(vertex_proj * g) for a full [B,3,N] upstream gradient (the TF autodiff chain, App. A.4)."""
     p = fr("synth").sample_params_constrained(B, seed=40 + B)
