@@ -251,6 +251,9 @@ int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, i
                                                                                g.mtiles(), g.ntiles, layout_flags,
                                                                                reinterpret_cast<uint4*>(base + g.bwd_offset()));
   FR_LAUNCHED("pack_basis_bwd_kernel");
+  b16::pack_mean_kernel<<<ceil_div(3 * g.ntiles * kTileVerts, 256), 256, 0, st>>>(mu, nver, g.ntiles, layout_flags,
+                                                                               reinterpret_cast<float*>(base + g.mean_offset()));
+  FR_LAUNCHED("pack_mean_kernel");
   return FR_OK;
 }
 
@@ -296,9 +299,10 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
     const unsigned char* base = reinterpret_cast<const unsigned char*>(packed);
     const float* inv_scale = reinterpret_cast<const float*>(base + g.scale_offset());
     const int nb = b16::faces_per_tile(batch), nbt = ceil_div(batch, nb);
-    b16::recon_bwd_pack_grad_kernel<<<dim3(ceil_div(g.ntiles * (kTileVerts / 8), 4 * b16::kGroupsPerThread), ceil_div(batch, 64)), 256, 0,
-                                      st>>>(vertex_grad, w.pose, w.gmax, reinterpret_cast<const float4*>(packed), g.kg, g.ks + g.ke, g.kpad,
-                                            batch, nver, g.ntiles, nb, flags, w.gtiles, w.gscale, w.G);
+    // (the operand tiles of faces between batch and the next multiple of 64 are zero-filled by the blocks that own them)
+    b16::recon_bwd_pack_grad_kernel<<<dim3(ceil_div(g.ntiles * (kTileVerts / 8), 32), ceil_div(batch_padded(batch), 8)), 256, 0, st>>>(
+        vertex_grad, w.pose, w.gmax, reinterpret_cast<const float*>(base + g.mean_offset()), g.ks + g.ke, g.kpad, batch, nver, g.ntiles,
+        nb, flags, w.gtiles, w.gscale, w.G);
     FR_LAUNCHED("recon_bwd_pack_grad_kernel");
     int ctas = sm_count() / nbt;
     if (ctas < 1) ctas = 1;

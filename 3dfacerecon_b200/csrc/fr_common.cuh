@@ -79,7 +79,10 @@ struct BasisGeom {
   int mtiles() const { return (kpad16 + 127) / 128; }
   size_t bwd_offset() const { return scale_offset() + ((size_t)kpad16 * sizeof(float) + 1023) / 1024 * 1024; }
   size_t bwd_bytes() const { return (size_t)ntiles * 3 * (kTileVerts / 16) * 2 * mtiles() * 4096; }
-  size_t bytes() const { return bwd_offset() + bwd_bytes(); }
+  //   [mean_offset, +mean_bytes)      the mean once more as plain fp32 [3][ntiles*128] (the backward contracts it in fp32)
+  size_t mean_offset() const { return bwd_offset() + bwd_bytes(); }
+  size_t mean_bytes() const { return (size_t)3 * ntiles * kTileVerts * sizeof(float); }
+  size_t bytes() const { return mean_offset() + mean_bytes(); }
 };
 inline BasisGeom basis_geom(int nver, int ks, int ke) {
   BasisGeom g;

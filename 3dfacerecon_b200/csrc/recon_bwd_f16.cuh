@@ -96,23 +96,54 @@ pack_basis_bwd_kernel(const float* __restrict__ pc_shape, const float* __restric
   tiles[stage + per_chunk + piece] = wlo;
 }
 
+// plain fp32 copy of the mean, [3][ntiles*128] (zero beyond nver)
+__global__ void __launch_bounds__(256)
+pack_mean_kernel(const float* __restrict__ mu, int nver, int ntiles, unsigned flags, float* __restrict__ mean32) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int npad = ntiles * kTileVerts;
+  if (idx >= 3 * npad) return;
+  const int c = idx / npad, n = idx - c * npad;
+  mean32[idx] = (n < nver) ? mu[(flags & FR_MEAN_INTERLEAVED) ? (size_t)3 * n + c : (size_t)c * nver + n] : 0.0f;
+}
+
 // ---------------------------------------------------------------------------------------------- dv operand (per call)
-// block (64 faces, 4 vertex groups of 8), kGroupsPerThread groups per thread; grid (ceil(ntiles*16 / (4*kGroupsPerThread)),
-// ceil(batch / 64)).  gmax[b*4 + r] = max |g[b][r][:]|.
-// The MEAN column of the contraction, G[b][kmean] = sum mu[(c,n)] dv[b,c,n], is accumulated here in fp32 (mu from the fp32
-// section of the packed basis) and not on the tensor cores: it is orders of magnitude larger than the other columns,
-// d f = sum_k coef_k G_k cancels against it, and the tensor core's truncating accumulation (a relative bias of a few 1e-6
-// over the ~200 accumulation steps of a CTA) would eat the 1e-4 tolerance of d f.
-constexpr int kGroupsPerThread = 8;
+// block = 8 faces (one per warp) x 256 vertices.  Each warp stages its face's three gradient rows in shared memory with
+// coalesced loads (skewed so that a lane can then read ITS 8 consecutive vertices without bank conflicts), rotates, scales
+// and splits them, and the fp16 pieces go back through shared memory so that every global store covers a full 128-byte
+// core matrix (8 faces x 8 vertices).  grid (ceil(ntiles*128 / 256), ceil(batch / 8)).  gmax[b*4 + r] = max |g[b][r][:]|.
+// The MEAN column of the contraction, G[b][kmean] = sum mu[(c,n)] dv[b,c,n], is accumulated here in fp32 and not on the
+// tensor cores: it is orders of magnitude larger than the other columns, d f = sum_k coef_k G_k cancels against it, and the
+// tensor core's truncating accumulation (a relative bias of a few 1e-6 over the ~200 accumulation steps of a CTA, always
+// towards zero) would eat the 1e-4 tolerance of d f.
+constexpr int kPgVerts = 256, kPgRow = kPgVerts + kPgVerts / 32;            // skew: one pad float per 32
+__device__ __forceinline__ int pg_skew(int v) { return v + (v >> 5); }
 __global__ void __launch_bounds__(256)
 recon_bwd_pack_grad_kernel(const float* __restrict__ vertex_grad, const float* __restrict__ pose, const float* __restrict__ gmax,
-                           const float4* __restrict__ packed32, int kg, int kmean, int kpad, int batch, int nver, int ntiles,
-                           int nb, unsigned flags, unsigned char* __restrict__ gtiles, float* __restrict__ gscale,
-                           float* __restrict__ G) {
-  __shared__ float red[4][64];
-  const int fl64 = threadIdx.x & 63, vq = threadIdx.x >> 6;
-  const int b = blockIdx.y * 64 + fl64;
+                           const float* __restrict__ mean32, int kmean, int kpad, int batch, int nver, int ntiles, int nb,
+                           unsigned flags, unsigned char* __restrict__ gtiles, float* __restrict__ gscale, float* __restrict__ G) {
+  // the staged gradient rows and the outgoing fp16 pieces share one buffer (a barrier separates the two uses)
+  __shared__ __align__(16) unsigned char s_buf[sizeof(float) * 8 * 3 * kPgRow];
+  __shared__ float s_mu[3][kPgRow];
+  float (*s_g)[3][kPgRow] = reinterpret_cast<float (*)[3][kPgRow]>(s_buf);
+  uint4 (*pieces)[2][32][8] = reinterpret_cast<uint4 (*)[2][32][8]>(s_buf);   // [c][hi|lo][vertex group][face]
+  static_assert(sizeof(uint4) * 3 * 2 * 32 * 8 <= sizeof(float) * 8 * 3 * kPgRow, "pieces must fit in the staging buffer");
+  const int lane = threadIdx.x & 31, f8 = threadIdx.x >> 5;
+  const int b = blockIdx.y * 8 + f8;
+  const int n0 = blockIdx.x * kPgVerts, npad = ntiles * kTileVerts;
   const bool live = b < batch;
+  for (int i = threadIdx.x; i < 3 * kPgVerts; i += 256) {
+    const int c = i / kPgVerts, v = i - c * kPgVerts;
+    s_mu[c][pg_skew(v)] = (n0 + v < npad) ? mean32[(size_t)c * npad + n0 + v] : 0.0f;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* row = vertex_grad + ((size_t)b * 3 + c) * nver;
+#pragma unroll
+    for (int t = 0; t < kPgVerts / 32; ++t) {
+      const int v = t * 32 + lane;
+      s_g[f8][c][pg_skew(v)] = (live && n0 + v < nver) ? row[n0 + v] : 0.0f;
+    }
+  }
   // per-face power-of-two scale: |dv| <= sqrt(3) max|g| < 2 max|g|;  2 max|g| 2^u in [2^13, 2^14)
   float up = 1.0f;
   if (live) {
@@ -124,7 +155,7 @@ recon_bwd_pack_grad_kernel(const float* __restrict__ vertex_grad, const float* _
       u = max(-100, min(100, 14 - e));
     }
     up = ldexpf(1.0f, u);
-    if (blockIdx.x == 0 && vq == 0) gscale[b] = ldexpf(1.0f, -u);
+    if (blockIdx.x == 0 && lane == 0) gscale[b] = ldexpf(1.0f, -u);
   }
   const float ysign = (flags & FR_YFLIP_NONE) ? 1.0f : -1.0f;
   float R[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -132,50 +163,49 @@ recon_bwd_pack_grad_kernel(const float* __restrict__ vertex_grad, const float* _
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = pose[(size_t)b * kPoseStride + 12 + i];
   }
-  const int bt = b / nb, fl = b % nb;
-  const size_t stage_b = b_stage_bytes(nb);
+  __syncthreads();
   float gmean = 0.0f;
-  for (int r = 0; r < kGroupsPerThread; ++r) {
-    const int vg = (blockIdx.x * kGroupsPerThread + r) * 4 + vq;           // global group of 8 vertices
-    if (vg >= ntiles * (kTileVerts / 8)) break;
-    const int tile = vg / (kTileVerts / 8), j = (vg % (kTileVerts / 8)) / 2, vh = vg & 1;
-    __half hi[3][8], lo[3][8];
+  __half hi[3][8], lo[3][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int n = vg * 8 + i;
-      float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-      if (live && n < nver) {
-        const float* gp = vertex_grad + (size_t)b * 3 * nver + n;
-        const float gx = gp[0], gy = ysign * gp[nver], gz = gp[2 * (size_t)nver];
-        d0 = fmaf(R[6], gz, fmaf(R[3], gy, R[0] * gx));                     // same expression as recon_bwd_simt_kernel
-        d1 = fmaf(R[7], gz, fmaf(R[4], gy, R[1] * gx));
-        d2 = fmaf(R[8], gz, fmaf(R[5], gy, R[2] * gx));
-        const float4* mp = packed32 + ((size_t)(tile * 3) * kg + (kmean >> 2)) * kTileVerts + (n - tile * kTileVerts);
-        gmean = fmaf(f4_get(mp[0], kmean & 3), d0, gmean);
-        gmean = fmaf(f4_get(mp[(size_t)kg * kTileVerts], kmean & 3), d1, gmean);
-        gmean = fmaf(f4_get(mp[(size_t)2 * kg * kTileVerts], kmean & 3), d2, gmean);
-      }
-      const float d[3] = {d0 * up, d1 * up, d2 * up};
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        hi[c][i] = __float2half_rn(d[c]);
-        lo[c][i] = __float2half_rn(d[c] - __half2float(hi[c][i]));
-      }
-    }
-    unsigned char* base = gtiles + ((size_t)bt * ntiles + tile) * 3 * kChunksPerTile * stage_b;
+  for (int i = 0; i < 8; ++i) {
+    const int sv = pg_skew(lane * 8 + i);
+    const float gx = s_g[f8][0][sv], gy = ysign * s_g[f8][1][sv], gz = s_g[f8][2][sv];
+    const float d0 = fmaf(R[6], gz, fmaf(R[3], gy, R[0] * gx));             // same expression as recon_bwd_simt_kernel
+    const float d1 = fmaf(R[7], gz, fmaf(R[4], gy, R[1] * gx));
+    const float d2 = fmaf(R[8], gz, fmaf(R[5], gy, R[2] * gx));
+    gmean = fmaf(s_mu[0][sv], d0, gmean);
+    gmean = fmaf(s_mu[1][sv], d1, gmean);
+    gmean = fmaf(s_mu[2][sv], d2, gmean);
+    const float d[3] = {d0 * up, d1 * up, d2 * up};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      unsigned char* st = base + ((size_t)c * kChunksPerTile + j) * stage_b + (size_t)(fl >> 3) * 256 + vh * 128 + (fl & 7) * 16;
-      uint4 whi, wlo;
-      memcpy(&whi, hi[c], 16);
-      memcpy(&wlo, lo[c], 16);
-      *reinterpret_cast<uint4*>(st) = whi;
-      *reinterpret_cast<uint4*>(st + stage_b / 2) = wlo;
+      hi[c][i] = __float2half_rn(d[c]);
+      lo[c][i] = __float2half_rn(d[c] - __half2float(hi[c][i]));
     }
   }
-  red[vq][fl64] = gmean;
+  __syncthreads();                                                         // every thread is done with s_g
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    memcpy(&pieces[c][0][lane][f8], hi[c], 16);
+    memcpy(&pieces[c][1][lane][f8], lo[c], 16);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmean += __shfl_xor_sync(0xFFFFFFFFu, gmean, o);
+  if (lane == 0 && live) atomicAdd(G + (size_t)b * kpad + kmean, gmean);
   __syncthreads();
-  if (vq == 0 && live) atomicAdd(G + (size_t)b * kpad + kmean, (red[0][fl64] + red[1][fl64]) + (red[2][fl64] + red[3][fl64]));
+  // write out: one 16-byte piece per thread and trip, 8 consecutive threads = one 128-byte core matrix
+  const int b8 = blockIdx.y * 8;                                           // first face of the block (multiple of 8)
+  const int bt = b8 / nb, fg = (b8 % nb) >> 3;
+  const size_t stage_b = b_stage_bytes(nb);
+  for (int p = threadIdx.x; p < 3 * 2 * 32 * 8; p += 256) {
+    const int ff = p & 7, vgl = (p >> 3) & 31, half = (p >> 8) & 1, c = p >> 9;
+    const int vgg = blockIdx.x * 32 + vgl;
+    if (vgg >= ntiles * (kTileVerts / 8)) continue;
+    const int t2 = vgg / (kTileVerts / 8), j = (vgg % (kTileVerts / 8)) / 2, vh = vgg & 1;
+    unsigned char* dst = gtiles + (((size_t)bt * ntiles + t2) * 3 + c) * kChunksPerTile * stage_b + (size_t)j * stage_b +
+                         (size_t)half * (stage_b / 2) + (size_t)fg * 256 + vh * 128 + ff * 16;
+    *reinterpret_cast<uint4*>(dst) = pieces[c][half][vgl][ff];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- the contraction
