@@ -167,23 +167,30 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
       FR_LAUNCHED("raster_pack_kernel");
     }
     const unsigned gx = (unsigned)ceil_div(ntri, kRasterThreads);
+    const bool pdl = pdl_enabled();   // dependent launches: the kernels call pdl_wait() before touching their predecessor's output
+    const float4* crec = rec;
     if (batch >= 8)
-      raster_keys_kernel<8><<<dim3(gx, ceil_div(batch, 8)), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
+      FR_CUDA(launch_pdl(raster_keys_kernel<8>, dim3(gx, ceil_div(batch, 8)), dim3(kRasterThreads), 0, st, pdl, crec, tri, keys, batch, nver,
+                         ntri, height, width));
     else if (batch >= 3)
-      raster_keys_kernel<4><<<dim3(gx, ceil_div(batch, 4)), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
+      FR_CUDA(launch_pdl(raster_keys_kernel<4>, dim3(gx, ceil_div(batch, 4)), dim3(kRasterThreads), 0, st, pdl, crec, tri, keys, batch, nver,
+                         ntri, height, width));
     else
-      raster_keys_kernel<1><<<dim3(gx, batch), kRasterThreads, 0, st>>>(rec, tri, keys, batch, nver, ntri, height, width);
+      FR_CUDA(launch_pdl(raster_keys_kernel<1>, dim3(gx, batch), dim3(kRasterThreads), 0, st, pdl, crec, tri, keys, batch, nver, ntri,
+                         height, width));
     FR_LAUNCHED("raster_keys_kernel");
   } else if (!records_ready) {
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   }
   const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
+  const unsigned long long* ckeys = keys;
+  const bool rpdl = pdl_enabled() && ntri > 0;   // (with no triangles the predecessor is a memset, not a kernel that triggers)
   if (texture_image != nullptr || normal != nullptr)
-    raster_resolve_kernel<true><<<rgrid, kRasterThreads, 0, st>>>(
-        keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
+    FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, rpdl, ckeys, vertex, tri, texture,
+                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix));
   else
-    raster_resolve_kernel<false><<<rgrid, kRasterThreads, 0, st>>>(
-        keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix);
+    FR_CUDA(launch_pdl(raster_resolve_kernel<false>, rgrid, dim3(kRasterThreads), 0, st, rpdl, ckeys, vertex, tri, texture,
+                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix));
   FR_LAUNCHED("raster_resolve_kernel");
   return FR_OK;
 }

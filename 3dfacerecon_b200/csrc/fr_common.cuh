@@ -99,6 +99,29 @@ inline BasisGeom basis_geom(int nver, int ks, int ke) {
 }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become resident while its predecessor in
+// the stream is still running; it must call pdl_wait() before touching anything the predecessor writes (and before
+// writing anything the predecessor reads).  The predecessor calls pdl_trigger() once its blocks are resident.  Both are
+// no-ops for normally launched kernels.  This hides the launch / drain gap between the kernels of one step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool dependent,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dependent ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // 128-bit streaming load through the read-only path without polluting L1 (basis is read once per CTA).
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;

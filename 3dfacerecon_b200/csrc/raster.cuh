@@ -39,6 +39,7 @@ constexpr int kSnapPerThread = 4;
 __global__ void __launch_bounds__(kRasterThreads)
 raster_pack_kernel(const float* __restrict__ vertex, float4* __restrict__ rec, unsigned long long* __restrict__ keys,
                    int nver, int npix, int width, int height) {
+  pdl_trigger();
   const int b = blockIdx.y;
   const int base = blockIdx.x * (kRasterThreads * kSnapPerThread) + threadIdx.x;
   const float* vx = vertex + (size_t)b * 3 * nver;
@@ -103,6 +104,8 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
 
   const int tid = threadIdx.x;
   if (tid == 0) q_count = 0u;
+  pdl_trigger();   // the resolve pass may become resident once every block of this grid has started
+  pdl_wait();      // records and cleared keys of the producing kernel (pack pass or reconstruction epilogue) are complete
   __syncthreads();
 
   const int t = blockIdx.x * kRasterThreads + tid;
@@ -194,6 +197,7 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
                       const float* __restrict__ tri, const float* __restrict__ texture, long long texture_batch_stride,
                       float* __restrict__ depth, float* __restrict__ texture_image, float* __restrict__ normal,
                       float* __restrict__ tri_ind, int nver, int ntri, int npix) {
+  pdl_wait();      // every atomicMax of the keys kernel has landed
   const int b = blockIdx.y;
   const int base = blockIdx.x * (kRasterThreads * kResolvePerThread) + threadIdx.x;
   const size_t fo = (size_t)b * npix;

@@ -181,6 +181,7 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
                       int ke, int kpad16, unsigned flags, unsigned char* __restrict__ bsplit, float* __restrict__ pose16) {
   __shared__ float red[8];
   __shared__ float s_pose[kPoseStride];
+  pdl_trigger();                                   // the reconstruction kernel may become resident (it waits before reading our output)
   const int b = blockIdx.x, tid = threadIdx.x;
   const bool live = b < batch;
   float cmax = 0.0f;
@@ -265,6 +266,8 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();                                   // the rasterizer's blocks may become resident (they wait before reading records / keys)
+  pdl_wait();                                      // the prep kernel's coefficient operands and poses are complete from here on
   for (int i = threadIdx.x; i < kN * kPose16Stride; i += kThreads) s_pose[i] = pose16[(size_t)b0 * kPose16Stride + i];
   tc_fence_before();
   __syncthreads();
@@ -408,7 +411,7 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + g.ks + g.ke;
   f16::recon_prep_f16_kernel<<<bpad, 256, 0, st>>>(params, inv_scale, dparam, batch, g.ks, g.ke, g.kpad16, flags,
-                                                  static_cast<unsigned char*>(bsplit), pose16);
+                                                  static_cast<unsigned char*>(bsplit), pose16);   // normal launch: waits for everything before
   FR_LAUNCHED("recon_prep_f16_kernel");
   const f16::SmemLayout L = f16::smem_layout(g.nch16);
   const int nbt = ceil_div(batch, f16::kN);
@@ -416,9 +419,9 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
   if (ctas < 1) ctas = 1;
   if (ctas > g.ntiles) ctas = g.ntiles;
   FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  f16::recon_fwd_f16_kernel<<<dim3(ctas, nbt), f16::kThreads, L.total, st>>>(
-      base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), pose16, out, batch, nver, g.nch16, g.ntiles, im_size, flags,
-      keys != nullptr ? key_vec_per_face : 0);
+  FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel, dim3(ctas, nbt), dim3(f16::kThreads), L.total, st, pdl_enabled(),
+                     base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), out, batch, nver,
+                     g.nch16, g.ntiles, im_size, flags, keys != nullptr ? key_vec_per_face : 0));
   FR_LAUNCHED("recon_fwd_f16_kernel");
   return FR_OK;
 }

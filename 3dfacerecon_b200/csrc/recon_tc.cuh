@@ -415,6 +415,11 @@ inline int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   return e ? std::atoi(e) : dflt;
 }
+// FR_PDL=0 launches every kernel with full stream serialisation (A/B switch for the programmatic dependent launches)
+inline bool pdl_enabled() {
+  static const int v = env_int("FR_PDL", 1);
+  return v != 0;
+}
 
 // FR_RECON_PATH = simt | tf32 | f16 overrides the forward dispatch (debugging / A-B comparisons): 1, 2, 3; 0 = default.
 inline int recon_path_override() {
