@@ -176,6 +176,57 @@ def test_fused_call_matches_separate_calls(bfm, B):
             assert bool(torch.isnan(vertex).all())                         # untouched
 
 
+@pytest.mark.parametrize("B,H,W", [(70, 33, 31), (9, 48, 64), (130, 20, 20)])
+def test_fused_call_small_model_odd_shapes(small_model, B, H, W):
+    """The fused call on a small model (K = 18: one 16-k chunk pair, one M tile), several 64-face batch tiles, non-square images
+    and an odd pixel count (keys cleared by memset instead of the reconstruction epilogue): bit-identical to the two calls."""
+    lib, check = fr("_lib").lib(), fr("_lib").check
+    ks, ke = small_model["ndim_shape"], small_model["ndim_exp"]
+    p = fr("synth").sample_params_constrained(B, ks, ke, max(H, W), seed=7 + B)
+    dm = fr("model").DeviceModel(small_model, DEV)
+    pt = torch.from_numpy(p).to(DEV)
+    sp = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, H, W), dtype=torch.uint8, device=DEV)
+    rb = lib.fr_recon_workspace_bytes(B, dm.nver, ks, ke)
+    vp = torch.empty((B, 3, dm.nver), device=DEV)
+    want_d, want_t = torch.empty((B, H, W, 1), device=DEV), torch.empty((B, H, W, 1), device=DEV)
+    check(lib.fr_recon_project_forward(pt.data_ptr(), dm.packed.data_ptr(), vp.data_ptr(), B, dm.nver, ks, ke, float(max(H, W)),
+                                       dm.run_flags, ws.data_ptr(), rb, sp))
+    check(lib.fr_render_depth_forward(vp.data_ptr(), dm.tri.data_ptr(), None, 0, want_d.data_ptr(), None, None, want_t.data_ptr(), B,
+                                      dm.nver, dm.ntri, H, W, ws.data_ptr() + rb, ws.numel() - rb, sp))
+    ws.fill_(0x5C)
+    got_d, got_t = torch.empty_like(want_d), torch.empty_like(want_t)
+    check(lib.fr_recon_render_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), None, got_d.data_ptr(), got_t.data_ptr(),
+                                      B, dm.nver, dm.ntri, ks, ke, H, W, float(max(H, W)), dm.run_flags, ws.data_ptr(), ws.numel(), sp))
+    torch.cuda.synchronize()
+    assert (want_t >= 0).sum() > 0.05 * want_t.numel()                    # the faces are in frame
+    assert got_d.cpu().numpy().tobytes() == want_d.cpu().numpy().tobytes()
+    assert got_t.cpu().numpy().tobytes() == want_t.cpu().numpy().tobytes()
+    want_vp = recon.vertices_transform(p, small_model, max(H, W))
+    assert np.abs(vp.cpu().numpy() - want_vp).max() <= VERT_TOL * np.abs(want_vp).max()
+
+
+@pytest.mark.parametrize("B", [4, 20, 70, 260])
+def test_small_model_backward_all_paths(small_model, B):
+    """Reconstruction backward on the small model: FFMA kernel (B = 4) and the tcgen05 contraction with one M tile, one and
+    several 64-face operand groups and two 256-face batch tiles (B = 260), against the float64 restatement."""
+    ks, ke = small_model["ndim_shape"], small_model["ndim_exp"]
+    p = fr("synth").sample_params_constrained(B, ks, ke, 64, seed=90 + B, full_range=True)
+    nver = small_model["mu"].size // 3
+    g = np.random.default_rng(B).normal(size=(B, 3, nver)).astype(np.float32)
+    g[B // 2] *= 1e-3                                                      # per-face operand scales must not leak between faces
+    dm = fr("model").DeviceModel(small_model, DEV)
+    pt = torch.from_numpy(p).to(DEV).requires_grad_(True)
+    vp = fr("nets.network").recon_project(pt, dm, 64)
+    (vp * torch.from_numpy(g).to(DEV)).sum().backward()
+    got = pt.grad.cpu().numpy().astype(np.float64)
+    want = recon.vertices_transform_backward(p, small_model, g)
+    assert not got[:, 0:3].any()
+    for sl in (slice(3, 6), slice(6, 7), slice(7, 7 + ks), slice(7 + ks, 7 + ks + ke)):
+        scale = np.abs(want[:, sl]).max(axis=1, keepdims=True)
+        assert (np.abs(got[:, sl] - want[:, sl]) <= GRAD_TOL * scale).all(), sl
+
+
 def test_session_pipelined_slots_match_synchronous(bfm):
     """fr_session_submit / fr_session_wait: batches alternating over the two slots (different sizes, outputs in pinned
     memory) give bit-identical results to the synchronous call, and a busy slot refuses a second submit."""
