@@ -371,9 +371,25 @@ def run_ours(args):
                 ops.render_depth(vp, dm.tri, dm.vertex_code.unsqueeze(0), img1)
 
         ms_1 = time_torch(fwd1, 20)
+        # config 3's per-GPU share at 8 GPUs (512 faces) and the whole 4096-face batch on this one GPU, fused call, depth + tri_ind
+        big = {}
+        for B3 in (512, 4096):
+            p3 = torch.from_numpy(synth.sample_params_constrained(B3, seed=3)).to(dev)
+            d3 = torch.empty((B3, H, W, 1), dtype=torch.float32, device=dev)
+            t3 = torch.empty((B3, H, W, 1), dtype=torch.float32, device=dev)
+            ws3 = torch.empty(lib.fr_pipeline_workspace_bytes(B3, nver, ks, ke, H, W), dtype=torch.uint8, device=dev)
+
+            def fwd3():
+                check(lib.fr_recon_render_forward(p3.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), None, d3.data_ptr(),
+                                                  t3.data_ptr(), B3, nver, ntri, ks, ke, H, W, IM_SIZE, dm.run_flags, ws3.data_ptr(),
+                                                  ws3.numel(), sp))
+            ms3 = time_torch(fwd3, 5)
+            big["config3_b%d_fwd" % B3] = {"ms": ms3, "faces_per_s": B3 / (ms3 * 1e-3), "api": "fr_recon_render_forward, one call"}
+            del p3, d3, t3, ws3
         extras = {"config4_b256_fwd_bwd": {"ms": ms_fb, "faces_per_s": B4 / (ms_fb * 1e-3), "fwd_only_ms": ms_f4,
                                            "api": "recon_project + render_depth (all four outputs) + autograd backward, torch API, L2 warm"},
                   "config1_b1_fwd": {"ms": ms_1, "api": "recon_project + render_depth (all four outputs), torch API, L2 warm"}}
+        extras.update(big)
         del p4, img4, gd4
 
     # end to end through the host-buffer C-ABI session: every step copies its params in from pinned host memory and its
