@@ -197,6 +197,7 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
                       const float* __restrict__ tri, const float* __restrict__ texture, long long texture_batch_stride,
                       float* __restrict__ depth, float* __restrict__ texture_image, float* __restrict__ normal,
                       float* __restrict__ tri_ind, int nver, int ntri, int npix) {
+  __shared__ __align__(16) float s_attr[kAttributes ? 2 : 1][kAttributes ? 3 * kRasterThreads * kResolvePerThread : 4];
   pdl_wait();      // every atomicMax of the keys kernel has landed
   const int b = blockIdx.y;
   const int base = blockIdx.x * (kRasterThreads * kResolvePerThread) + threadIdx.x;
@@ -245,16 +246,33 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
     }
     depth[o] = d;
     tri_ind[o] = ti;
-    if (kAttributes) {
-      if (normal != nullptr) {
-        normal[3 * o + 0] = n[0];
-        normal[3 * o + 1] = n[1];
-        normal[3 * o + 2] = n[2];
-      }
-      if (texture_image != nullptr) {
-        texture_image[3 * o + 0] = tx[0];
-        texture_image[3 * o + 1] = tx[1];
-        texture_image[3 * o + 2] = tx[2];
+    if (kAttributes) {   // 3-channel outputs go through shared memory: a 12-byte-stride store per channel triples the L2 write traffic
+      const int pl = p - blockIdx.x * (kRasterThreads * kResolvePerThread);
+      s_attr[0][3 * pl + 0] = n[0];
+      s_attr[0][3 * pl + 1] = n[1];
+      s_attr[0][3 * pl + 2] = n[2];
+      s_attr[1][3 * pl + 0] = tx[0];
+      s_attr[1][3 * pl + 1] = tx[1];
+      s_attr[1][3 * pl + 2] = tx[2];
+    }
+  }
+  if (kAttributes) {
+    __syncthreads();
+    constexpr int kBlockPix = kRasterThreads * kResolvePerThread;
+    const int p0 = blockIdx.x * kBlockPix;
+    const int cnt = min(kBlockPix, npix - p0) * 3;                         // floats of this block per attribute
+    float* outs[2] = {normal, texture_image};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (outs[a] == nullptr) continue;
+      float* dst = outs[a] + 3 * (fo + p0);
+      if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (int i = threadIdx.x * 4; i < cnt; i += kRasterThreads * 4) {
+          if (i + 4 <= cnt) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(&s_attr[a][i]);
+          else for (int e = i; e < cnt; ++e) dst[e] = s_attr[a][e];
+        }
+      } else {
+        for (int i = threadIdx.x; i < cnt; i += kRasterThreads) dst[i] = s_attr[a][i];
       }
     }
   }
