@@ -39,6 +39,8 @@ SIGNATURES = {
     "fr_render_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fr_render_depth_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "fr_render_depth_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fr_rendering_layer_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "fr_rendering_layer_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fr_pipeline_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "fr_recon_render_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
     "fr_session_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u, _i, ctypes.POINTER(_vp)]),

@@ -139,7 +139,7 @@ int recon_project_forward_impl(const float* params, const float* packed, const R
 int render_depth_forward_impl(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                               float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
                               int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream,
-                              bool records_ready) {
+                              bool records_ready, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false}) {
   FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
              "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
   // render_depth_op.cc:161-166: the reference refuses ntri >= 10M (its static scratch); nver < 2^24 keeps float indices exact
@@ -187,10 +187,10 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
   const bool rpdl = pdl_enabled() && ntri > 0;   // (with no triangles the predecessor is a memset, not a kernel that triggers)
   if (texture_image != nullptr || normal != nullptr)
     FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, rpdl, ckeys, vertex, tri, texture,
-                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix));
+                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
   else
     FR_CUDA(launch_pdl(raster_resolve_kernel<false>, rgrid, dim3(kRasterThreads), 0, st, rpdl, ckeys, vertex, tri, texture,
-                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix));
+                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
   FR_LAUNCHED("raster_resolve_kernel");
   return FR_OK;
 }
@@ -366,7 +366,36 @@ int fr_render_depth_backward(const float* depth_grad, const float* tri, const fl
   const int npix = height * width;
   FR_CUDA(cudaMemsetAsync(vertex_grad, 0, sizeof(float) * (size_t)batch * 3 * nver, st));
   render_backward_kernel<<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(depth_grad, tri, tri_ind,
-                                                                                              vertex_grad, nver, ntri, npix);
+                                                                                              vertex_grad, nver, ntri, npix,
+                                                                                              nullptr, nullptr, nullptr);
+  FR_LAUNCHED("render_backward_kernel");
+  return FR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ rendering layer
+int fr_rendering_layer_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
+                               const float* im_gray, float* pncc, float* normalimg, float* maskimg, float* depthimg,
+                               float* raw_depth, float* tri_ind, int batch, int nver, int ntri, int height, int width,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  FR_REQUIRE(batch <= 0 || (pncc && normalimg && maskimg && depthimg && texture), "null pointer argument");
+  const LayerOut layer = {maskimg, im_gray, raw_depth, true};
+  return render_depth_forward_impl(vertex, tri, texture, texture_batch_stride, depthimg, pncc, normalimg, tri_ind, batch, nver, ntri,
+                                   height, width, workspace, workspace_bytes, stream, false, layer);
+}
+
+int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg_grad, const float* im_gray, const float* raw_depth,
+                                const float* tri, const float* tri_ind, float* vertex_grad, int batch, int nver, int ntri,
+                                int height, int width, void* stream) {
+  FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
+             "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
+  FR_REQUIRE((long long)height * width < (1ll << 31), "image too large");
+  if (batch == 0) return FR_OK;
+  FR_REQUIRE(raw_depth && (tri || ntri == 0) && tri_ind && vertex_grad && (depthimg_grad || maskimg_grad), "null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int npix = height * width;
+  FR_CUDA(cudaMemsetAsync(vertex_grad, 0, sizeof(float) * (size_t)batch * 3 * nver, st));
+  render_backward_kernel<<<dim3(ceil_div(npix, kRasterThreads), batch), kRasterThreads, 0, st>>>(
+      depthimg_grad, tri, tri_ind, vertex_grad, nver, ntri, npix, maskimg_grad, im_gray, raw_depth);
   FR_LAUNCHED("render_backward_kernel");
   return FR_OK;
 }

@@ -191,12 +191,23 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
 // from the key (a pure streaming pass); the vertex gathers only happen when normals / texture are requested or the
 // decoded depth is a signed-zero tie.
 constexpr int kResolvePerThread = 4;
+// Extra outputs of FaceRecNet.rendering_layer (nets/network.py:184-199) when the post-processing is fused into the resolve
+// pass (fr_rendering_layer_forward): `texture_image` then receives pncc = clip(tex, 1e-6, 1), `normal` the normals flipped to
+// +z and normalised, `depth` max(depth, 1e-6); maskimg = clip(depth, 1e-6, 1) * im_gray; raw_depth keeps the op's depth for
+// the gradient gates.  All pointers null = the plain op.
+struct LayerOut {
+  float* maskimg;
+  const float* im_gray;   // [B,H,W,1] or null (mask only)
+  float* raw_depth;
+  bool enabled;
+};
+
 template <bool kAttributes>
 __global__ void __launch_bounds__(kRasterThreads)
 raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ vertex,
                       const float* __restrict__ tri, const float* __restrict__ texture, long long texture_batch_stride,
                       float* __restrict__ depth, float* __restrict__ texture_image, float* __restrict__ normal,
-                      float* __restrict__ tri_ind, int nver, int ntri, int npix) {
+                      float* __restrict__ tri_ind, int nver, int ntri, int npix, LayerOut layer) {
   __shared__ __align__(16) float s_attr[kAttributes ? 2 : 1][kAttributes ? 3 * kRasterThreads * kResolvePerThread : 4];
   pdl_wait();      // every atomicMax of the keys kernel has landed
   const int b = blockIdx.y;
@@ -244,6 +255,26 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
         }
       }
     }
+    if (kAttributes && layer.enabled) {
+      // nets/network.py:185-199, same float operations in the same order as the torch / TF elementwise passes
+      if (layer.raw_depth != nullptr) layer.raw_depth[o] = d;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tx[c] = fminf(fmaxf(tx[c], 1e-6f), 1.0f);                     // :185 pncc
+      if (n[2] < 0.0f) {                                                                          // :188-189
+        n[0] = __fmul_rn(-1.0f, n[0]);
+        n[1] = __fmul_rn(-1.0f, n[1]);
+        n[2] = __fmul_rn(-1.0f, n[2]);
+      }
+      float mag = __fadd_rn(__fadd_rn(__fmul_rn(n[0], n[0]), __fmul_rn(n[1], n[1])), __fmul_rn(n[2], n[2]));   // :190
+      mag = (mag > 1e-6f) ? mag : 1.0f;                                                          // :191
+      const float den = __fadd_rn(__fsqrt_rn(mag), 1e-6f);                                        // :192
+      n[0] = __fdiv_rn(n[0], den);
+      n[1] = __fdiv_rn(n[1], den);
+      n[2] = __fdiv_rn(n[2], den);
+      const float m = fminf(fmaxf(d, 1e-6f), 1.0f);                                               // :195
+      layer.maskimg[o] = (layer.im_gray != nullptr) ? __fmul_rn(m, __ldg(layer.im_gray + o)) : m; // :196
+      d = fmaxf(d, 1e-6f);                                                                        // :199
+    }
     depth[o] = d;
     tri_ind[o] = ti;
     if (kAttributes) {   // 3-channel outputs go through shared memory: a 12-byte-stride store per channel triples the L2 write traffic
@@ -281,7 +312,9 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
 // Backward (render_depth_op.cc:325-368).  vertex_grad must be zero on entry (the API memsets it).
 __global__ void __launch_bounds__(kRasterThreads)
 render_backward_kernel(const float* __restrict__ depth_grad, const float* __restrict__ tri,
-                       const float* __restrict__ tri_ind, float* __restrict__ vertex_grad, int nver, int ntri, int npix) {
+                       const float* __restrict__ tri_ind, float* __restrict__ vertex_grad, int nver, int ntri, int npix,
+                       const float* __restrict__ mask_grad, const float* __restrict__ im_gray,
+                       const float* __restrict__ raw_depth) {
   const int p = blockIdx.x * kRasterThreads + threadIdx.x;
   const int b = blockIdx.y;
   const unsigned lane = threadIdx.x & 31u;
@@ -292,7 +325,21 @@ render_backward_kernel(const float* __restrict__ depth_grad, const float* __rest
     const float tf = __ldg(tri_ind + o);
     if (tf >= 0.0f && tf < (float)ntri) {
       t = (int)tf;
-      share = __fdiv_rn(__fmul_rn(__ldg(depth_grad + o), 1.0f), 3.0f);  // (g * 1.0f) / 3.0f, :361
+      float g;
+      if (raw_depth == nullptr) {
+        g = __ldg(depth_grad + o);
+      } else {
+        // fused rendering layer: the op's depth_grad is what autodiff would have summed from its two consumers,
+        // max(depth, 1e-6) (passes where depth >= 1e-6) and clip(depth, 1e-6, 1) * im_gray (passes inside the clip range)
+        const float dr = __ldg(raw_depth + o);
+        g = 0.0f;
+        if (depth_grad != nullptr && dr >= 1e-6f) g = __ldg(depth_grad + o);
+        if (mask_grad != nullptr && dr >= 1e-6f && dr <= 1.0f) {
+          const float gm = __ldg(mask_grad + o);
+          g = __fadd_rn(g, (im_gray != nullptr) ? __fmul_rn(gm, __ldg(im_gray + o)) : gm);
+        }
+      }
+      share = __fdiv_rn(__fmul_rn(g, 1.0f), 3.0f);  // (g * 1.0f) / 3.0f, :361
     }
   }
   // warp aggregation: lanes that hit the same triangle add their shares once (lane order => deterministic

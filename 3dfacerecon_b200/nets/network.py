@@ -6,7 +6,7 @@ Only the methods on the params -> depth-map path are mirrored, with the referenc
 here                           reference                              what runs
 =============================  =====================================  ==========================================
 ``vertices_transform``         ``nets/network.py:140-171``            ``fr_recon_project_forward/backward`` (CUDA)
-``rendering_layer``            ``nets/network.py:174-201``            ``render_depth`` (CUDA) + torch elementwise
+``rendering_layer``            ``nets/network.py:174-201``            ``fr_rendering_layer_forward/backward`` (CUDA)
 ``depth_rendering_layer``      ``nets/network.py:300-308``            both of the above
 ``set_constraints``            ``nets/network.py:204-218``            torch elementwise
 ``parse_pose_params``          ``nets/network.py:253-263``            slicing
@@ -71,6 +71,58 @@ class _ReconProject(torch.autograd.Function):
         return dparams, None, None, None
 
 
+class _RenderingLayer(torch.autograd.Function):
+    """``FaceRecNet.rendering_layer`` (``nets/network.py:174-201``) with the four post-processing passes inside the resolve
+    kernel (``fr_rendering_layer_forward``).  Gradients flow to ``vertex_proj`` from ``depthimg`` and ``maskimg`` only, as in
+    the reference (the op registers no gradient for texture / normal, ``rendering_layer/ops.py:95``)."""
+
+    @staticmethod
+    def forward(ctx, vertex_proj, tri, texture, im_gray, height, width):
+        if not vertex_proj.is_cuda:
+            raise RuntimeError("vertex_proj is on %s: rendering_layer has no CPU path" % vertex_proj.device)
+        ver, tri = vertex_proj.float().contiguous(), tri.float().contiguous()
+        B, N, T = int(ver.shape[0]), int(ver.shape[2]), int(tri.shape[1])
+        dev = ver.device
+        if texture.dim() == 2 or (texture.stride(0) == 0 and texture[0].is_contiguous()):
+            tex = (texture if texture.dim() == 2 else texture[0]).float().contiguous()
+            tex_ptr, tex_stride, keep = tex.data_ptr(), 0, tex
+        else:
+            tex = texture.float().contiguous()
+            tex_ptr, tex_stride, keep = tex.data_ptr(), 3 * N, tex
+        gray = None if im_gray is None else im_gray.float().contiguous()
+        new = lambda c: torch.empty((B, height, width, c), dtype=torch.float32, device=dev)
+        pncc, normalimg, maskimg, depthimg, raw, tri_ind = new(3), new(3), new(1), new(1), new(1), new(1)
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, lib().fr_render_workspace_bytes(B, N, height, width))
+            check(lib().fr_rendering_layer_forward(ver.data_ptr(), tri.data_ptr(), tex_ptr, tex_stride,
+                                                   None if gray is None else gray.data_ptr(), pncc.data_ptr(), normalimg.data_ptr(),
+                                                   maskimg.data_ptr(), depthimg.data_ptr(), raw.data_ptr(), tri_ind.data_ptr(), B, N, T,
+                                                   height, width, ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        del keep
+        ctx.save_for_backward(tri, tri_ind, raw, gray if gray is not None else raw.new_empty(0))
+        ctx.dims = (B, N, T, height, width)
+        ctx.mark_non_differentiable(pncc, normalimg)
+        return pncc, normalimg, maskimg, depthimg
+
+    @staticmethod
+    def backward(ctx, _g_pncc, _g_normal, g_mask, g_depth):
+        tri, tri_ind, raw, gray = ctx.saved_tensors
+        B, N, T, H, W = ctx.dims
+        dev = raw.device
+        g_mask = None if g_mask is None else g_mask.float().contiguous()
+        g_depth = None if g_depth is None else g_depth.float().contiguous()
+        vertex_grad = torch.empty((B, 3, N), dtype=torch.float32, device=dev)
+        if g_mask is None and g_depth is None:
+            return vertex_grad.zero_(), None, None, None, None, None
+        with torch.cuda.device(dev):
+            check(lib().fr_rendering_layer_backward(None if g_depth is None else g_depth.data_ptr(),
+                                                    None if g_mask is None else g_mask.data_ptr(),
+                                                    gray.data_ptr() if gray.numel() else None, raw.data_ptr(), tri.data_ptr(),
+                                                    tri_ind.data_ptr(), vertex_grad.data_ptr(), B, N, T, H, W,
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+        return vertex_grad, None, None, None, None, None
+
+
 def recon_project(params, model: DeviceModel, im_size=200, flags=None):
     """Functional form of ``vertices_transform`` for a [B,d] parameter tensor."""
     return _ReconProject.apply(params, model, float(im_size), model.run_flags if flags is None else int(flags))
@@ -110,6 +162,11 @@ class FaceRecNet:
 
     # ------------------------------------------------------------------ network.py:174-201
     def rendering_layer(self, vertex_proj, triangles, colors):
+        """network.py:174-201 in one kernel pass after the rasterizer; ``rendering_layer_unfused`` is the
+        literal transcription it is tested against."""
+        return _RenderingLayer.apply(vertex_proj, triangles, colors, self.im_gray, self.im_size, self.im_size)
+
+    def rendering_layer_unfused(self, vertex_proj, triangles, colors):
         B = vertex_proj.shape[0]
         texture = colors if colors.dim() == 3 else colors.unsqueeze(0).expand(B, -1, -1)      # tf.tile, network.py:179
         im_gray = self.im_gray

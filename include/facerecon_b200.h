@@ -100,6 +100,21 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
 int fr_render_depth_backward(const float* depth_grad, const float* tri, const float* tri_ind, float* vertex_grad,
                              int batch, int nver, int ntri, int height, int width, void* stream);
 
+/* ---- FaceRecNet.rendering_layer (nets/network.py:174-201): render_depth + its four elementwise post-processing passes
+ * in the resolve kernel.  pncc [B,H,W,3] = clip(texture_image, 1e-6, 1); normalimg [B,H,W,3] = normals flipped
+ * to +z and divided by sqrt(mag)+1e-6 (mag <= 1e-6 -> 1); maskimg [B,H,W,1] = clip(depth, 1e-6, 1) * im_gray (im_gray NULL:
+ * the mask alone); depthimg [B,H,W,1] = max(depth, 1e-6); raw_depth [B,H,W,1] = the op's depth (optional, needed by the
+ * backward's gates).  Same workspace as fr_render_depth_forward. */
+int fr_rendering_layer_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
+                               const float* im_gray, float* pncc, float* normalimg, float* maskimg, float* depthimg,
+                               float* raw_depth, float* tri_ind, int batch, int nver, int ntri, int height, int width,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* Its gradient as autodiff composes it: depth_grad of the op = depthimg_grad where depth >= 1e-6, plus maskimg_grad * im_gray
+ * where 1e-6 <= depth <= 1 (either gradient may be NULL), then RenderDepthGrad. */
+int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg_grad, const float* im_gray, const float* raw_depth,
+                                const float* tri, const float* tri_ind, float* vertex_grad, int batch, int nver, int ntri,
+                                int height, int width, void* stream);
+
 /* ---- fused: params -> depth map (the north-star path in one call) -------------------------------
  * Same results as fr_recon_project_forward followed by fr_render_depth_forward (depth + tri_ind only), but the
  * reconstruction epilogue writes the rasterizer's vertex records directly, so the rasterizer's repack pass over the

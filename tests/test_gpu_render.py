@@ -182,3 +182,37 @@ def test_unsure_queue_overflow():
     want = oracle.oracle_render_depth_forward(v, tri, tex, 64, 64)
     assert (want[3][0] == 0).sum() > 1024                        # the degenerate triangle really covers > queue capacity
     _assert_same(_gpu_render(v, tri, tex, 64, 64), want, "overflow")
+
+
+def test_rendering_layer_fused_matches_unfused(small_model):
+    """FaceRecNet.rendering_layer with the post-processing fused into the resolve kernel against the literal
+    torch transcription of network.py:184-199 -- outputs and the gradient w.r.t. the vertices (depthimg and maskimg paths,
+    clip gates included: the face is pushed through z = 0 and z = 1 so that all three regimes occur)."""
+    net_mod = fr("nets.network")
+    B, S = 5, 64
+    ks, ke = small_model["ndim_shape"], small_model["ndim_exp"]
+    gray = torch.rand((B, S, S, 1), device=DEV)
+    net = net_mod.FaceRecNet(im_gray=gray, mesh_data=small_model, batch_size=B, im_size=S, device=DEV)
+    p = fr("synth").sample_params_constrained(B, ks, ke, S, seed=11)
+    vp0 = net.vertices_transform(torch.from_numpy(p).to(DEV)[:, None, None, :]).detach()
+    zs = vp0[:, 2, :]
+    vp0[:, 2, :] = (zs - zs.mean()) / (zs.std() + 1e-9) * 0.6 + 0.5       # depths straddle 1e-6 and 1
+    outs, grads = [], []
+    for fused in (True, False):
+        vp = vp0.clone().requires_grad_(True)
+        layer = net.rendering_layer if fused else net.rendering_layer_unfused
+        pncc, normalimg, maskimg, depthimg = layer(vp, net.tri, net.vertex_code)
+        w1 = torch.linspace(0.5, 1.5, depthimg.numel(), device=DEV).view_as(depthimg)
+        w2 = torch.linspace(-1.0, 2.0, maskimg.numel(), device=DEV).view_as(maskimg)
+        ((depthimg * w1).sum() + (maskimg * w2).sum()).backward()
+        outs.append([t.detach().cpu().numpy() for t in (pncc, normalimg, maskimg, depthimg)])
+        grads.append(vp.grad.cpu().numpy())
+    covered = outs[1][3] > 1e-6
+    assert covered.mean() > 0.02 and (outs[1][2] >= 1.0 * 0.0).all()
+    for a, b, name in zip(outs[0], outs[1], ("pncc", "normalimg", "maskimg", "depthimg")):
+        if name == "normalimg":
+            assert np.abs(a - b).max() <= 2e-6, name                      # sqrt / divide / 3-term sum order
+        else:
+            assert a.tobytes() == b.tobytes(), name
+    assert np.abs(grads[0]).max() > 0
+    assert np.abs(grads[0] - grads[1]).max() <= 1e-6 * np.abs(grads[1]).max()
