@@ -22,6 +22,7 @@ struct ReconWorkspace {
   float* coefT;   // [kpad][bpad]
   float* pose;    // [bpad][24]
   float* G;       // [bpad][kpad]
+  double* gmean64;  // [bpad] the mean column of G in float64 (tensor-core backward); directly after G: one memset clears both
   float* dt;      // [bpad][4]
   void* tc;       // 3xTF32 tensor-core path scratch (split coefficients)
   void* bsplit16; // fp16-pair tensor-core path: coefficient operands per 64-face batch tile
@@ -44,6 +45,7 @@ ReconWorkspace carve_recon(void* base, int batch, const BasisGeom& g) {
   w.coefT = static_cast<float*>(take(sizeof(float) * (size_t)g.kpad * bpad));
   w.pose = static_cast<float*>(take(sizeof(float) * (size_t)bpad * kPoseStride));
   w.G = static_cast<float*>(take(sizeof(float) * (size_t)bpad * g.kpad));
+  w.gmean64 = static_cast<double*>(take(sizeof(double) * (size_t)bpad));
   w.dt = static_cast<float*>(take(sizeof(float) * (size_t)bpad * 4));
   w.tc = take(recon_tc_workspace_bytes(batch, g));
   w.bsplit16 = take(recon_f16_bsplit_bytes(batch, g));
@@ -296,7 +298,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
                                                                  g.kpad, flags, w.coefT, w.pose, nullptr);
   FR_LAUNCHED("recon_prep_kernel");
-  FR_CUDA(cudaMemsetAsync(w.G, 0, sizeof(float) * (size_t)bpad * g.kpad, st));
+  FR_CUDA(cudaMemsetAsync(w.G, 0, (size_t)(reinterpret_cast<char*>(w.gmean64 + bpad) - reinterpret_cast<char*>(w.G)), st));
   // dispatch: tcgen05 contraction above 8 faces (FR_RECON_PATH=simt forces the FFMA kernel)
   const uint32_t bwd_smem = b16::smem_bytes(g.mtiles(), b16::faces_per_tile(batch));
   const bool use_tc = recon_bwd_f16_fits(g) && bwd_smem <= 227u * 1024u && batch > 8 && recon_path_override() != 1;
@@ -308,8 +310,8 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
     const int nb = b16::faces_per_tile(batch), nbt = ceil_div(batch, nb);
     // (the operand tiles of faces between batch and the next multiple of 64 are zero-filled by the blocks that own them)
     b16::recon_bwd_pack_grad_kernel<<<dim3(ceil_div(g.ntiles * (kTileVerts / 8), 32), ceil_div(batch_padded(batch), 8)), 256, 0, st>>>(
-        vertex_grad, w.pose, w.gmax, reinterpret_cast<const float*>(base + g.mean_offset()), g.ks + g.ke, g.kpad, batch, nver, g.ntiles,
-        nb, flags, w.gtiles, w.gscale, w.G);
+        vertex_grad, w.pose, w.gmax, reinterpret_cast<const float*>(base + g.mean_offset()), batch, nver, g.ntiles, nb, flags, w.gtiles,
+        w.gscale, w.gmean64);
     FR_LAUNCHED("recon_bwd_pack_grad_kernel");
     int ctas = sm_count() / nbt;
     if (ctas < 1) ctas = 1;
@@ -319,7 +321,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
                                                                               w.G, batch, nb, g.mtiles(), g.ntiles, g.kpad);
     FR_LAUNCHED("recon_bwd_f16_kernel");
     recon_bwd_finalize_kernel<<<batch, 256, 0, st>>>(w.G, w.coefT, w.pose, w.dt, bpad, ndim_shape, ndim_exp, g.kpad, dparam,
-                                                    params_grad);
+                                                    params_grad, w.gmean64);
     FR_LAUNCHED("recon_bwd_finalize_kernel");
     return FR_OK;
   }
@@ -336,7 +338,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
       reinterpret_cast<const float4*>(packed), w.pose, vertex_grad, w.G, batch, nver, g.kg, g.ntiles, flags);
   FR_LAUNCHED("recon_bwd_simt_kernel");
   recon_bwd_finalize_kernel<<<batch, 256, 0, st>>>(w.G, w.coefT, w.pose, w.dt, bpad, ndim_shape, ndim_exp, g.kpad, dparam,
-                                                  params_grad);
+                                                  params_grad, nullptr);
   FR_LAUNCHED("recon_bwd_finalize_kernel");
   return FR_OK;
 }

@@ -382,27 +382,31 @@ recon_bwd_simt_kernel(const float4* __restrict__ packed, const float* __restrict
 
 // params_grad[b] = [0,0,0 | dt | df | f.G[:ks+ke]]   with df = sum_{k<=ks+ke} coef[k][b] * G[b][k]
 __global__ void __launch_bounds__(256)
+// gmean64 (nullable): the mean column's contraction accumulated separately in float64 (tensor-core backward).
+// d f is a sum of ~230 terms of either sign around 1e7: it is accumulated in float64 so that the result is as good as its terms.
 recon_bwd_finalize_kernel(const float* __restrict__ G, const float* __restrict__ coefT, const float* __restrict__ pose,
                           const float* __restrict__ dt, int bpad, int ks, int ke, int kpad, int dparam,
-                          float* __restrict__ params_grad) {
+                          float* __restrict__ params_grad, const double* __restrict__ gmean64) {
   const int b = blockIdx.x;
   const float f = pose[(size_t)b * kPoseStride + 21];
   const float* Gb = G + (size_t)b * kpad;
   float* out = params_grad + (size_t)b * dparam;
-  float s = 0.0f;
+  double s = 0.0;
   for (int k = threadIdx.x; k <= ks + ke; k += 256) {
     const float gk = Gb[k];
-    s = fmaf(coefT[(size_t)k * bpad + b], gk, s);
+    s += (double)coefT[(size_t)k * bpad + b] * (double)gk;
+    if (k == ks + ke && gmean64 != nullptr) s += gmean64[b];
     if (k < ks + ke) out[FR_NDIM_POSE + k] = f * gk;
   }
-  __shared__ float red[8];
+  __shared__ double red[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float tot = 0.0f;
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    double tot64 = 0.0;
+    for (int w = 0; w < 8; ++w) tot64 += red[w];
+    const float tot = (float)tot64;
     out[0] = 0.0f;  // tf.py_func has no gradient (nets/network.py:150)
     out[1] = 0.0f;
     out[2] = 0.0f;

@@ -119,8 +119,9 @@ constexpr int kPgVerts = 256, kPgRow = kPgVerts + kPgVerts / 32;            // s
 __device__ __forceinline__ int pg_skew(int v) { return v + (v >> 5); }
 __global__ void __launch_bounds__(256)
 recon_bwd_pack_grad_kernel(const float* __restrict__ vertex_grad, const float* __restrict__ pose, const float* __restrict__ gmax,
-                           const float* __restrict__ mean32, int kmean, int kpad, int batch, int nver, int ntiles, int nb,
-                           unsigned flags, unsigned char* __restrict__ gtiles, float* __restrict__ gscale, float* __restrict__ G) {
+                           const float* __restrict__ mean32, int batch, int nver, int ntiles, int nb,
+                           unsigned flags, unsigned char* __restrict__ gtiles, float* __restrict__ gscale,
+                           double* __restrict__ gmean64) {
   // the staged gradient rows and the outgoing fp16 pieces share one buffer (a barrier separates the two uses)
   __shared__ __align__(16) unsigned char s_buf[sizeof(float) * 8 * 3 * kPgRow];
   __shared__ float s_mu[3][kPgRow];
@@ -191,7 +192,7 @@ recon_bwd_pack_grad_kernel(const float* __restrict__ vertex_grad, const float* _
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) gmean += __shfl_xor_sync(0xFFFFFFFFu, gmean, o);
-  if (lane == 0 && live) atomicAdd(G + (size_t)b * kpad + kmean, gmean);
+  if (lane == 0 && live) atomicAdd(gmean64 + b, (double)gmean);           // 200+ partial sums of ~1e7 per face: keep them exact
   __syncthreads();
   // write out: one 16-byte piece per thread and trip, 8 consecutive threads = one 128-byte core matrix
   const int b8 = blockIdx.y * 8;                                           // first face of the block (multiple of 8)

@@ -63,5 +63,10 @@ class DeviceModel:
             check(lib().fr_pack_basis(d_mu.data_ptr(), d_ps.data_ptr() if d_ps.numel() else None,
                                       d_pe.data_ptr() if d_pe.numel() else None, self.nver, self.ndim_shape,
                                       self.ndim_exp, self.pack_flags, self.packed.data_ptr(), _stream_ptr(self.device)))
+            # Gram matrix of [pc_shape | pc_exp] for the geometry loss: one plain float64 library GEMM at
+            # model load replaces the reference's two 146 MB basis contractions per training step (network.py:348-355)
+            d_basis = torch.cat([d_ps, d_pe], dim=1).double()
+            self.gram = (d_basis.t() @ d_basis)
+            del d_basis
             torch.cuda.current_stream(self.device).synchronize()   # d_mu/d_ps/d_pe die here
         self.basis_bytes = int(nbytes)

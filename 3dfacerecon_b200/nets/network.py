@@ -9,6 +9,7 @@ here                           reference                              what runs
 ``rendering_layer``            ``nets/network.py:174-201``            ``fr_rendering_layer_forward/backward`` (CUDA)
 ``depth_rendering_layer``      ``nets/network.py:300-308``            both of the above
 ``set_constraints``            ``nets/network.py:204-218``            torch elementwise
+``geometry_loss``              ``nets/network.py:346-355``            Gram-matrix form (no basis pass)
 ``parse_pose_params``          ``nets/network.py:253-263``            slicing
 ``rotation_matrix(_batch)``    ``nets/network.py:266-297``            numpy, host-side mirror for inspection only
 =============================  =====================================  ==========================================
@@ -189,6 +190,18 @@ class FaceRecNet:
         self.pncc_batch, self.normal_batch, self.maskimg_batch, self.coarse_depth_map = \
             self.rendering_layer(self.vertices_proj, self.tri, self.vertex_code)
         return self.coarse_depth_map
+
+    # ------------------------------------------------------------------ network.py:346-355
+    def geometry_loss(self, pred_params, params_label):
+        """``tf.losses.mean_squared_error(Basis . label, Basis . pred)`` over the 3N x B reconstructed coordinates, without
+        touching the basis: with d = label - pred it equals  sum_b d_b^T (Basis^T Basis) d_b / (3N B);  the 228 x 228 Gram
+        matrix is computed once at model load (``DeviceModel.gram``, float64)."""
+        def geo(p):
+            p = p.squeeze(2).squeeze(1) if p.dim() == 4 else p
+            return p[:, self.ndim_pose:self.ndim_pose + self.ndim_shape + self.ndim_exp]
+        d = (geo(params_label) - geo(pred_params)).double()
+        quad = ((d @ self.model.gram) * d).sum()
+        return (quad / (3.0 * self.model.nver * d.shape[0])).float()
 
     # ------------------------------------------------------------------ network.py:204-218
     def set_constraints(self, pred_params):

@@ -250,6 +250,28 @@ def test_session_pipelined_slots_match_synchronous(bfm):
     sess.close()
 
 
+def test_geometry_loss_gram_form(bfm):
+    """the geometry loss through the 228 x 228 Gram matrix == the literal mean squared difference of the two
+    basis contractions (network.py:346-355), value and gradient w.r.t. the predicted coefficients."""
+    B = 6
+    net = fr("nets.network").FaceRecNet(mesh_data=bfm, batch_size=B, im_size=200, device=DEV)
+    rng = np.random.default_rng(3)
+    pred = fr("synth").sample_params_constrained(B, seed=70)
+    label = fr("synth").sample_params_constrained(B, seed=71)
+    pt = torch.from_numpy(pred).to(DEV).requires_grad_(True)
+    loss = net.geometry_loss(pt[:, None, None, :], torch.from_numpy(label).to(DEV)[:, None, None, :])
+    loss.backward()
+    basis = np.concatenate([bfm["pc_shape"], bfm["pc_exp"]], axis=1).astype(np.float64)
+    d = (label[:, 7:] - pred[:, 7:]).astype(np.float64)
+    diff = basis @ d.T                                                    # [3N, B]
+    want = (diff ** 2).mean()
+    want_grad = -2.0 * (basis.T @ diff).T / diff.size
+    assert abs(float(loss) - want) <= 1e-6 * want
+    got_grad = pt.grad.cpu().numpy()
+    assert not got_grad[:, :7].any()
+    assert np.abs(got_grad[:, 7:] - want_grad).max() <= 1e-5 * np.abs(want_grad).max()
+
+
 def test_facerecnet_mirror(bfm):
     """The FaceRecNet geometry slice end to end: default pred_params -> depth_rendering_layer (network.py:300-308)."""
     net = fr("nets.network").FaceRecNet(mesh_data=bfm, batch_size=2, im_size=200, device=DEV)
