@@ -266,7 +266,7 @@ def test_geometry_loss_gram_form(bfm):
     diff = basis @ d.T                                                    # [3N, B]
     want = (diff ** 2).mean()
     want_grad = -2.0 * (basis.T @ diff).T / diff.size
-    assert abs(float(loss) - want) <= 1e-6 * want
+    assert abs(float(loss.detach()) - want) <= 1e-6 * want
     got_grad = pt.grad.cpu().numpy()
     assert not got_grad[:, :7].any()
     assert np.abs(got_grad[:, 7:] - want_grad).max() <= 1e-5 * np.abs(want_grad).max()
