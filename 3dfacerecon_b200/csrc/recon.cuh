@@ -54,11 +54,18 @@ pack_basis_kernel(const float* __restrict__ mu, const float* __restrict__ pc_sha
 // ---------------------------------------------------------------------------------------------- prep
 // Rotation as the reference builds it: float64 sin/cos, float64 3x3 products, cast to float32
 // (nets/network.py:277-290 / rendering_layer/sample_test.py:59-72); then M = f (*) R in float32 (network.py:165).
+__device__ inline void pose_matrices_sc(double sp, double cp, double sg, double cg, double st, double ct, const float* __restrict__ p,
+                                        unsigned flags, float* __restrict__ out);
 __device__ inline void pose_matrices(const float* __restrict__ p, unsigned flags, float* __restrict__ out) {
   double sp, cp, sg, cg, st, ct;
   sincos((double)p[0], &sp, &cp);  // phi   : pitch
   sincos((double)p[1], &sg, &cg);  // gamma : yaw
   sincos((double)p[2], &st, &ct);  // theta : roll
+  pose_matrices_sc(sp, cp, sg, cg, st, ct, p, flags, out);
+}
+// ... from the six sines / cosines (the tensor-core prep kernel evaluates the three float64 sincos on three threads)
+__device__ inline void pose_matrices_sc(double sp, double cp, double sg, double cg, double st, double ct, const float* __restrict__ p,
+                                        unsigned flags, float* __restrict__ out) {
   const double rx[9] = {1, 0, 0, 0, cp, sp, 0, -sp, cp};
   const double ry[9] = {cg, 0, -sg, 0, 1, 0, sg, 0, cg};
   const double rz[9] = {ct, st, 0, -st, ct, 0, 0, 0, 1};

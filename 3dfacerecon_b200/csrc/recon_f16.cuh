@@ -181,6 +181,7 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
                       int ke, int kpad16, unsigned flags, unsigned char* __restrict__ bsplit, float* __restrict__ pose16) {
   __shared__ float red[8];
   __shared__ float s_pose[kPoseStride];
+  __shared__ double s_sc[6];
   pdl_trigger();                                   // the reconstruction kernel may become resident (it waits before reading our output)
   const int b = blockIdx.x, tid = threadIdx.x;
   const bool live = b < batch;
@@ -196,8 +197,14 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
   if ((tid & 31) == 0) red[tid >> 5] = cmax;
-  if (tid == 0 && live) pose_matrices(params + (size_t)b * dparam, flags, s_pose);
+  // the three float64 sincos are the longest dependency chain of this kernel: one angle per warp (lanes 0 of warps 1..3)
+  if (live && (tid & 31) == 0 && tid >= 32 && tid < 128) {
+    const int a = (tid >> 5) - 1;
+    sincos((double)params[(size_t)b * dparam + a], &s_sc[2 * a], &s_sc[2 * a + 1]);
+  }
   __syncthreads();
+  if (tid == 0 && live)
+    pose_matrices_sc(s_sc[0], s_sc[1], s_sc[2], s_sc[3], s_sc[4], s_sc[5], params + (size_t)b * dparam, flags, s_pose);
   cmax = red[0];
 #pragma unroll
   for (int w = 1; w < 8; ++w) cmax = fmaxf(cmax, red[w]);
@@ -224,6 +231,7 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
     *reinterpret_cast<__half*>(tile + off) = b0;
     *reinterpret_cast<__half*>(tile + half + off) = b1;
   }
+  __syncthreads();                     // s_pose (written by thread 0 above)
   if (tid < kPose16Stride) {
     float v = 0.0f;
     if (live) {
