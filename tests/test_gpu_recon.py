@@ -227,6 +227,44 @@ def test_small_model_backward_all_paths(small_model, B):
         assert (np.abs(got[:, sl] - want[:, sl]) <= GRAD_TOL * scale).all(), sl
 
 
+def test_fused_call_is_cuda_graph_capturable(small_model):
+    """include/facerecon_b200.h promises stream-ordered, capturable calls (the reference launches on the legacy default
+    stream and mallocs per call): capture the fused call -- prep kernel, programmatic dependent launches, rasterizer -- in a
+    CUDA graph, replay it on new parameters, compare with the eager call."""
+    lib, check = fr("_lib").lib(), fr("_lib").check
+    ks, ke = small_model["ndim_shape"], small_model["ndim_exp"]
+    B, S = 20, 48
+    dm = fr("model").DeviceModel(small_model, DEV)
+    pa = torch.from_numpy(fr("synth").sample_params_constrained(B, ks, ke, S, seed=1)).to(DEV)
+    pb = torch.from_numpy(fr("synth").sample_params_constrained(B, ks, ke, S, seed=2)).to(DEV)
+    params = pa.clone()
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, S, S), dtype=torch.uint8, device=DEV)
+    depth, tri_ind = torch.empty((B, S, S, 1), device=DEV), torch.empty((B, S, S, 1), device=DEV)
+
+    def call(stream):
+        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), None, depth.data_ptr(),
+                                          tri_ind.data_ptr(), B, dm.nver, dm.ntri, ks, ke, S, S, float(S), dm.run_flags, ws.data_ptr(),
+                                          ws.numel(), stream.cuda_stream))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        call(side)                                                        # warm-up outside the capture (function attributes)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        call(torch.cuda.current_stream())
+    for src in (pb, pa, pb):
+        params.copy_(src)
+        graph.replay()
+        torch.cuda.synchronize()
+        got = (depth.clone(), tri_ind.clone())
+        call(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        assert got[0].cpu().numpy().tobytes() == depth.cpu().numpy().tobytes()
+        assert got[1].cpu().numpy().tobytes() == tri_ind.cpu().numpy().tobytes()
+    assert (tri_ind >= 0).any()
+
+
 def test_session_pipelined_slots_match_synchronous(bfm):
     """fr_session_submit / fr_session_wait: batches alternating over the two slots (different sizes, outputs in pinned
     memory) give bit-identical results to the synchronous call, and a busy slot refuses a second submit."""
