@@ -8,7 +8,6 @@
 #include "fr_common.cuh"
 #include "raster.cuh"
 #include "recon.cuh"
-#include "recon_tc.cuh"
 #include "recon_f16.cuh"
 #include "recon_bwd_f16.cuh"
 
@@ -24,8 +23,7 @@ struct ReconWorkspace {
   float* G;       // [bpad][kpad]
   double* gmean64;  // [bpad] the mean column of G in float64 (tensor-core backward); directly after G: one memset clears both
   float* dt;      // [bpad][4]
-  void* tc;       // 3xTF32 tensor-core path scratch (split coefficients)
-  void* bsplit16; // fp16-pair tensor-core path: coefficient operands per 64-face batch tile
+  void* bsplit16; // tensor-core forward: fp16 coefficient operands per 64-face batch tile
   float* pose16;  // ... and [bpad][16] scaled pose
   unsigned char* gtiles;  // tensor-core backward: fp16 operand tiles of the rotated vertex gradient
   float* gmax;            // ... [bpad][4] per-face, per-row gradient maxima
@@ -47,7 +45,6 @@ ReconWorkspace carve_recon(void* base, int batch, const BasisGeom& g) {
   w.G = static_cast<float*>(take(sizeof(float) * (size_t)bpad * g.kpad));
   w.gmean64 = static_cast<double*>(take(sizeof(double) * (size_t)bpad));
   w.dt = static_cast<float*>(take(sizeof(float) * (size_t)bpad * 4));
-  w.tc = take(recon_tc_workspace_bytes(batch, g));
   w.bsplit16 = take(recon_f16_bsplit_bytes(batch, g));
   w.pose16 = static_cast<float*>(take(recon_f16_pose_bytes(batch)));
   w.gtiles = static_cast<unsigned char*>(take(recon_bwd_f16_fits(g) ? b16::grad_tiles_bytes(batch, g) : 0));
@@ -111,7 +108,7 @@ int recon_project_forward_impl(const float* params, const float* packed, const R
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
 
-  // dispatch: fp16-pair tcgen05 kernel above 8 faces (FR_RECON_PATH = simt | tf32 | f16 overrides it, for A/B comparisons)
+  // dispatch: fp16-pair tcgen05 kernel above 8 faces (FR_RECON_PATH = simt | f16 overrides it, for A/B comparisons)
   const int ov = recon_path_override();
   const size_t key_bytes_face = out.keys ? sizeof(unsigned long long) * (size_t)out.width * out.height : 0;
   if (recon_f16_fits(g) && (ov == 3 || (ov == 0 && batch > 8))) {
@@ -121,14 +118,9 @@ int recon_project_forward_impl(const float* params, const float* packed, const R
                                 fold ? out.keys : nullptr, fold ? (int)(key_bytes_face / 16) : 0);
   }
   if (out.keys != nullptr) FR_CUDA(cudaMemsetAsync(out.keys, 0, key_bytes_face * batch, st));
-  const bool use_tc = ov == 2 && recon_tc_applicable(batch, g, flags);
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
-                                                                 g.kpad, flags, w.coefT, w.pose,
-                                                                 use_tc ? static_cast<unsigned char*>(w.tc) : nullptr);
+                                                                 g.kpad, flags, w.coefT, w.pose);
   FR_LAUNCHED("recon_prep_kernel");
-
-  if (use_tc)
-    return launch_recon_fwd_tc(packed, w.coefT, w.pose, w.tc, out, batch, nver, g, im_size, flags, sm_count(), st);
   if (batch <= 4) return launch_recon_fwd_simt<4>(packed, w, out, batch, nver, g, im_size, flags, 1, st);
   if (batch <= 8) return launch_recon_fwd_simt<8>(packed, w, out, batch, nver, g, im_size, flags, 1, st);
   const int gy = batch <= 16 ? 1 : (batch <= 32 ? 2 : 4);
@@ -213,16 +205,6 @@ int fr_debug_set_mid_event(void* cuda_event) {
   return FR_OK;
 }
 
-// developer diagnostics (not part of the public header): per-role cycle counters of the tensor-core kernel's block 0
-int fr_debug_tc_counters(unsigned long long* out32, int reset) {
-  if (out32 && cudaMemcpyFromSymbol(out32, fr::tc::g_tc_dbg, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
-  if (reset) {
-    unsigned long long z[32] = {0};
-    if (cudaMemcpyToSymbol(fr::tc::g_tc_dbg, z, sizeof(z)) != cudaSuccess) return 1;
-  }
-  return 0;
-}
-
 // ------------------------------------------------------------------------------------------------ packing
 size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp) {
   if (nver <= 0 || ndim_shape < 0 || ndim_exp < 0) return 0;
@@ -296,7 +278,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
 
   // recomputed rather than trusted from a previous forward: the workspace is the caller's scratch
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
-                                                                 g.kpad, flags, w.coefT, w.pose, nullptr);
+                                                                 g.kpad, flags, w.coefT, w.pose);
   FR_LAUNCHED("recon_prep_kernel");
   FR_CUDA(cudaMemsetAsync(w.G, 0, (size_t)(reinterpret_cast<char*>(w.gmean64 + bpad) - reinterpret_cast<char*>(w.G)), st));
   // dispatch: tcgen05 contraction above 8 faces (FR_RECON_PATH=simt forces the FFMA kernel)

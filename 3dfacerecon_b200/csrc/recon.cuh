@@ -8,7 +8,7 @@
 //   recon_bwd_dt_kernel      d t3d
 //   recon_bwd_simt_kernel    G[b,k] = sum_{c,n} P[(c,n),k] * (R_b^T g'_b)[c,n]   (second streaming pass)
 //   recon_bwd_finalize_kernel d alpha = f.G,  d f = sum_k coef[k].G[k]
-// The tensor-core (tcgen05, 3xTF32) flavour of the forward pass lives in recon_tc.cuh.
+// The tensor-core (tcgen05) flavours live in recon_f16.cuh (forward) and recon_bwd_f16.cuh (backward).
 #ifndef FR_RECON_CUH_
 #define FR_RECON_CUH_
 
@@ -103,7 +103,7 @@ __device__ inline void pose_matrices_sc(double sp, double cp, double sg, double 
 // column; beyond: 0; padded faces: 0).  pose [bpad][24].
 __global__ void __launch_bounds__(256)
 recon_prep_kernel(const float* __restrict__ params, int dparam, int batch, int bpad, int ks, int ke, int kpad,
-                  unsigned flags, float* __restrict__ coefT, float* __restrict__ pose, unsigned char* __restrict__ bsplit) {
+                  unsigned flags, float* __restrict__ coefT, float* __restrict__ pose) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx < kpad * bpad) {
     const int k = idx / bpad, b = idx - k * bpad;
@@ -113,18 +113,6 @@ recon_prep_kernel(const float* __restrict__ params, int dparam, int batch, int b
       else if (k == ks + ke) v = 1.0f;
     }
     coefT[idx] = v;
-    if (bsplit != nullptr) {
-      // tensor-core path: the same coefficient split into hi (exact tf32) + lo, stored per 64-face batch tile in the UMMA
-      // canonical K-major no-swizzle layout [hi|lo][8-face group][k/4][face%8][k%4] that recon_fwd_tc_kernel bulk-copies
-      const uint32_t hi = __float_as_uint(v) & 0xFFFFE000u;
-      const float lo = v - __uint_as_float(hi);
-      const uint32_t sbo = (uint32_t)(kpad / 4) * 128u, half = (kBatchPad / 8) * sbo;
-      const int n = b % kBatchPad;
-      unsigned char* tile = bsplit + (size_t)(b / kBatchPad) * 2 * half;
-      const uint32_t off = (uint32_t)(n >> 3) * sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
-      *reinterpret_cast<uint32_t*>(tile + off) = hi;
-      *reinterpret_cast<float*>(tile + half + off) = lo;
-    }
   }
   if (idx < bpad) {
     if (idx < batch) {

@@ -276,8 +276,8 @@ recon_bwd_f16_kernel(const unsigned char* __restrict__ atiles, const unsigned ch
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = smem_u32(smem + s * stage_bytes);
-        const uint64_t da = tc::make_b_desc(sa, 2048u, 128u);
-        const uint64_t db_hi = tc::make_b_desc(sa + a_bytes, 128u, 256u), db_lo = db_hi + (uint64_t)((b_bytes / 2) >> 4);
+        const uint64_t da = tc::make_smem_desc(sa, 2048u, 128u);
+        const uint64_t db_hi = tc::make_smem_desc(sa + a_bytes, 128u, 256u), db_lo = db_hi + (uint64_t)((b_bytes / 2) >> 4);
         for (int m = 0; m < mtiles; ++m) {
           const uint32_t d = tmem + (uint32_t)(m * nb);
           const uint64_t a_hi = da + (uint64_t)((m * 4096) >> 4), a_lo = a_hi + (uint64_t)((mtiles * 4096) >> 4);

@@ -18,13 +18,14 @@
 //                        against the next tile's MMAs
 // Measured on B200 (tools/mma_bench3.cu): an SS-form M128 N64 MMA takes 48 cycles (operand reads at 128 B/clk), K8 tf32
 // and K16 f16 alike, so a 16-k chunk costs 144 tensor cycles here against 192 for the 3xTF32 TS-form kernel
-// (recon_tc.cuh) -- and that kernel also needs 8 converter warps and a TMEM operand ring only 4 chunks deep.
+// (tools/experiments/recon_tc_3xtf32.cuh) -- and that kernel also needs 8 converter warps and a TMEM operand ring only 4 chunks deep.
 #ifndef FR_RECON_F16_CUH_
 #define FR_RECON_F16_CUH_
 
 #include <cuda_fp16.h>
 
-#include "recon_tc.cuh"
+#include "recon.cuh"
+#include "tcgen05_common.cuh"
 
 namespace fr {
 namespace f16 {
@@ -304,9 +305,9 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     // ================================================================== MMA issuer (whole warp converged, one elected lane issues)
     mbar_wait(&bars->b_full, 0);
     tc_fence_after();
-    const uint64_t db0 = tc::make_b_desc(smem_u32(smem + L.b0), 128u, L.sbo);
-    const uint64_t db1 = tc::make_b_desc(smem_u32(smem + L.b1), 128u, L.sbo);
-    const uint64_t da0 = tc::make_b_desc(smem_u32(smem + L.raw), 2048u, 128u);   // same descriptor format for A
+    const uint64_t db0 = tc::make_smem_desc(smem_u32(smem + L.b0), 128u, L.sbo);
+    const uint64_t db1 = tc::make_smem_desc(smem_u32(smem + L.b1), 128u, L.sbo);
+    const uint64_t da0 = tc::make_smem_desc(smem_u32(smem + L.raw), 2048u, 128u);   // same descriptor format for A
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const uint32_t dbuf = tcount % kDBufs;

@@ -1,0 +1,98 @@
+// tcgen05 / mbarrier / bulk-copy primitives shared by the tensor-core kernels (recon_f16.cuh, recon_bwd_f16.cuh):
+// thin inline-PTX wrappers, the shared-memory matrix descriptor, and the developer switches read from the environment.
+#ifndef FR_TCGEN05_COMMON_CUH_
+#define FR_TCGEN05_COMMON_CUH_
+
+#include <cstdlib>
+
+#include "fr_common.cuh"
+
+namespace fr {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug traps (-> launch error the API reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// one lane of a fully converged warp (keeps tcgen05.mma / commit on the uniform datapath: a lane-0 branch makes the
+// compiler serialise every uniform-register operand through per-thread loops and triples the issue cost)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, no swizzle: 8-row x 16-byte core matrices,
+// LBO = bytes between the two 16-byte K chunks of one k8 step, SBO = bytes between 8-row groups; version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace tc
+
+inline int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+// FR_PDL=0 launches every kernel with full stream serialisation (A/B switch for the programmatic dependent launches)
+inline bool pdl_enabled() {
+  static const int v = env_int("FR_PDL", 1);
+  return v != 0;
+}
+
+// FR_RECON_PATH = simt | f16 overrides the dispatch (debugging / A-B comparisons): 1 = FFMA kernels, 3 = tensor cores; 0 = default.
+inline int recon_path_override() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = std::getenv("FR_RECON_PATH");
+    cached = (e == nullptr) ? 0 : (e[0] == 's' ? 1 : (e[0] == 'f' ? 3 : 0));
+  }
+  return cached;
+}
+
+}  // namespace fr
+
+#endif  // FR_TCGEN05_COMMON_CUH_
