@@ -160,17 +160,17 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
           vertex, rec, keys, nver, npix, width, height);
       FR_LAUNCHED("raster_pack_kernel");
     }
-    const unsigned gx = (unsigned)ceil_div(ntri, kRasterThreads);
+    const unsigned gx = (unsigned)ceil_div(ntri, kKeysThreads);
     const bool pdl = pdl_enabled();   // dependent launches: the kernels call pdl_wait() before touching their predecessor's output
     const float4* crec = rec;
     if (batch >= 8)
-      FR_CUDA(launch_pdl(raster_keys_kernel<8>, dim3(gx, ceil_div(batch, 8)), dim3(kRasterThreads), 0, st, pdl, crec, tri, keys, batch, nver,
+      FR_CUDA(launch_pdl(raster_keys_kernel<8>, dim3(gx, ceil_div(batch, 8)), dim3(kKeysThreads), 0, st, pdl, crec, tri, keys, batch, nver,
                          ntri, height, width));
     else if (batch >= 3)
-      FR_CUDA(launch_pdl(raster_keys_kernel<4>, dim3(gx, ceil_div(batch, 4)), dim3(kRasterThreads), 0, st, pdl, crec, tri, keys, batch, nver,
+      FR_CUDA(launch_pdl(raster_keys_kernel<4>, dim3(gx, ceil_div(batch, 4)), dim3(kKeysThreads), 0, st, pdl, crec, tri, keys, batch, nver,
                          ntri, height, width));
     else
-      FR_CUDA(launch_pdl(raster_keys_kernel<1>, dim3(gx, batch), dim3(kRasterThreads), 0, st, pdl, crec, tri, keys, batch, nver, ntri,
+      FR_CUDA(launch_pdl(raster_keys_kernel<1>, dim3(gx, batch), dim3(kKeysThreads), 0, st, pdl, crec, tri, keys, batch, nver, ntri,
                          height, width));
     FR_LAUNCHED("raster_keys_kernel");
   } else if (!records_ready) {

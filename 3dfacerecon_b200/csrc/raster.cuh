@@ -20,6 +20,10 @@
 namespace fr {
 
 constexpr int kRasterThreads = 256;
+#ifndef FR_KEYS_THREADS
+#define FR_KEYS_THREADS 128   // A/B on B200 at B = 64: 64 -> 55.5 us, 128 -> 54.5 us, 256 -> 59 us, 512 -> 66 us (smaller blocks: less time lost at the phase barrier)
+#endif
+constexpr int kKeysThreads = FR_KEYS_THREADS;   // threads (= triangles) per block of raster_keys_kernel
 
 // float triangle index -> int the way the reference does ((int)tri(k,i), render_depth_op.cc:204-206),
 // rejecting anything that would index outside [0, nver).
@@ -93,12 +97,15 @@ __device__ __forceinline__ void raster_draw(const float4& r1, const float4& r2, 
 // busy and without a divergent pixel loop in the single-pixel warps.
 // All record indices are 32-bit: the API guarantees batch * 3 * nver < 2^31.
 template <int FPT>
-__global__ void __launch_bounds__(kRasterThreads)
+#ifndef FR_KEYS_MINB
+#define FR_KEYS_MINB 1
+#endif
+__global__ void __launch_bounds__(kKeysThreads, FR_KEYS_MINB)
 raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri, unsigned long long* __restrict__ keys,
                    int batch, int nver, int ntri, int height, int width) {
-  __shared__ uint2 q_box[kRasterThreads * FPT];           // biased bbox (lo_min, hi_max)
-  __shared__ unsigned short q_id[kRasterThreads * FPT];   // (local triangle << 3) | face slot
-  __shared__ int s_idx[3][kRasterThreads];
+  __shared__ uint2 q_box[kKeysThreads * FPT];           // biased bbox (lo_min, hi_max)
+  __shared__ unsigned short q_id[kKeysThreads * FPT];   // (local triangle << 3) | face slot
+  __shared__ int s_idx[3][kKeysThreads];
   __shared__ unsigned q_count;                            // single-pixel survivors | multi-pixel survivors << 16
   static_assert(FPT <= 8, "face slot is packed into 3 bits");
 
@@ -108,7 +115,7 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
   pdl_wait();      // records and cleared keys of the producing kernel (pack pass or reconstruction epilogue) are complete
   __syncthreads();
 
-  const int t = blockIdx.x * kRasterThreads + tid;
+  const int t = blockIdx.x * kKeysThreads + tid;
   const int b0 = blockIdx.y * FPT;
   int p1 = 0, p2 = 0, p3 = 0;
   bool valid = t < ntri;
@@ -140,7 +147,7 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
   const unsigned multimask = keepmask & ~singlemask;
   if (keepmask != 0u) {     // one packed shared atomic reserves both queue ranges
     const unsigned got = atomicAdd(&q_count, (unsigned)__popc(singlemask) | ((unsigned)__popc(multimask) << 16));
-    int ps = (int)(got & 0xFFFFu), pm = kRasterThreads * FPT - 1 - (int)(got >> 16);
+    int ps = (int)(got & 0xFFFFu), pm = kKeysThreads * FPT - 1 - (int)(got >> 16);
 #pragma unroll
     for (int f = 0; f < FPT; ++f) {
       if ((keepmask >> f) & 1u) {
@@ -155,10 +162,10 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
   const unsigned counts = q_count;
   const int n_single = (int)(counts & 0xFFFFu), n_multi = (int)(counts >> 16);
   const int npix = height * width;
-  const int tri0 = blockIdx.x * kRasterThreads;
+  const int tri0 = blockIdx.x * kKeysThreads;
   // ---- phase B1: one pixel per survivor; two survivors per thread and trip keep six 16-byte gathers in flight
-  for (int i0 = tid; i0 < n_single; i0 += 2 * kRasterThreads) {
-    const int i1 = i0 + kRasterThreads;
+  for (int i0 = tid; i0 < n_single; i0 += 2 * kKeysThreads) {
+    const int i1 = i0 + kKeysThreads;
     const bool two = i1 < n_single;
     const int ib = two ? i1 : i0;
     const uint2 bxa = q_box[i0], bxb = q_box[ib];
@@ -174,8 +181,8 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
     if (two) raster_draw(c1, c2, c3, bxb, tri0 + tlb, keys + (size_t)bb * npix, width, true);
   }
   // ---- phase B2: survivors with several candidate pixels
-  for (int j = tid; j < n_multi; j += kRasterThreads) {
-    const int i = kRasterThreads * FPT - 1 - j;
+  for (int j = tid; j < n_multi; j += kKeysThreads) {
+    const int i = kKeysThreads * FPT - 1 - j;
     const uint2 bx = q_box[i];
     const int id = q_id[i];
     const int tl = id >> 3;
