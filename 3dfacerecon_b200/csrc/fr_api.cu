@@ -119,7 +119,7 @@ int recon_project_forward_impl(const float* params, const float* packed, const R
   }
   if (out.keys != nullptr) FR_CUDA(cudaMemsetAsync(out.keys, 0, key_bytes_face * batch, st));
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
-                                                                 g.kpad, flags, w.coefT, w.pose);
+                                                                 g.kpad, flags, im_size, w.coefT, w.pose);
   FR_LAUNCHED("recon_prep_kernel");
   if (batch <= 4) return launch_recon_fwd_simt<4>(packed, w, out, batch, nver, g, im_size, flags, 1, st);
   if (batch <= 8) return launch_recon_fwd_simt<8>(packed, w, out, batch, nver, g, im_size, flags, 1, st);
@@ -264,7 +264,7 @@ int fr_recon_project_forward(const float* params, const float* packed, float* ve
 }
 
 int fr_recon_project_backward(const float* params, const float* packed, const float* vertex_grad, float* params_grad,
-                              int batch, int nver, int ndim_shape, int ndim_exp, unsigned flags, void* workspace,
+                              int batch, int nver, int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                               size_t workspace_bytes, void* stream) {
   if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
   if (batch == 0) return FR_OK;
@@ -278,7 +278,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
 
   // recomputed rather than trusted from a previous forward: the workspace is the caller's scratch
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
-                                                                 g.kpad, flags, w.coefT, w.pose);
+                                                                 g.kpad, flags, im_size, w.coefT, w.pose);
   FR_LAUNCHED("recon_prep_kernel");
   FR_CUDA(cudaMemsetAsync(w.G, 0, (size_t)(reinterpret_cast<char*>(w.gmean64 + bpad) - reinterpret_cast<char*>(w.G)), st));
   // dispatch: tcgen05 contraction above 8 faces (FR_RECON_PATH=simt forces the FFMA kernel)
@@ -303,7 +303,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
                                                                               w.G, batch, nb, g.mtiles(), g.ntiles, g.kpad);
     FR_LAUNCHED("recon_bwd_f16_kernel");
     recon_bwd_finalize_kernel<<<batch, 256, 0, st>>>(w.G, w.coefT, w.pose, w.dt, bpad, ndim_shape, ndim_exp, g.kpad, dparam,
-                                                    params_grad, w.gmean64);
+                                                    params_grad, w.gmean64, params, flags, im_size);
     FR_LAUNCHED("recon_bwd_finalize_kernel");
     return FR_OK;
   }
@@ -320,7 +320,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
       reinterpret_cast<const float4*>(packed), w.pose, vertex_grad, w.G, batch, nver, g.kg, g.ntiles, flags);
   FR_LAUNCHED("recon_bwd_simt_kernel");
   recon_bwd_finalize_kernel<<<batch, 256, 0, st>>>(w.G, w.coefT, w.pose, w.dt, bpad, ndim_shape, ndim_exp, g.kpad, dparam,
-                                                  params_grad, nullptr);
+                                                  params_grad, nullptr, params, flags, im_size);
   FR_LAUNCHED("recon_bwd_finalize_kernel");
   return FR_OK;
 }
@@ -570,7 +570,7 @@ int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float
   if (int rc = fr_render_depth_backward(s->depth_grad, s->tri, sl.tri_ind, s->vgrad, batch, s->nver, s->ntri, s->height,
                                         s->width, sl.stream))
     return rc;
-  if (int rc = fr_recon_project_backward(sl.params, s->packed, s->vgrad, s->pgrad, batch, s->nver, s->ks, s->ke, s->flags,
+  if (int rc = fr_recon_project_backward(sl.params, s->packed, s->vgrad, s->pgrad, batch, s->nver, s->ks, s->ke, sl.im_size, s->flags,
                                          sl.ws, s->ws_bytes, sl.stream))
     return rc;
   FR_CUDA(cudaMemcpyAsync(params_grad, s->pgrad, sizeof(float) * (size_t)batch * d, cudaMemcpyDeviceToHost, sl.stream));

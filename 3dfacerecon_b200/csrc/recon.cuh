@@ -99,24 +99,43 @@ __device__ inline void pose_matrices_sc(double sp, double cp, double sg, double 
   out[23] = 0.0f;
 }
 
+// FaceRecNet.set_constraints (nets/network.py:204-218) for entry i of the parameter vector: sigmoid, then the per-block
+// affine map, with the reference's separate multiply / subtract roundings.  d(constrained)/d(raw) = scale * s (1 - s).
+__device__ __forceinline__ float param_scale(int i, int ks, float im_size) {
+  return i < 3 ? 3.0f : (i < 5 ? im_size : (i == 5 ? 0.0f : (i == 6 ? 1e-3f : (i < FR_NDIM_POSE + ks ? 1e4f : 3.0f))));
+}
+__device__ __forceinline__ float param_sigmoid(float raw) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-raw))); }
+__device__ __forceinline__ float read_param(const float* __restrict__ row, int i, unsigned flags, int ks, float im_size) {
+  const float v = row[i];
+  if (!(flags & FR_PARAMS_RAW)) return v;
+  const float y = __fmul_rn(param_sigmoid(v), param_scale(i, ks, im_size));
+  return (i < 3 || i >= FR_NDIM_POSE + ks) ? __fsub_rn(y, 1.5f) : y;
+}
+__device__ __forceinline__ void read_pose_params(const float* __restrict__ row, unsigned flags, int ks, float im_size, float* p7) {
+#pragma unroll
+  for (int i = 0; i < FR_NDIM_POSE; ++i) p7[i] = read_param(row, i, flags, ks, im_size);
+}
+
 // coefT [kpad][bpad]: row k = coefficient k of every face (k == ks+ke: the constant 1 that multiplies the mean
 // column; beyond: 0; padded faces: 0).  pose [bpad][24].
 __global__ void __launch_bounds__(256)
 recon_prep_kernel(const float* __restrict__ params, int dparam, int batch, int bpad, int ks, int ke, int kpad,
-                  unsigned flags, float* __restrict__ coefT, float* __restrict__ pose) {
+                  unsigned flags, float im_size, float* __restrict__ coefT, float* __restrict__ pose) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx < kpad * bpad) {
     const int k = idx / bpad, b = idx - k * bpad;
     float v = 0.0f;
     if (b < batch) {
-      if (k < ks + ke) v = params[(size_t)b * dparam + FR_NDIM_POSE + k];
+      if (k < ks + ke) v = read_param(params + (size_t)b * dparam, FR_NDIM_POSE + k, flags, ks, im_size);
       else if (k == ks + ke) v = 1.0f;
     }
     coefT[idx] = v;
   }
   if (idx < bpad) {
     if (idx < batch) {
-      pose_matrices(params + (size_t)idx * dparam, flags, pose + (size_t)idx * kPoseStride);
+      float p7[FR_NDIM_POSE];
+      read_pose_params(params + (size_t)idx * dparam, flags, ks, im_size, p7);
+      pose_matrices(p7, flags, pose + (size_t)idx * kPoseStride);
     } else {
       for (int i = 0; i < kPoseStride; ++i) pose[(size_t)idx * kPoseStride + i] = 0.0f;
     }
@@ -381,8 +400,15 @@ __global__ void __launch_bounds__(256)
 // d f is a sum of ~230 terms of either sign around 1e7: it is accumulated in float64 so that the result is as good as its terms.
 recon_bwd_finalize_kernel(const float* __restrict__ G, const float* __restrict__ coefT, const float* __restrict__ pose,
                           const float* __restrict__ dt, int bpad, int ks, int ke, int kpad, int dparam,
-                          float* __restrict__ params_grad, const double* __restrict__ gmean64) {
+                          float* __restrict__ params_grad, const double* __restrict__ gmean64, const float* __restrict__ params,
+                          unsigned flags, float im_size) {
   const int b = blockIdx.x;
+  // FR_PARAMS_RAW: chain through set_constraints, d raw_i = d p_i * scale_i * s (1 - s)
+  auto chain = [&](int i, float g) {
+    if (!(flags & FR_PARAMS_RAW)) return g;
+    const float s = param_sigmoid(params[(size_t)b * dparam + i]);
+    return g * (param_scale(i, ks, im_size) * (s * (1.0f - s)));
+  };
   const float f = pose[(size_t)b * kPoseStride + 21];
   const float* Gb = G + (size_t)b * kpad;
   float* out = params_grad + (size_t)b * dparam;
@@ -391,7 +417,7 @@ recon_bwd_finalize_kernel(const float* __restrict__ G, const float* __restrict__
     const float gk = Gb[k];
     s += (double)coefT[(size_t)k * bpad + b] * (double)gk;
     if (k == ks + ke && gmean64 != nullptr) s += gmean64[b];
-    if (k < ks + ke) out[FR_NDIM_POSE + k] = f * gk;
+    if (k < ks + ke) out[FR_NDIM_POSE + k] = chain(FR_NDIM_POSE + k, f * gk);
   }
   __shared__ double red[8];
 #pragma unroll
@@ -405,10 +431,10 @@ recon_bwd_finalize_kernel(const float* __restrict__ G, const float* __restrict__
     out[0] = 0.0f;  // tf.py_func has no gradient (nets/network.py:150)
     out[1] = 0.0f;
     out[2] = 0.0f;
-    out[3] = dt[b * 4 + 0];
-    out[4] = dt[b * 4 + 1];
-    out[5] = dt[b * 4 + 2];
-    out[6] = tot;
+    out[3] = chain(3, dt[b * 4 + 0]);
+    out[4] = chain(4, dt[b * 4 + 1]);
+    out[5] = chain(5, dt[b * 4 + 2]);
+    out[6] = chain(6, tot);
   }
 }
 

@@ -179,7 +179,8 @@ pack_basis_f16_kernel(const float* __restrict__ mu, const float* __restrict__ pc
 // layout [b0|b1][8-face group][k / 8][face % 8][k % 8] the kernel bulk-copies; pose16 = 2^-t f.R | t3d.
 __global__ void __launch_bounds__(256)
 recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict__ inv_scale, int dparam, int batch, int ks,
-                      int ke, int kpad16, unsigned flags, unsigned char* __restrict__ bsplit, float* __restrict__ pose16) {
+                      int ke, int kpad16, unsigned flags, float im_size, unsigned char* __restrict__ bsplit,
+                      float* __restrict__ pose16) {
   __shared__ float red[8];
   __shared__ float s_pose[kPoseStride];
   __shared__ double s_sc[6];
@@ -190,7 +191,7 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
   for (int k = tid; k < kpad16; k += 256) {
     float v = 0.0f;
     if (live) {
-      if (k < ks + ke) v = params[(size_t)b * dparam + FR_NDIM_POSE + k];
+      if (k < ks + ke) v = read_param(params + (size_t)b * dparam, FR_NDIM_POSE + k, flags, ks, im_size);
       else if (k == ks + ke) v = 1.0f;
     }
     cmax = fmaxf(cmax, fabsf(v * inv_scale[k]));
@@ -201,11 +202,14 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
   // the three float64 sincos are the longest dependency chain of this kernel: one angle per warp (lanes 0 of warps 1..3)
   if (live && (tid & 31) == 0 && tid >= 32 && tid < 128) {
     const int a = (tid >> 5) - 1;
-    sincos((double)params[(size_t)b * dparam + a], &s_sc[2 * a], &s_sc[2 * a + 1]);
+    sincos((double)read_param(params + (size_t)b * dparam, a, flags, ks, im_size), &s_sc[2 * a], &s_sc[2 * a + 1]);
   }
   __syncthreads();
-  if (tid == 0 && live)
-    pose_matrices_sc(s_sc[0], s_sc[1], s_sc[2], s_sc[3], s_sc[4], s_sc[5], params + (size_t)b * dparam, flags, s_pose);
+  if (tid == 0 && live) {
+    float p7[FR_NDIM_POSE];
+    read_pose_params(params + (size_t)b * dparam, flags, ks, im_size, p7);
+    pose_matrices_sc(s_sc[0], s_sc[1], s_sc[2], s_sc[3], s_sc[4], s_sc[5], p7, flags, s_pose);
+  }
   cmax = red[0];
 #pragma unroll
   for (int w = 1; w < 8; ++w) cmax = fmaxf(cmax, red[w]);
@@ -222,7 +226,7 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
   for (int k = tid; k < kpad16; k += 256) {
     float v = 0.0f;
     if (live) {
-      if (k < ks + ke) v = params[(size_t)b * dparam + FR_NDIM_POSE + k];
+      if (k < ks + ke) v = read_param(params + (size_t)b * dparam, FR_NDIM_POSE + k, flags, ks, im_size);
       else if (k == ks + ke) v = 1.0f;
     }
     const float c = v * inv_scale[k] * up;
@@ -419,7 +423,7 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
   const float* inv_scale = reinterpret_cast<const float*>(base + g.scale_offset());
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + g.ks + g.ke;
-  f16::recon_prep_f16_kernel<<<bpad, 256, 0, st>>>(params, inv_scale, dparam, batch, g.ks, g.ke, g.kpad16, flags,
+  f16::recon_prep_f16_kernel<<<bpad, 256, 0, st>>>(params, inv_scale, dparam, batch, g.ks, g.ke, g.kpad16, flags, im_size,
                                                   static_cast<unsigned char*>(bsplit), pose16);   // normal launch: waits for everything before
   FR_LAUNCHED("recon_prep_f16_kernel");
   const f16::SmemLayout L = f16::smem_layout(g.nch16);

@@ -8,7 +8,7 @@ here                           reference                              what runs
 ``vertices_transform``         ``nets/network.py:140-171``            ``fr_recon_project_forward/backward`` (CUDA)
 ``rendering_layer``            ``nets/network.py:174-201``            ``fr_rendering_layer_forward/backward`` (CUDA)
 ``depth_rendering_layer``      ``nets/network.py:300-308``            both of the above
-``set_constraints``            ``nets/network.py:204-218``            torch elementwise
+``set_constraints``            ``nets/network.py:204-218``            torch elementwise; fused: ``vertices_transform_raw``
 ``geometry_loss``              ``nets/network.py:346-355``            Gram-matrix form (no basis pass)
 ``parse_pose_params``          ``nets/network.py:253-263``            slicing
 ``rotation_matrix(_batch)``    ``nets/network.py:266-297``            numpy, host-side mirror for inspection only
@@ -52,7 +52,7 @@ class _ReconProject(torch.autograd.Function):
                                                  model.ndim_shape, model.ndim_exp, float(im_size), flags, ws.data_ptr(),
                                                  ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         ctx.save_for_backward(params)
-        ctx.model, ctx.flags = model, flags
+        ctx.model, ctx.flags, ctx.im_size = model, flags, float(im_size)
         return out
 
     @staticmethod
@@ -67,8 +67,9 @@ class _ReconProject(torch.autograd.Function):
             nbytes = lib().fr_recon_workspace_bytes(B, model.nver, model.ndim_shape, model.ndim_exp)
             ws = _workspace(dev, nbytes)
             check(lib().fr_recon_project_backward(params.data_ptr(), model.packed.data_ptr(), grad_out.data_ptr(),
-                                                  dparams.data_ptr(), B, model.nver, model.ndim_shape, model.ndim_exp, flags,
-                                                  ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+                                                  dparams.data_ptr(), B, model.nver, model.ndim_shape, model.ndim_exp,
+                                                  ctx.im_size, flags, ws.data_ptr(), ws.numel(),
+                                                  torch.cuda.current_stream(dev).cuda_stream))
         return dparams, None, None, None
 
 
@@ -124,9 +125,12 @@ class _RenderingLayer(torch.autograd.Function):
         return vertex_grad, None, None, None, None, None
 
 
-def recon_project(params, model: DeviceModel, im_size=200, flags=None):
-    """Functional form of ``vertices_transform`` for a [B,d] parameter tensor."""
-    return _ReconProject.apply(params, model, float(im_size), model.run_flags if flags is None else int(flags))
+def recon_project(params, model: DeviceModel, im_size=200, flags=None, raw=False):
+    """Functional form of ``vertices_transform`` for a [B,d] parameter tensor.  ``raw=True``: ``params`` are the regressor's raw
+    outputs and ``set_constraints`` (``nets/network.py:204-218``) is applied inside the prep kernels; the
+    gradient then lands on the raw values."""
+    flags = model.run_flags if flags is None else int(flags)
+    return _ReconProject.apply(params, model, float(im_size), flags | (_lib.FR_PARAMS_RAW if raw else 0))
 
 
 class FaceRecNet:
@@ -160,6 +164,11 @@ class FaceRecNet:
         if p.dim() == 4:
             p = p.squeeze(2).squeeze(1)                      # tf.squeeze(pred_params, [1, 2]), network.py:142
         return recon_project(p, self.model, self.im_size)
+
+    def vertices_transform_raw(self, raw_params):
+        """``vertices_transform(set_constraints(raw_params))`` with the constraints fused into the prep kernels."""
+        p = raw_params.squeeze(2).squeeze(1) if raw_params.dim() == 4 else raw_params
+        return recon_project(p, self.model, self.im_size, raw=True)
 
     # ------------------------------------------------------------------ network.py:174-201
     def rendering_layer(self, vertex_proj, triangles, colors):

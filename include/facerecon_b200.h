@@ -44,6 +44,9 @@ extern "C" {
 #define FR_YFLIP_S_Y_1 0x0u       /* y' = S - y - 1 nets/network.py:168 (default) */
 #define FR_YFLIP_S_Y 0x2u         /* y' = S - y     rendering_layer/sample_test.py:105 */
 #define FR_YFLIP_NONE 0x4u        /* no flip        prepare_data/Project2D.m:12 */
+#define FR_PARAMS_RAW 0x100u      /* params are the regressor's raw outputs: FaceRecNet.set_constraints (nets/network.py:204-218:
+                                   * sigmoid, then angles*3-1.5 | t_xy*im_size | t_z*0 | f*1e-3 | shape*1e4 | exp*3-1.5) is applied
+                                   * inside the prep kernels, and the backward returns the gradient w.r.t. the raw values */
 /* Pack-time flags of fr_pack_basis (memory layout of the 3N-long axis): */
 #define FR_MEAN_PLANAR 0x0u       /* mu[c*N+n]      nets/network.py:157 (default) */
 #define FR_MEAN_INTERLEAVED 0x10u /* mu[3*n+c]      rendering_layer/sample_test.py:101 */
@@ -76,7 +79,7 @@ int fr_recon_project_forward(const float* params, const float* packed, float* ve
  * (gradient w.r.t. vertex_proj) -> params_grad [batch, 7+ndim_shape+ndim_exp]; the three angle entries
  * are 0 because tf.py_func (network.py:150) has no gradient. */
 int fr_recon_project_backward(const float* params, const float* packed, const float* vertex_grad, float* params_grad,
-                              int batch, int nver, int ndim_shape, int ndim_exp, unsigned flags, void* workspace,
+                              int batch, int nver, int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                               size_t workspace_bytes, void* stream);
 
 /* ---- TF op "RenderDepth" (render_depth_op.cc:378-458, :535-569; functor :132-322) ---------------

@@ -288,6 +288,32 @@ def test_session_pipelined_slots_match_synchronous(bfm):
     sess.close()
 
 
+@pytest.mark.parametrize("B", [5, 24])
+def test_set_constraints_fused_into_prep(bfm, B):
+    """FR_PARAMS_RAW -- set_constraints inside the prep kernels (FFMA path at B = 5, tcgen05 path at B = 24) ==
+    the torch transcription of network.py:204-218 followed by vertices_transform; same for the gradient w.r.t. the raw values."""
+    net = fr("nets.network").FaceRecNet(mesh_data=bfm, batch_size=B, im_size=200, device=DEV)
+    rng = np.random.default_rng(B)
+    raw_np = rng.normal(scale=1.5, size=(B, 235)).astype(np.float32)
+    raw_np[:, 0:3] *= 0.2                                                   # keep the faces roughly frontal
+    g = torch.from_numpy(rng.normal(size=(B, 3, 53215)).astype(np.float32)).to(DEV)
+    outs, grads = [], []
+    for fused in (True, False):
+        raw = torch.from_numpy(raw_np).to(DEV).requires_grad_(True)
+        if fused:
+            vp = net.vertices_transform_raw(raw[:, None, None, :])
+        else:
+            vp = net.vertices_transform(net.set_constraints(raw[:, None, None, :]))
+        (vp * g).sum().backward()
+        outs.append(vp.detach().cpu().numpy())
+        grads.append(raw.grad.cpu().numpy().astype(np.float64))
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-6 * np.abs(outs[1]).max()
+    for sl in (slice(3, 5), slice(6, 7), slice(7, 206), slice(206, 235)):
+        scale = np.abs(grads[1][:, sl]).max(axis=1, keepdims=True) + 1e-30
+        assert (np.abs(grads[0][:, sl] - grads[1][:, sl]) <= GRAD_TOL * scale).all(), sl
+    assert not grads[0][:, 0:3].any() and not grads[0][:, 5].any()
+
+
 def test_geometry_loss_gram_form(bfm):
     """the geometry loss through the 228 x 228 Gram matrix == the literal mean squared difference of the two
     basis contractions (network.py:346-355), value and gradient w.r.t. the predicted coefficients."""
