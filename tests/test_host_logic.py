@@ -112,3 +112,22 @@ def test_synthetic_model_shapes():
     assert set(m) == {"vertex", "tri", "mu", "mu_tex", "pc_tex", "param_tex", "pc_shape", "pc_exp", "ndim_shape", "ndim_exp", "ndim_pose"}
     p = fr("synth").sample_params_constrained(5, 4, 2)
     assert p.shape == (5, 13) and (p[:, 5] == 0).all() and (np.abs(p[:, :3]) <= 1.5).all()
+
+
+def test_label_wire_format_round_trip(tmp_path):
+    """the 235-line %.6f label files (utils/data_process.py:38-60): batch shape, precision, error behaviour."""
+    dp = fr("utils.data_process")
+    params = fr("synth").sample_params_constrained(3, seed=9)
+    files = []
+    for i, p in enumerate(params):
+        files.append(str(tmp_path / ("%d.txt" % i)))
+        dp.write_label(files[-1], p)
+    got = dp.prepare_input_label(files, 3, 235)
+    assert got.shape == (3, 1, 1, 235) and got.dtype == np.float64
+    assert np.abs(got[:, 0, 0, :] - params).max() <= 5.1e-7 + 1e-7 * np.abs(params).max()    # %.6f quantisation
+    with pytest.raises(FileNotFoundError):
+        dp.prepare_input_label([files[0], str(tmp_path / "missing.txt"), files[2]], 3, 235)
+    short = str(tmp_path / "short.txt")
+    dp.write_label(short, params[0][:100])
+    with pytest.raises(IOError):
+        dp.prepare_input_label([short], 1, 235)
