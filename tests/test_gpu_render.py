@@ -216,3 +216,55 @@ def test_rendering_layer_fused_matches_unfused(small_model):
             assert a.tobytes() == b.tobytes(), name
     assert np.abs(grads[0]).max() > 0
     assert np.abs(grads[0] - grads[1]).max() <= 1e-6 * np.abs(grads[1]).max()
+
+
+def test_full_size_properties_batch_256():
+    """BASELINE config sizes (53 215 vertices, 105 840 triangles, 200 x 200), 256 faces -- too many for the CPU oracle in a
+    test, so size-independent properties instead: (a) the 256-face call equals four 64-face calls byte for byte,
+    (b) a repeated face gives repeated maps, (c) every covered pixel's depth is exactly the float mean of its winner's three
+    vertex depths and every background pixel holds the reference's background value, (d) the winner really covers the pixel
+    centre (its bounding box contains it), (e) coverage is plausible."""
+    lib, check = fr("_lib").lib(), fr("_lib").check
+    synth = fr("synth")
+    model = synth.make_synthetic_model(seed=0, jitter=0.2)
+    dm = fr("model").DeviceModel(model, DEV)
+    B, S = 256, 200
+    p = synth.sample_params_constrained(B, seed=12)
+    p[200] = p[7]                                                          # (b)
+    pt = torch.from_numpy(p).to(DEV)
+    sp = torch.cuda.current_stream().cuda_stream
+
+    def fused(params, nb):
+        ws = torch.empty(lib.fr_pipeline_workspace_bytes(nb, dm.nver, dm.ndim_shape, dm.ndim_exp, S, S), dtype=torch.uint8, device=DEV)
+        vp = torch.empty((nb, 3, dm.nver), device=DEV)
+        d, t = torch.empty((nb, S, S, 1), device=DEV), torch.empty((nb, S, S, 1), device=DEV)
+        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), vp.data_ptr(), d.data_ptr(),
+                                          t.data_ptr(), nb, dm.nver, dm.ntri, dm.ndim_shape, dm.ndim_exp, S, S, float(S), dm.run_flags,
+                                          ws.data_ptr(), ws.numel(), sp))
+        torch.cuda.synchronize()
+        return vp, d, t
+
+    vp, depth, tri_ind = fused(pt, B)
+    for q in range(4):                                                     # (a)
+        vq, dq, tq = fused(pt[64 * q:64 * (q + 1)].contiguous(), 64)
+        assert torch.equal(dq, depth[64 * q:64 * (q + 1)]) and torch.equal(tq, tri_ind[64 * q:64 * (q + 1)])
+        assert torch.equal(vq, vp[64 * q:64 * (q + 1)])
+    assert torch.equal(depth[200], depth[7]) and torch.equal(tri_ind[200], tri_ind[7])
+    covered = tri_ind[..., 0] >= 0
+    frac = covered.float().mean().item()
+    assert 0.15 < frac < 0.95, frac                                        # (e)
+    bidx = torch.arange(B, device=DEV)[:, None, None].expand(-1, S, S)[covered]
+    t = tri_ind[..., 0][covered].long()
+    i1, i2, i3 = (dm.tri[k].long()[t] for k in range(3))
+    z = vp[:, 2, :]
+    zsum = (z[bidx, i1] + z[bidx, i2]) + z[bidx, i3]
+    want = zsum / torch.full_like(zsum, 3.0)                               # (c) render_depth_op.cc:217 -- tensor / tensor: an IEEE divide
+                                                                           # (tensor / python scalar multiplies by the reciprocal)
+    assert torch.equal(depth[..., 0][covered], want)
+    assert (depth[..., 0][~covered] == -99999999999999.0).all()
+    ys, xs = torch.meshgrid(torch.arange(S, device=DEV), torch.arange(S, device=DEV), indexing="ij")
+    px = xs[None].expand(B, -1, -1)[covered].float()
+    py = ys[None].expand(B, -1, -1)[covered].float()
+    x = torch.stack([vp[:, 0, :][bidx, i] for i in (i1, i2, i3)])
+    y = torch.stack([vp[:, 1, :][bidx, i] for i in (i1, i2, i3)])
+    assert bool(((x.min(0).values <= px) & (px <= x.max(0).values) & (y.min(0).values <= py) & (py <= y.max(0).values)).all())   # (d)
