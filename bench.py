@@ -457,6 +457,9 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: batch-64 synthetic 235-d params -> 3DMM recon + pose projection + "
                                    "200x200 depth render (depth + tri_ind), forward only, per GPU",
+                       "arithmetic": "f32 results; reconstruction on tcgen05 with fp16 hi/lo operand pairs (22 significant bits) and "
+                                     "fp32 accumulation, rasterizer cull in packed integers and inside tests in separately rounded f64 "
+                                     "(bit-exact with the reference)",
                        "batch_per_gpu": B, "nver": nver, "ntri": ntri, "ndim_shape": ks, "ndim_exp": ke, "image": [H, W],
                        "l2": "flushed before every timed step (512 MiB write, outside the events)",
                        "call": "fr_recon_render_forward, depth + tri_ind out; the optional vertex_proj output is not requested in "
@@ -475,6 +478,8 @@ def run_ours(args):
                          "peak_source": peak_src, "algorithmic_bytes": dbytes, "ms": dms,
                          "how": "device time between CUDA events of the same real step (the library records one between the "
                                 "two parts), algorithmic bytes per SURVEY.md 8(d)",
+                         "limiter": "the render part is bound by instruction issue and dependent gathers (profiles/r01_summary.md), "
+                                    "the recon part by HBM" if dom.startswith("render") else "HBM (basis stream + vertex records)",
                          "other_part": {"kernel": other, "algorithmic_bytes": parts[other][0], "ms": parts[other][1],
                                         "achieved": parts[other][0] / (parts[other][1] * 1e-3) / 1e9,
                                         "frac": parts[other][0] / (parts[other][1] * 1e-3) / 1e9 / peak,
