@@ -59,10 +59,12 @@ extern "C" {
 const char* fr_last_error(void);
 int fr_version(void);
 
-/* ---- model packing: utils/parser_3dmm.py dict -> one K-contiguous device matrix -----------------
- * Packs [pc_shape | pc_exp | mu | 0-pad] into the tiled layout the kernels stream (DESIGN.md
- * "Packed basis").  mu [3N], pc_shape [3N,ndim_shape], pc_exp [3N,ndim_exp] are device pointers in
- * the reference's layouts (nets/network.py:41-43).  One-off, at model load. */
+/* ---- model packing: utils/parser_3dmm.py dict -> one device buffer ------------------------------
+ * Packs [pc_shape | pc_exp | mu | 0-pad] into the layouts the kernels stream (DESIGN.md "Packed basis"):
+ * an fp32 float4-tiled section (FFMA kernels), fp16 hi/lo tcgen05 operand tiles of the column-scaled basis
+ * for the forward and, transposed, for the backward contraction, the column scales and an fp32 copy of
+ * the mean.  mu [3N], pc_shape [3N,ndim_shape], pc_exp [3N,ndim_exp] are device pointers in the
+ * reference's layouts (nets/network.py:41-43).  One-off, at model load. */
 size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp);
 int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, int nver, int ndim_shape, int ndim_exp,
                   unsigned layout_flags, float* packed, void* stream);
@@ -77,7 +79,7 @@ int fr_recon_project_forward(const float* params, const float* packed, float* ve
 
 /* Gradient of the above as TF autodiff produces it: vertex_grad [batch,3,nver]
  * (gradient w.r.t. vertex_proj) -> params_grad [batch, 7+ndim_shape+ndim_exp]; the three angle entries
- * are 0 because tf.py_func (network.py:150) has no gradient. */
+ * are 0 because tf.py_func (network.py:150) has no gradient.  im_size only matters with FR_PARAMS_RAW. */
 int fr_recon_project_backward(const float* params, const float* packed, const float* vertex_grad, float* params_grad,
                               int batch, int nver, int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                               size_t workspace_bytes, void* stream);
