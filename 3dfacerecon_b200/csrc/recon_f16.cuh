@@ -280,8 +280,9 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   pdl_trigger();                                   // the rasterizer's blocks may become resident (they wait before reading records / keys)
-  pdl_wait();                                      // the prep kernel's coefficient operands and poses are complete from here on
-  for (int i = threadIdx.x; i < kN * kPose16Stride; i += kThreads) s_pose[i] = pose16[(size_t)b0 * kPose16Stride + i];
+  // No pdl_wait() here: only the coefficient operands and the poses come from the prep kernel.  The basis stream, the key
+  // clearing, the TMEM allocation start at once and overlap the prep kernel; the producer waits before it loads the
+  // coefficient operands, the epilogue warps before they read the poses.
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -290,20 +291,27 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
   if (warp == kProducerWarp) {
     // ================================================================== producer (TMA engine)
     if (lane == 0) {
-      const uint32_t bbytes = (kN / 8) * L.sbo;
-      mbar_arrive_expect_tx(&bars->b_full, 2u * bbytes);
-      bulk_load(smem + L.b0, bsplit + (size_t)blockIdx.y * 2 * bbytes, bbytes, &bars->b_full);
-      bulk_load(smem + L.b1, bsplit + (size_t)blockIdx.y * 2 * bbytes + bbytes, bbytes, &bars->b_full);
+      bool b_loaded = false;
+      auto load_b = [&]() {                                    // the prep kernel's output: wait for it (programmatic dependent launch)
+        pdl_wait();
+        const uint32_t bbytes = (kN / 8) * L.sbo;
+        mbar_arrive_expect_tx(&bars->b_full, 2u * bbytes);
+        bulk_load(smem + L.b0, bsplit + (size_t)blockIdx.y * 2 * bbytes, bbytes, &bars->b_full);
+        bulk_load(smem + L.b1, bsplit + (size_t)blockIdx.y * 2 * bbytes + bbytes, bbytes, &bars->b_full);
+        b_loaded = true;
+      };
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const unsigned char* src = tiles + (size_t)tile * tile_bytes;
         for (int sg = 0; sg < nch16; ++sg, ++it) {             // nch16 stages of 3 chunks per tile
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          if (it == (uint32_t)kStages) load_b();               // the ring is full of basis stages: the MMAs need the operands now
           mbar_wait(&bars->raw_empty[s], ph ^ 1u);
           mbar_arrive_expect_tx(&bars->raw_full[s], kStageBytes);
           bulk_load(smem + L.raw + s * kStageBytes, src + (size_t)sg * kStageBytes, kStageBytes, &bars->raw_full[s]);
         }
       }
+      if (!b_loaded) load_b();                                 // fewer stages than the ring holds
     }
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer (whole warp converged, one elected lane issues)
@@ -361,6 +369,9 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       for (size_t i = (size_t)blockIdx.x * (kEpiWarps * 32) + threadIdx.x; i < nvec; i += (size_t)gridDim.x * (kEpiWarps * 32))
         kv[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    pdl_wait();                                                   // the prep kernel's poses
+    for (int i = threadIdx.x; i < kN * kPose16Stride; i += kEpiWarps * 32) s_pose[i] = pose16[(size_t)b0 * kPose16Stride + i];
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // the epilogue warps only (threads 0 .. 255)
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
