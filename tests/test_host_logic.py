@@ -131,3 +131,39 @@ def test_label_wire_format_round_trip(tmp_path):
     dp.write_label(short, params[0][:100])
     with pytest.raises(IOError):
         dp.prepare_input_label([short], 1, 235)
+
+
+def test_fp16_pair_operand_arithmetic_budget():
+    """Host emulation of the operand arithmetic of recon_f16.cuh (no GPU): column-scaled basis split into fp16 hi + lo,
+    per-face scaled coefficients split into fp16 b0 + b1, the three products the kernel issues (hi.b0 + lo.b0 + hi.b1),
+    exact accumulation -- the representation alone must stay far inside the 1e-5 vertex tolerance, also for a model whose
+    columns differ by many orders of magnitude and for coefficients of very different sizes."""
+    synth = fr("synth")
+    m = synth.make_synthetic_model(grid=(23, 31), ndim_shape=12, ndim_exp=5, seed=3, jitter=0.2)
+    ks, ke = 12, 5
+    P = np.concatenate([m["pc_shape"], m["pc_exp"], m["mu"].reshape(-1, 1)], axis=1).astype(np.float64)    # [3N, K]
+    rng = np.random.default_rng(0)
+    P[:, 3] *= 1e-6                                                        # a tiny column and a huge one
+    P[:, 7] *= 1e5
+    params = synth.sample_params_constrained(9, ks, ke, 64, seed=5, full_range=True)
+    coef = np.concatenate([params[:, 7:], np.ones((9, 1), np.float32)], axis=1).astype(np.float64)         # mean coefficient 1
+    coef[2, :5] *= 1e-4
+    coef[5, 9] *= 300.0
+    # pack time: 2^s_k with colmax 2^s in [2^14, 2^15)  (basis_colscale_kernel)
+    colmax = np.abs(P).max(axis=0)
+    s = 15 - np.frexp(colmax)[1]
+    Ps = (P * np.exp2(s)).astype(np.float32)
+    hi = Ps.astype(np.float16)
+    lo = (Ps - hi.astype(np.float32)).astype(np.float16)
+    assert np.isfinite(hi.astype(np.float64)).all() and np.abs(hi.astype(np.float64)).max() < 2.0 ** 15 + 16
+    # prep kernel: c = coef 2^-s 2^t with max_k |c| in [2^13, 2^14)  (recon_prep_f16_kernel)
+    c = (coef * np.exp2(-s)).astype(np.float32)
+    t = 14 - np.frexp(np.abs(c).max(axis=1))[1]
+    cs = (c * np.exp2(t)[:, None]).astype(np.float32)
+    b0 = cs.astype(np.float16)
+    b1 = (cs - b0.astype(np.float32)).astype(np.float16)
+    H, L, B0, B1 = (a.astype(np.float64) for a in (hi, lo, b0, b1))
+    got = (H @ B0.T + L @ B0.T + H @ B1.T) * np.exp2(-t)[None, :]          # the kernel's three MMAs, exact accumulation
+    want = P @ coef.T
+    err = np.abs(got - want).max(axis=0) / np.abs(want).max(axis=0)
+    assert err.max() < 2e-6, err                                          # representation: ~2^-21 relative, tolerance 1e-5
