@@ -27,6 +27,10 @@
 #include "recon.cuh"
 #include "tcgen05_common.cuh"
 
+#ifndef FR_BASIS_EVICT_FIRST
+#define FR_BASIS_EVICT_FIRST 1   // A/B on B200: 102.8 -> 101.6 us per step (the records / keys stay in L2 for the rasterizer)
+#endif
+
 namespace fr {
 namespace f16 {
 
@@ -301,6 +305,9 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         b_loaded = true;
       };
       uint32_t it = 0;
+#if FR_BASIS_EVICT_FIRST
+      const uint64_t stream_policy = tc::l2_evict_first_policy();
+#endif
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const unsigned char* src = tiles + (size_t)tile * tile_bytes;
         for (int sg = 0; sg < nch16; ++sg, ++it) {             // nch16 stages of 3 chunks per tile
@@ -308,7 +315,11 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
           if (it == (uint32_t)kStages) load_b();               // the ring is full of basis stages: the MMAs need the operands now
           mbar_wait(&bars->raw_empty[s], ph ^ 1u);
           mbar_arrive_expect_tx(&bars->raw_full[s], kStageBytes);
+#if FR_BASIS_EVICT_FIRST
+          tc::bulk_load_hint(smem + L.raw + s * kStageBytes, src + (size_t)sg * kStageBytes, kStageBytes, &bars->raw_full[s], stream_policy);
+#else
           bulk_load(smem + L.raw + s * kStageBytes, src + (size_t)sg * kStageBytes, kStageBytes, &bars->raw_full[s]);
+#endif
         }
       }
       if (!b_loaded) load_b();                                 // fewer stages than the ring holds

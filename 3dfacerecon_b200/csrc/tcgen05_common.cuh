@@ -42,6 +42,19 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// The same with an L2 eviction policy: the basis is read exactly once per launch, so it is streamed evict-first and does
+// not push the vertex records / keys the next kernel needs out of L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
 // one lane of a fully converged warp (keeps tcgen05.mma / commit on the uniform datapath: a lane-0 branch makes the
 // compiler serialise every uniform-register operand through per-thread loops and triples the issue cost)
 __device__ __forceinline__ bool elect_one() {
