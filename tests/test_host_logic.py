@@ -167,3 +167,34 @@ def test_fp16_pair_operand_arithmetic_budget():
     want = P @ coef.T
     err = np.abs(got - want).max(axis=0) / np.abs(want).max(axis=0)
     assert err.max() < 2e-6, err                                          # representation: ~2^-21 relative, tolerance 1e-5
+
+
+def test_backward_operand_arithmetic_budget():
+    """Host emulation of the tensor-core backward's operand arithmetic (recon_bwd_f16.cuh): the rotated vertex gradient scaled
+    per face by a power of two from its own maximum and split into fp16 hi + lo, the column-scaled basis split likewise, the
+    three products the kernel issues, the mean column kept in float32/64 -- against the float64 contraction.  Faces with
+    gradients eight orders of magnitude apart must not disturb each other."""
+    synth = fr("synth")
+    m = synth.make_synthetic_model(grid=(23, 31), ndim_shape=12, ndim_exp=5, seed=3, jitter=0.2)
+    P = np.concatenate([m["pc_shape"], m["pc_exp"]], axis=1).astype(np.float64)                            # [3N, K], mean handled apart
+    rng = np.random.default_rng(1)
+    B = 6
+    dv = rng.normal(size=(B, P.shape[0])).astype(np.float32).astype(np.float64)
+    dv[1] *= 1e-6
+    dv[4] *= 1e3
+    colmax = np.abs(np.concatenate([P, m["mu"].reshape(-1, 1).astype(np.float64)], axis=1)).max(axis=0)
+    s = (15 - np.frexp(colmax)[1])[:P.shape[1]]
+    Ps = (P * np.exp2(s)).astype(np.float32)
+    hi = Ps.astype(np.float16)
+    lo = (Ps - hi.astype(np.float32)).astype(np.float16)
+    gm = 2.0 * np.abs(dv).max(axis=1)                                      # the kernel bounds |dv| by 2 max|g|; here dv itself
+    u = 14 - np.frexp(gm)[1]
+    dvs = (dv * np.exp2(u)[:, None]).astype(np.float32)
+    ghi = dvs.astype(np.float16)
+    glo = (dvs - ghi.astype(np.float32)).astype(np.float16)
+    assert np.isfinite(ghi.astype(np.float64)).all()
+    H, L, GH, GL = (a.astype(np.float64) for a in (hi, lo, ghi, glo))
+    got = (GH @ H + GH @ L + GL @ H) * np.exp2(-u)[:, None] * np.exp2(-s)[None, :]   # D 2^-u_b 2^-s_k, exact accumulation
+    want = dv @ P
+    err = np.abs(got - want).max(axis=1) / np.abs(want).max(axis=1)
+    assert err.max() < 5e-6, err                                          # gradients are judged at 1e-4
