@@ -31,19 +31,24 @@ SIGNATURES = {
     "fr_last_error": (ctypes.c_char_p, []),
     "fr_version": (_i, []),
     "fr_launch_count": (ctypes.c_ulonglong, []),
-    "fr_debug_set_mid_event": (_i, [_vp]),
-    "fr_packed_basis_bytes": (_sz, [_i, _i, _i]),
-    "fr_pack_basis": (_i, [_vp, _vp, _vp, _i, _i, _i, _u, _vp, _vp]),
+    "fr_mesh_table_create": (_i, [_vp, _i, _i, _vp, _i, _i, ctypes.POINTER(_vp)]),
+    "fr_mesh_table_from_blob": (_i, [_vp, _sz, _i, ctypes.POINTER(_vp)]),
+    "fr_mesh_table_destroy": (None, [_vp]),
+    "fr_mesh_table_blob": (_vp, [_vp, ctypes.POINTER(_sz)]),
+    "fr_mesh_table_clusters": (_i, [_vp]),
+    "fr_mesh_table_vertex_slots": (_i, [_vp]),
+    "fr_packed_basis_bytes": (_sz, [_i, _i, _i, _vp]),
+    "fr_pack_basis": (_i, [_vp, _vp, _vp, _i, _i, _i, _u, _vp, _vp, _vp]),
     "fr_recon_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "fr_recon_project_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
+    "fr_recon_project_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
     "fr_recon_project_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
-    "fr_render_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "fr_render_depth_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "fr_render_workspace_bytes": (_sz, [_i, _i, _i, _i, _vp]),
+    "fr_render_depth_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "fr_render_depth_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "fr_rendering_layer_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "fr_rendering_layer_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "fr_rendering_layer_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "fr_pipeline_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "fr_recon_render_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
+    "fr_pipeline_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _vp]),
+    "fr_recon_render_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp, _vp]),
     "fr_session_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u, _i, ctypes.POINTER(_vp)]),
     "fr_session_destroy": (None, [_vp]),
     "fr_session_forward": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),

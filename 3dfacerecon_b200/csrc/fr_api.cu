@@ -1,15 +1,27 @@
 // C ABI of facerecon_b200 (include/facerecon_b200.h): argument validation, workspace carving and kernel
 // launches.  No CPU fallback anywhere: every compute entry point launches sm_100a kernels or fails.
+#include <algorithm>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <new>
 #include <vector>
 
 #include "fr_common.cuh"
+#include "mesh_table.h"
 #include "raster.cuh"
+#include "raster_cluster.cuh"
 #include "recon.cuh"
 #include "recon_f16.cuh"
 #include "recon_bwd_f16.cuh"
+
+// Host handle of a mesh table (mesh_table.h): the blob on the host and, when created for a device, its copy there.
+struct fr_mesh_table {
+  std::vector<unsigned char> host;
+  unsigned char* dev;
+  int device;
+  fr::MeshTableHeader hdr;
+};
 
 using namespace fr;
 
@@ -94,30 +106,42 @@ int launch_recon_fwd_simt(const float* packed, const ReconWorkspace& w, ReconOut
   return FR_OK;
 }
 
-// fr_recon_project_forward with a choice of outputs (planar tensor and / or rasterizer records, recon.cuh ReconOut)
-int recon_project_forward_impl(const float* params, const float* packed, const ReconOut& out, int batch, int nver,
-                               int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+int check_mesh(const fr_mesh_table* mesh, int nver, int ntri) {
+  if (mesh == nullptr) return FR_OK;
+  FR_REQUIRE(mesh->dev != nullptr, "the mesh table was created without a device copy (device < 0)");
+  FR_REQUIRE(mesh->hdr.nver == nver, "mesh table was built for nver=%d, called with nver=%d", mesh->hdr.nver, nver);
+  FR_REQUIRE(ntri < 0 || mesh->hdr.ntri == ntri, "mesh table was built for ntri=%d, called with ntri=%d", mesh->hdr.ntri, ntri);
+  return FR_OK;
+}
+const int32_t* mesh_cluster_vert(const fr_mesh_table* mesh) {
+  return mesh ? reinterpret_cast<const int32_t*>(mesh->dev + mesh->hdr.off_vert) : nullptr;
+}
+
+// Tensor-core path for this batch?  (FR_RECON_PATH = simt | f16 overrides the dispatch, for A/B comparisons.)
+bool use_f16_forward(const BasisGeom& g, int batch, bool raster) {
+  const int ov = recon_path_override();
+  return recon_f16_fits(g, raster) && (ov == 3 || (ov == 0 && batch > 8));
+}
+
+// fr_recon_project_forward; with `target` the tensor-core kernel also rasterizes (fused call, use_f16_forward(g, batch, true)
+// must hold) and out.planar becomes optional.
+int recon_project_forward_impl(const float* params, const float* packed, const fr_mesh_table* mesh, const ReconOut& out,
+                               const f16::RasterTarget* target, int batch, int nver, int ndim_shape, int ndim_exp, float im_size,
+                               unsigned flags, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
+  if (int rc = check_mesh(mesh, nver, -1)) return rc;
   if (batch == 0) return FR_OK;
-  FR_REQUIRE(params && packed && (out.planar || out.rec), "null pointer argument");
-  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp);
+  FR_REQUIRE(params && packed && (out.planar || target), "null pointer argument");
+  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp, mesh ? mesh->hdr.nclusters : 0);
   const ReconWorkspace w = carve_recon(workspace, batch, g);
   if (int rc = check_workspace(workspace, workspace_bytes, w.bytes)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
 
-  // dispatch: fp16-pair tcgen05 kernel above 8 faces (FR_RECON_PATH = simt | f16 overrides it, for A/B comparisons)
-  const int ov = recon_path_override();
-  const size_t key_bytes_face = out.keys ? sizeof(unsigned long long) * (size_t)out.width * out.height : 0;
-  if (recon_f16_fits(g) && (ov == 3 || (ov == 0 && batch > 8))) {
-    const bool fold = out.keys != nullptr && key_bytes_face % 16 == 0;     // the kernel clears the keys itself, 16 bytes at a time
-    if (out.keys != nullptr && !fold) FR_CUDA(cudaMemsetAsync(out.keys, 0, key_bytes_face * batch, st));
-    return launch_recon_fwd_f16(params, packed, w.bsplit16, w.pose16, out, batch, nver, g, im_size, flags, sm_count(), st,
-                                fold ? out.keys : nullptr, fold ? (int)(key_bytes_face / 16) : 0);
-  }
-  if (out.keys != nullptr) FR_CUDA(cudaMemsetAsync(out.keys, 0, key_bytes_face * batch, st));
+  if (target != nullptr || use_f16_forward(g, batch, false))
+    return launch_recon_fwd_f16(params, packed, w.bsplit16, w.pose16, out, target, mesh_cluster_vert(mesh), batch, nver, g, im_size,
+                                flags, sm_count(), st);
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
                                                                  g.kpad, flags, im_size, w.coefT, w.pose);
   FR_LAUNCHED("recon_prep_kernel");
@@ -127,13 +151,9 @@ int recon_project_forward_impl(const float* params, const float* packed, const R
   return launch_recon_fwd_simt<16>(packed, w, out, batch, nver, g, im_size, flags, gy, st);
 }
 
-// fr_render_depth_forward; with records_ready the workspace already holds this batch's vertex records and cleared
-// visibility keys (written by the fused call's reconstruction epilogue), `vertex` may then be null unless normals or
-// texture are requested.
-int render_depth_forward_impl(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
-                              float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
-                              int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream,
-                              bool records_ready, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false}) {
+size_t key_bytes(int batch, int height, int width) { return align_up(sizeof(unsigned long long) * (size_t)batch * height * width, kAlign); }
+
+int check_render_dims(int batch, int nver, int ntri, int height, int width) {
   FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
              "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
   // render_depth_op.cc:161-166: the reference refuses ntri >= 10M (its static scratch); nver < 2^24 keeps float indices exact
@@ -141,27 +161,60 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
   FR_REQUIRE(nver <= (1 << 24), "nver %d exceeds the exact range of float triangle indices", nver);
   FR_REQUIRE(height <= 32000 && width <= 32000 && (long long)height * width < (1ll << 31), "image too large");
   FR_REQUIRE((long long)batch * 3 * nver < (1ll << 31), "batch * 3 * nver must stay below 2^31: split the batch");
+  FR_REQUIRE(batch <= 65535, "batch %d exceeds 65535 faces per call: split the batch", batch);   // faces ride in gridDim.y
+  return FR_OK;
+}
+
+// Resolve pass: keys -> depth / tri_ind (+ normals, texture, rendering-layer post-processing).
+int launch_resolve(const unsigned long long* keys, const float* vertex, const float* tri, const float* texture,
+                   long long texture_batch_stride, float* depth, float* texture_image, float* normal, float* tri_ind, int batch,
+                   int nver, int ntri, int npix, const LayerOut& layer, bool dependent, cudaStream_t st) {
+  const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
+  if (texture_image != nullptr || normal != nullptr)
+    FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, tri, texture,
+                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
+  else
+    FR_CUDA(launch_pdl(raster_resolve_kernel<false>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, tri, texture,
+                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
+  FR_LAUNCHED("raster_resolve_kernel");
+  return FR_OK;
+}
+
+// fr_render_depth_forward.  With a mesh table: visibility keys only in the workspace, the cluster rasterizer stages the
+// vertices in shared memory (raster_cluster.cuh).  Without: the generic path (16-byte vertex records in the workspace,
+// per-triangle gathers, raster.cuh).
+int render_depth_forward_impl(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
+                              float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
+                              int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
+                              void* stream, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false}) {
+  if (int rc = check_render_dims(batch, nver, ntri, height, width)) return rc;
+  if (int rc = check_mesh(mesh, nver, ntri)) return rc;
   if (batch == 0) return FR_OK;
-  FR_REQUIRE((vertex || records_ready) && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
-  FR_REQUIRE(vertex || (texture_image == nullptr && normal == nullptr), "normals / texture need the planar vertex tensor");
+  FR_REQUIRE(vertex && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
   FR_REQUIRE(texture_image == nullptr || texture != nullptr, "texture_image requested without a texture");
   FR_REQUIRE(texture_batch_stride == 0 || texture_batch_stride >= 3ll * nver, "texture_batch_stride must be 0 or >= 3*nver");
-  const size_t need = fr_render_workspace_bytes(batch, nver, height, width);
+  const size_t need = fr_render_workspace_bytes(batch, nver, height, width, mesh);
   if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* keys = static_cast<unsigned long long*>(workspace);
   const int npix = height * width;
-  float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) +
-                                          align_up(sizeof(unsigned long long) * (size_t)batch * npix, kAlign));
+  const bool pdl = pdl_enabled();   // dependent launches: the kernels call pdl_wait() before touching their predecessor's output
+  bool resolve_dependent = false;
 
-  if (ntri > 0) {
-    if (!records_ready) {   // the pack pass also clears the visibility keys
-      raster_pack_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
-          vertex, rec, keys, nver, npix, width, height);
-      FR_LAUNCHED("raster_pack_kernel");
-    }
+  if (ntri > 0 && mesh != nullptr && mesh->hdr.ntri_slots > 0) {
+    FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
+    FR_CUDA(cudaFuncSetAttribute(rc::raster_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rc::KernelSmem)));
+    const dim3 grid(mesh->hdr.nclusters, ceil_div(batch, rc::kStageFaces));
+    FR_CUDA(launch_pdl(rc::raster_cluster_kernel, grid, dim3(rc::kThreads), sizeof(rc::KernelSmem), st, false, vertex,
+                       static_cast<const unsigned char*>(mesh->dev), keys, batch, nver, height, width));
+    FR_LAUNCHED("raster_cluster_kernel");
+    resolve_dependent = pdl;
+  } else if (ntri > 0 && mesh == nullptr) {
+    float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) + key_bytes(batch, height, width));
+    raster_pack_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
+        vertex, rec, keys, nver, npix, width, height);   // also clears the visibility keys
+    FR_LAUNCHED("raster_pack_kernel");
     const unsigned gx = (unsigned)ceil_div(ntri, kKeysThreads);
-    const bool pdl = pdl_enabled();   // dependent launches: the kernels call pdl_wait() before touching their predecessor's output
     const float4* crec = rec;
     if (batch >= 8)
       FR_CUDA(launch_pdl(raster_keys_kernel<8>, dim3(gx, ceil_div(batch, 8)), dim3(kKeysThreads), 0, st, pdl, crec, tri, keys, batch, nver,
@@ -173,20 +226,12 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
       FR_CUDA(launch_pdl(raster_keys_kernel<1>, dim3(gx, batch), dim3(kKeysThreads), 0, st, pdl, crec, tri, keys, batch, nver, ntri,
                          height, width));
     FR_LAUNCHED("raster_keys_kernel");
-  } else if (!records_ready) {
+    resolve_dependent = pdl;
+  } else {   // nothing to draw (with no kernel in front, the resolve pass is a normal launch)
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   }
-  const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
-  const unsigned long long* ckeys = keys;
-  const bool rpdl = pdl_enabled() && ntri > 0;   // (with no triangles the predecessor is a memset, not a kernel that triggers)
-  if (texture_image != nullptr || normal != nullptr)
-    FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, rpdl, ckeys, vertex, tri, texture,
-                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
-  else
-    FR_CUDA(launch_pdl(raster_resolve_kernel<false>, rgrid, dim3(kRasterThreads), 0, st, rpdl, ckeys, vertex, tri, texture,
-                       texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
-  FR_LAUNCHED("raster_resolve_kernel");
-  return FR_OK;
+  return launch_resolve(keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver, ntri,
+                        npix, layer, resolve_dependent, st);
 }
 
 }  // namespace
@@ -197,26 +242,94 @@ const char* fr_last_error(void) { return error_buffer(); }
 int fr_version(void) { return FR_VERSION; }
 unsigned long long fr_launch_count(void) { return launch_counter().load(); }
 
-// measurement hook: a CUDA event the fused call records between its reconstruction and its rasterizer kernels, so that a
-// benchmark can time the two parts of ONE real step (bench.py "roofline"); null disables it.  Not thread-safe.
-static cudaEvent_t g_mid_event = nullptr;
-int fr_debug_set_mid_event(void* cuda_event) {
-  g_mid_event = static_cast<cudaEvent_t>(cuda_event);
+// ------------------------------------------------------------------------------------------------ mesh table
+static int mesh_finish(fr_mesh_table* m, int device, fr_mesh_table** out) {
+  std::memcpy(&m->hdr, m->host.data(), sizeof(m->hdr));
+  m->dev = nullptr;
+  m->device = device;
+  if (device >= 0) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&m->dev, m->host.size());
+    if (e == cudaSuccess) e = cudaMemcpy(m->dev, m->host.data(), m->host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      if (m->dev) cudaFree(m->dev);
+      delete m;
+      return fail(FR_ERR_CUDA, "mesh table upload failed: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = m;
   return FR_OK;
 }
 
+int fr_mesh_table_create(const float* tri, int ntri, int nver, const float* positions, int positions_interleaved, int device,
+                         fr_mesh_table** out) {
+  FR_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  FR_REQUIRE(nver > 0 && nver <= (1 << 24) && ntri >= 0 && ntri < 10 * 1000 * 1000 && (tri != nullptr || ntri == 0),
+             "bad mesh dimensions nver=%d ntri=%d", nver, ntri);
+  fr_mesh_table* m = new (std::nothrow) fr_mesh_table();
+  if (!m) return fail(FR_ERR_CUDA, "out of host memory");
+  try {
+    MeshTableBuilder builder(tri, ntri, nver, positions, positions_interleaved != 0);
+    m->host = builder.build();
+  } catch (const std::exception& e) {
+    delete m;
+    return fail(FR_ERR_CUDA, "mesh table build failed: %s", e.what());
+  }
+  return mesh_finish(m, device, out);
+}
+
+int fr_mesh_table_from_blob(const void* blob, size_t bytes, int device, fr_mesh_table** out) {
+  FR_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  FR_REQUIRE(blob != nullptr && bytes >= sizeof(MeshTableHeader), "mesh table blob too small");
+  MeshTableHeader h;
+  std::memcpy(&h, blob, sizeof(h));
+  FR_REQUIRE(h.magic == kMeshMagic && h.version == kMeshVersion, "not a mesh table (magic %08x version %u)", h.magic, h.version);
+  FR_REQUIRE(h.total_bytes == bytes && h.nclusters >= 0 && h.ntri_slots >= 0 && h.off_vert == sizeof(MeshTableHeader) &&
+                 (size_t)h.off_vert + (size_t)h.nclusters * kClusterVerts * 4 <= h.off_tri_begin &&
+                 (size_t)h.off_tri_begin + ((size_t)h.nclusters + 1) * 4 <= h.off_tri && (size_t)h.off_tri + (size_t)h.ntri_slots * 8 <= bytes,
+             "mesh table blob is inconsistent");
+  const unsigned char* p = static_cast<const unsigned char*>(blob);
+  uint32_t hash = 2166136261u;
+  for (size_t i = sizeof(MeshTableHeader); i < bytes; ++i) hash = (hash ^ p[i]) * 16777619u;
+  FR_REQUIRE(hash == h.hash, "mesh table blob is corrupt (hash mismatch)");
+  fr_mesh_table* m = new (std::nothrow) fr_mesh_table();
+  if (!m) return fail(FR_ERR_CUDA, "out of host memory");
+  m->host.assign(p, p + bytes);
+  return mesh_finish(m, device, out);
+}
+
+void fr_mesh_table_destroy(fr_mesh_table* m) {
+  if (!m) return;
+  if (m->dev) {
+    cudaSetDevice(m->device);
+    cudaFree(m->dev);
+  }
+  delete m;
+}
+
+const void* fr_mesh_table_blob(const fr_mesh_table* m, size_t* bytes) {
+  if (!m) return nullptr;
+  if (bytes) *bytes = m->host.size();
+  return m->host.data();
+}
+int fr_mesh_table_clusters(const fr_mesh_table* m) { return m ? m->hdr.nclusters : 0; }
+int fr_mesh_table_vertex_slots(const fr_mesh_table* m) { return m ? m->hdr.nvert_slots : 0; }
+
 // ------------------------------------------------------------------------------------------------ packing
-size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp) {
+size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp, const fr_mesh_table* mesh) {
   if (nver <= 0 || ndim_shape < 0 || ndim_exp < 0) return 0;
-  return basis_geom(nver, ndim_shape, ndim_exp).bytes();
+  return basis_geom(nver, ndim_shape, ndim_exp, mesh ? mesh->hdr.nclusters : 0).bytes();
 }
 
 int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, int nver, int ndim_shape, int ndim_exp,
-                  unsigned layout_flags, float* packed, void* stream) {
+                  unsigned layout_flags, const fr_mesh_table* mesh, float* packed, void* stream) {
   if (int rc = check_model_dims(0, nver, ndim_shape, ndim_exp)) return rc;
+  if (int rc = check_mesh(mesh, nver, -1)) return rc;
   FR_REQUIRE(mu && packed && (pc_shape || ndim_shape == 0) && (pc_exp || ndim_exp == 0), "null model pointer");
   FR_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 16 == 0, "packed basis must be 16-byte aligned");
-  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp);
+  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp, mesh ? mesh->hdr.nclusters : 0);
   const size_t total = (size_t)g.ntiles * 3 * g.kg * kTileVerts;
   pack_basis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       mu, pc_shape, pc_exp, nver, ndim_shape, ndim_exp, g.kg, g.ntiles, layout_flags, reinterpret_cast<float4*>(packed));
@@ -231,9 +344,9 @@ int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, i
   FR_LAUNCHED("basis_colmax_kernel");
   f16::basis_colscale_kernel<<<ceil_div(g.kpad16, 256), 256, 0, st>>>(scale, g.kreal, g.kpad16);
   FR_LAUNCHED("basis_colscale_kernel");
-  const size_t pieces = (size_t)g.ntiles * 3 * g.nch16 * 2 * kTileVerts;
+  const size_t pieces = (size_t)g.nclusters * 3 * g.nch16 * 2 * kTileVerts;       // one 128-row tile per cluster (mesh_table.h)
   f16::pack_basis_f16_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(mu, pc_shape, pc_exp, scale, nver, ndim_shape, ndim_exp,
-                                                                              g.nch16, g.ntiles, layout_flags,
+                                                                              g.nch16, g.nclusters, layout_flags, mesh_cluster_vert(mesh),
                                                                               reinterpret_cast<uint4*>(base + g.f16_offset()));
   FR_LAUNCHED("pack_basis_f16_kernel");
   // ... and the same pairs transposed for the backward contraction over the vertices
@@ -254,12 +367,12 @@ size_t fr_recon_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_ex
   return carve_recon(nullptr, batch, basis_geom(nver, ndim_shape, ndim_exp)).bytes;
 }
 
-int fr_recon_project_forward(const float* params, const float* packed, float* vertex_proj, int batch, int nver,
-                             int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
+int fr_recon_project_forward(const float* params, const float* packed, const fr_mesh_table* mesh, float* vertex_proj, int batch,
+                             int nver, int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                              size_t workspace_bytes, void* stream) {
   FR_REQUIRE(batch == 0 || vertex_proj != nullptr, "null pointer argument");
-  const ReconOut out = {vertex_proj, nullptr, 0, 0, nullptr};
-  return recon_project_forward_impl(params, packed, out, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace,
+  const ReconOut out = {vertex_proj};
+  return recon_project_forward_impl(params, packed, mesh, out, nullptr, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace,
                                     workspace_bytes, stream);
 }
 
@@ -290,8 +403,9 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
     const unsigned char* base = reinterpret_cast<const unsigned char*>(packed);
     const float* inv_scale = reinterpret_cast<const float*>(base + g.scale_offset());
     const int nb = b16::faces_per_tile(batch), nbt = ceil_div(batch, nb);
-    // (the operand tiles of faces between batch and the next multiple of 64 are zero-filled by the blocks that own them)
-    b16::recon_bwd_pack_grad_kernel<<<dim3(ceil_div(g.ntiles * (kTileVerts / 8), 32), ceil_div(batch_padded(batch), 8)), 256, 0, st>>>(
+    // (launched over whole batch tiles: the operand tiles of the faces between batch and nbt * nb are zero-filled by the
+    // blocks that own them, so the contraction never reads unwritten workspace)
+    b16::recon_bwd_pack_grad_kernel<<<dim3(ceil_div(g.ntiles * (kTileVerts / 8), 32), ceil_div(nbt * nb, 8)), 256, 0, st>>>(
         vertex_grad, w.pose, w.gmax, reinterpret_cast<const float*>(base + g.mean_offset()), batch, nver, g.ntiles, nb, flags, w.gtiles,
         w.gscale, w.gmean64);
     FR_LAUNCHED("recon_bwd_pack_grad_kernel");
@@ -326,17 +440,18 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ render
-size_t fr_render_workspace_bytes(int batch, int nver, int height, int width) {
+size_t fr_render_workspace_bytes(int batch, int nver, int height, int width, const fr_mesh_table* mesh) {
   if (batch <= 0 || nver <= 0 || height <= 0 || width <= 0) return 0;
-  return align_up(sizeof(unsigned long long) * (size_t)batch * height * width, kAlign) +   // visibility keys
-         align_up(sizeof(float4) * (size_t)batch * nver, kAlign);                            // vertex records
+  return key_bytes(batch, height, width) +                                               // visibility keys
+         (mesh ? 0 : align_up(sizeof(float4) * (size_t)batch * nver, kAlign));           // generic path: vertex records
 }
 
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                             float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
-                            int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream) {
+                            int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
+                            void* stream) {
   return render_depth_forward_impl(vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver,
-                                   ntri, height, width, workspace, workspace_bytes, stream, false);
+                                   ntri, height, width, mesh, workspace, workspace_bytes, stream);
 }
 
 int fr_render_depth_backward(const float* depth_grad, const float* tri, const float* tri_ind, float* vertex_grad,
@@ -344,6 +459,7 @@ int fr_render_depth_backward(const float* depth_grad, const float* tri, const fl
   FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
              "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
   FR_REQUIRE((long long)height * width < (1ll << 31), "image too large");
+  FR_REQUIRE(batch <= 65535, "batch %d exceeds 65535 faces per call: split the batch", batch);
   if (batch == 0) return FR_OK;
   FR_REQUIRE(depth_grad && (tri || ntri == 0) && tri_ind && vertex_grad, "null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -360,11 +476,11 @@ int fr_render_depth_backward(const float* depth_grad, const float* tri, const fl
 int fr_rendering_layer_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                                const float* im_gray, float* pncc, float* normalimg, float* maskimg, float* depthimg,
                                float* raw_depth, float* tri_ind, int batch, int nver, int ntri, int height, int width,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes, void* stream) {
   FR_REQUIRE(batch <= 0 || (pncc && normalimg && maskimg && depthimg && texture), "null pointer argument");
   const LayerOut layer = {maskimg, im_gray, raw_depth, true};
   return render_depth_forward_impl(vertex, tri, texture, texture_batch_stride, depthimg, pncc, normalimg, tri_ind, batch, nver, ntri,
-                                   height, width, workspace, workspace_bytes, stream, false, layer);
+                                   height, width, mesh, workspace, workspace_bytes, stream, layer);
 }
 
 int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg_grad, const float* im_gray, const float* raw_depth,
@@ -373,6 +489,7 @@ int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg
   FR_REQUIRE(batch >= 0 && nver > 0 && ntri >= 0 && height > 0 && width > 0,
              "bad dimensions batch=%d nver=%d ntri=%d height=%d width=%d", batch, nver, ntri, height, width);
   FR_REQUIRE((long long)height * width < (1ll << 31), "image too large");
+  FR_REQUIRE(batch <= 65535, "batch %d exceeds 65535 faces per call: split the batch", batch);
   if (batch == 0) return FR_OK;
   FR_REQUIRE(raw_depth && (tri || ntri == 0) && tri_ind && vertex_grad && (depthimg_grad || maskimg_grad), "null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -385,34 +502,68 @@ int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg
 }
 
 // ------------------------------------------------------------------------------------------------ fused
-size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width) {
-  return fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp) + fr_render_workspace_bytes(batch, nver, height, width);
+// Workspace of fr_recon_render_forward: [reconstruction | visibility keys (+ records without a mesh table) | planar
+// vertex buffer when the call cannot run fused and the caller does not want vertex_proj].
+static bool fused_possible(const fr_mesh_table* mesh, int batch, int nver, int ndim_shape, int ndim_exp) {
+  if (mesh == nullptr || mesh->hdr.ntri_slots == 0) return false;
+  return use_f16_forward(basis_geom(nver, ndim_shape, ndim_exp, mesh->hdr.nclusters), batch, true);
 }
 
-int fr_recon_render_forward(const float* params, const float* packed, const float* tri, float* vertex_proj, float* depth,
-                            float* tri_ind, int batch, int nver, int ntri, int ndim_shape, int ndim_exp, int height,
-                            int width, float im_size, unsigned flags, void* workspace, size_t workspace_bytes,
-                            void* stream) {
-  FR_REQUIRE(batch >= 0 && nver > 0 && height > 0 && width > 0 && height <= 32000 && width <= 32000 &&
-                 (long long)height * width < (1ll << 31),
-             "bad dimensions batch=%d nver=%d height=%d width=%d", batch, nver, height, width);
+size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width,
+                                   const fr_mesh_table* mesh) {
+  if (batch <= 0 || nver <= 0) return 0;
+  const size_t planar = fused_possible(mesh, batch, nver, ndim_shape, ndim_exp) ? 0 : align_up(sizeof(float) * (size_t)batch * 3 * nver, kAlign);
+  return fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp) + fr_render_workspace_bytes(batch, nver, height, width, mesh) + planar;
+}
+
+int fr_recon_render_forward(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
+                            float* vertex_proj, float* depth, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
+                            int ndim_exp, int height, int width, float im_size, unsigned flags, void* workspace,
+                            size_t workspace_bytes, void* stream, void* const* stage_events) {
+  if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
+  if (int rc = check_render_dims(batch, nver, ntri, height, width)) return rc;
+  if (int rc = check_mesh(mesh, nver, ntri)) return rc;
   if (batch == 0) return FR_OK;
+  FR_REQUIRE(params && packed && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
   const size_t rb = fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp);
-  const size_t need = rb + fr_render_workspace_bytes(batch, nver, height, width);
+  const size_t vb = fr_render_workspace_bytes(batch, nver, height, width, mesh);
+  const size_t need = fr_pipeline_workspace_bytes(batch, nver, ndim_shape, ndim_exp, height, width, mesh);
   if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
-  // The reconstruction epilogue writes the rasterizer's vertex records straight into the render workspace (same carve-up
-  // as render_depth_forward_impl: keys first, records after), so the repack pass over vertex_proj disappears;
-  // vertex_proj itself is optional here.
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* rws = static_cast<char*>(workspace) + rb;
-  const size_t key_bytes = sizeof(unsigned long long) * (size_t)batch * height * width;
-  const ReconOut out = {vertex_proj, reinterpret_cast<float4*>(rws + align_up(key_bytes, kAlign)), width, height,
-                        reinterpret_cast<unsigned long long*>(rws)};
-  if (int rc = recon_project_forward_impl(params, packed, out, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace, rb,
-                                          stream))
+  auto record = [&](int i) -> cudaError_t {
+    return (stage_events != nullptr && stage_events[i] != nullptr) ? cudaEventRecord(static_cast<cudaEvent_t>(stage_events[i]), st)
+                                                                   : cudaSuccess;
+  };
+  if (fused_possible(mesh, batch, nver, ndim_shape, ndim_exp)) {
+    // prep kernel (clears the keys) -> tensor-core reconstruction with the cluster rasterizer in its epilogue -> resolve
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(rws);
+    const f16::RasterTarget target = {static_cast<const unsigned char*>(mesh->dev), keys, width, height};
+    const ReconOut out = {vertex_proj};
+    if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, batch, nver, ndim_shape, ndim_exp, im_size, flags,
+                                            workspace, rb, stream))
+      return rc;
+    FR_CUDA(record(0));
+    const LayerOut layer = {nullptr, nullptr, nullptr, false};
+    const bool dependent = pdl_enabled() && !(stage_events != nullptr && stage_events[0] != nullptr);
+    if (int rc = launch_resolve(keys, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height * width,
+                                layer, dependent, st))
+      return rc;
+    FR_CUDA(record(1));
+    return FR_OK;
+  }
+  // small batches / no mesh table: reconstruction into a planar tensor, then the stand-alone rasterizer
+  float* planar = vertex_proj ? vertex_proj : reinterpret_cast<float*>(rws + vb);
+  const ReconOut out = {planar};
+  if (int rc = recon_project_forward_impl(params, packed, mesh, out, nullptr, batch, nver, ndim_shape, ndim_exp, im_size, flags,
+                                          workspace, rb, stream))
     return rc;
-  if (g_mid_event != nullptr) FR_CUDA(cudaEventRecord(g_mid_event, static_cast<cudaStream_t>(stream)));
-  return render_depth_forward_impl(vertex_proj, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height,
-                                   width, rws, workspace_bytes - rb, stream, true);
+  FR_CUDA(record(0));
+  if (int rc = render_depth_forward_impl(planar, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height, width,
+                                         mesh, rws, vb, stream))
+    return rc;
+  FR_CUDA(record(1));
+  return FR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ session
@@ -431,6 +582,7 @@ struct fr_session {
   int device, nver, ntri, ks, ke, height, width, max_batch;
   unsigned flags;
   float *packed, *tri, *depth_grad, *vgrad, *pgrad;
+  fr_mesh_table* mesh;
   size_t ws_bytes;
   fr_slot slot[FR_SESSION_SLOTS];
 };
@@ -449,6 +601,7 @@ static void session_free(fr_session* s) {
   float* bufs[] = {s->packed, s->tri, s->depth_grad, s->vgrad, s->pgrad};
   for (float* p : bufs)
     if (p) cudaFree(p);
+  fr_mesh_table_destroy(s->mesh);
   delete s;
 }
 
@@ -473,8 +626,15 @@ int fr_session_create(const float* mu, const float* pc_shape, const float* pc_ex
     if (e != cudaSuccess && rc == FR_OK) rc = fail(FR_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
     return e == cudaSuccess;
   };
-  s->ws_bytes = fr_pipeline_workspace_bytes(max_batch, nver, ndim_shape, ndim_exp, height, width);
-  chk(cudaMalloc(&s->packed, fr_packed_basis_bytes(nver, ndim_shape, ndim_exp)), "cudaMalloc(packed)");
+  // mesh table from the mean shape's geometry (one-off, host side)
+  if (int mrc = fr_mesh_table_create(tri, ntri, nver, mu, (flags & FR_MEAN_INTERLEAVED) ? 1 : 0, device, &s->mesh)) {
+    session_free(s);
+    return mrc;
+  }
+  // the workspace must cover both dispatch classes (small batches run un-fused and need a planar vertex buffer)
+  s->ws_bytes = std::max(fr_pipeline_workspace_bytes(max_batch, nver, ndim_shape, ndim_exp, height, width, s->mesh),
+                         fr_pipeline_workspace_bytes(std::min(max_batch, 8), nver, ndim_shape, ndim_exp, height, width, s->mesh));
+  chk(cudaMalloc(&s->packed, fr_packed_basis_bytes(nver, ndim_shape, ndim_exp, s->mesh)), "cudaMalloc(packed)");
   chk(cudaMalloc(&s->tri, sizeof(float) * 3 * (size_t)ntri), "cudaMalloc(tri)");
   for (fr_slot& sl : s->slot) {
     chk(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -495,7 +655,7 @@ int fr_session_create(const float* mu, const float* pc_shape, const float* pc_ex
     if (ndim_exp) chk(cudaMemcpyAsync(d_pe, pc_exp, sizeof(float) * n3 * ndim_exp, cudaMemcpyHostToDevice, st), "copy pc_exp");
     chk(cudaMemcpyAsync(s->tri, tri, sizeof(float) * 3 * (size_t)ntri, cudaMemcpyHostToDevice, st), "copy tri");
   }
-  if (rc == FR_OK) rc = fr_pack_basis(d_mu, d_ps, d_pe, nver, ndim_shape, ndim_exp, flags, s->packed, st);
+  if (rc == FR_OK) rc = fr_pack_basis(d_mu, d_ps, d_pe, nver, ndim_shape, ndim_exp, flags, s->mesh, s->packed, st);
   if (rc == FR_OK) chk(cudaStreamSynchronize(st), "cudaStreamSynchronize");
   if (d_mu) cudaFree(d_mu);
   if (d_ps) cudaFree(d_ps);
@@ -521,8 +681,9 @@ int fr_session_submit(fr_session* s, int slot, const float* params, int batch, f
   const int d = FR_NDIM_POSE + s->ks + s->ke;
   const size_t npix = (size_t)s->height * s->width;
   FR_CUDA(cudaMemcpyAsync(sl.params, params, sizeof(float) * (size_t)batch * d, cudaMemcpyHostToDevice, sl.stream));
-  if (int rc = fr_recon_render_forward(sl.params, s->packed, s->tri, vertex_proj ? sl.vertex : nullptr, sl.depth, sl.tri_ind, batch, s->nver, s->ntri,
-                                       s->ks, s->ke, s->height, s->width, im_size, s->flags, sl.ws, s->ws_bytes, sl.stream))
+  if (int rc = fr_recon_render_forward(sl.params, s->packed, s->tri, s->mesh, vertex_proj ? sl.vertex : nullptr, sl.depth, sl.tri_ind, batch,
+                                       s->nver, s->ntri, s->ks, s->ke, s->height, s->width, im_size, s->flags, sl.ws, s->ws_bytes, sl.stream,
+                                       nullptr))
     return rc;
   FR_CUDA(cudaMemcpyAsync(depth, sl.depth, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, sl.stream));
   if (tri_ind) FR_CUDA(cudaMemcpyAsync(tri_ind, sl.tri_ind, sizeof(float) * batch * npix, cudaMemcpyDeviceToHost, sl.stream));

@@ -60,31 +60,33 @@ constexpr int kTileVerts = 128;  // vertices per tile == TMEM lanes == threads o
 struct BasisGeom {
   int nver, ks, ke;
   int kreal;   // ks + ke + 1 (the extra column is the mean, coefficient 1)
-  int kpad;    // kreal rounded up to 8 (fp32 section: float4 groups, one tf32 MMA K step)
+  int kpad;    // kreal rounded up to 8 (fp32 section: float4 groups)
   int kg;      // kpad / 4 float4 groups
-  int kpad16;  // kreal rounded up to 16 (fp16-pair section: one f16 MMA K step per chunk)
+  int kpad16;  // kreal rounded up to 16 (fp16-pair sections: one f16 MMA K step per chunk)
   int nch16;   // kpad16 / 16 chunks per (tile, coordinate) row
-  int ntiles;  // ceil(nver / 128)
-  // The packed basis has three sections (DESIGN.md "Packed basis"):
-  //   [0, f32_bytes)                  fp32, float4-tiled: SIMT forward (small batches) and the backward pass
-  //   [f16_offset, +f16_bytes)        fp16 hi/lo pairs of the column-scaled basis in tcgen05 operand tiles: tensor-core forward
+  int ntiles;  // ceil(nver / 128): tiles of consecutive vertices (fp32 section, backward section, mean)
+  int nclusters;  // row tiles of the tensor-core forward section: the mesh table's clusters (mesh_table.h), or ntiles
+                  // tiles of consecutive vertices when the basis is packed without a mesh table
+  // Sections of the packed basis (DESIGN.md "Packed basis"), in this order; only the last one depends on the mesh table:
+  //   [0, f32_bytes)                  fp32, float4-tiled: SIMT forward (small batches) and SIMT backward
   //   [scale_offset, +4 kpad16)       2^-s_k per column (what a coefficient is multiplied by to undo the column scale)
+  //   [bwd_offset, +bwd_bytes)        fp16 hi/lo pairs of the column-scaled basis, transposed for the backward contraction over
+  //                                   the vertices: per (tile, coordinate, 16-vertex chunk)  [hi m0 | hi m1 | lo m0 | lo m1]  with 128 k rows each
+  //   [mean_offset, +mean_bytes)      the mean once more as plain fp32 [3][ntiles*128] (the backward contracts it in fp32)
+  //   [f16_offset, +f16_bytes)        fp16 hi/lo pairs in tcgen05 operand tiles, one 128-row tile per cluster: tensor-core forward
   size_t tile_floats() const { return (size_t)3 * kg * kTileVerts * 4; }
   size_t f32_bytes() const { return (size_t)ntiles * tile_floats() * sizeof(float); }
-  size_t f16_offset() const { return (f32_bytes() + 1023) / 1024 * 1024; }
-  size_t f16_bytes() const { return (size_t)ntiles * 3 * nch16 * 8192; }
-  size_t scale_offset() const { return f16_offset() + f16_bytes(); }
-  //   [bwd_offset, +bwd_bytes)        the same fp16 hi/lo pairs once more, transposed for the backward contraction over the
-  //                                   vertices: per (tile, coordinate, 16-vertex chunk)  [hi m0 | hi m1 | lo m0 | lo m1]  with 128 k rows each
+  size_t scale_offset() const { return (f32_bytes() + 1023) / 1024 * 1024; }
   int mtiles() const { return (kpad16 + 127) / 128; }
   size_t bwd_offset() const { return scale_offset() + ((size_t)kpad16 * sizeof(float) + 1023) / 1024 * 1024; }
   size_t bwd_bytes() const { return (size_t)ntiles * 3 * (kTileVerts / 16) * 2 * mtiles() * 4096; }
-  //   [mean_offset, +mean_bytes)      the mean once more as plain fp32 [3][ntiles*128] (the backward contracts it in fp32)
   size_t mean_offset() const { return bwd_offset() + bwd_bytes(); }
   size_t mean_bytes() const { return (size_t)3 * ntiles * kTileVerts * sizeof(float); }
-  size_t bytes() const { return mean_offset() + mean_bytes(); }
+  size_t f16_offset() const { return (mean_offset() + mean_bytes() + 1023) / 1024 * 1024; }
+  size_t f16_bytes() const { return (size_t)nclusters * 3 * nch16 * 8192; }
+  size_t bytes() const { return f16_offset() + f16_bytes(); }
 };
-inline BasisGeom basis_geom(int nver, int ks, int ke) {
+inline BasisGeom basis_geom(int nver, int ks, int ke, int nclusters = 0) {
   BasisGeom g;
   g.nver = nver;
   g.ks = ks;
@@ -95,6 +97,7 @@ inline BasisGeom basis_geom(int nver, int ks, int ke) {
   g.kpad16 = (g.kreal + 15) / 16 * 16;
   g.nch16 = g.kpad16 / 16;
   g.ntiles = (nver + kTileVerts - 1) / kTileVerts;
+  g.nclusters = nclusters > 0 ? nclusters : g.ntiles;
   return g;
 }
 

@@ -183,8 +183,8 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
 }
 
 // kResolvePerThread pixels per thread (keys loaded up front, coalesced).  Depth and triangle index are decoded straight
-// from the key (a pure streaming pass); the vertex gathers only happen when normals / texture are requested or the
-// decoded depth is a signed-zero tie.
+// from the key (a pure streaming pass that never touches the vertices); the vertex gathers only happen when normals /
+// texture are requested.
 constexpr int kResolvePerThread = 4;
 // Extra outputs of FaceRecNet.rendering_layer (nets/network.py:184-199) when the post-processing is fused into the resolve
 // pass (fr_rendering_layer_forward): `texture_image` then receives pncc = clip(tex, 1e-6, 1), `normal` the normals flipped to
@@ -227,26 +227,22 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
     if (key != 0ull) {
       const int t = fr_key_triangle(key);
       ti = (float)t;
-      bool ambiguous;
-      d = fr_key_depth(key, &ambiguous);
-      if (kAttributes || ambiguous) {
+      d = fr_key_depth(key);           // exact bits of the winner's depth, including the sign of a zero (raster_core.h)
+      if (kAttributes) {               // the winner's vertices are only needed for normals / texture
         const int p1 = (int)__ldg(tri + t), p2 = (int)__ldg(tri + ntri + t), p3 = (int)__ldg(tri + 2 * (size_t)ntri + t);
-        const float* vx = vertex + (size_t)b * 3 * nver;
-        const float* vy = vx + nver;
-        const float* vz = vy + nver;
-        const float z1 = __ldg(vz + p1), z2 = __ldg(vz + p2), z3 = __ldg(vz + p3);
-        d = fr_tri_depth(z1, z2, z3);  // exact bits of the winner's depth (keeps a -0.0 the key folded away)
-        if (kAttributes) {
-          if (normal != nullptr)
-            fr_tri_normal(__ldg(vx + p1), __ldg(vy + p1), z1, __ldg(vx + p2), __ldg(vy + p2), z2, __ldg(vx + p3),
-                          __ldg(vy + p3), z3, n);
-          if (texture_image != nullptr) {
-            const float* tex = texture + (size_t)b * texture_batch_stride;
+        if (normal != nullptr) {
+          const float* vx = vertex + (size_t)b * 3 * nver;
+          const float* vy = vx + nver;
+          const float* vz = vy + nver;
+          fr_tri_normal(__ldg(vx + p1), __ldg(vy + p1), __ldg(vz + p1), __ldg(vx + p2), __ldg(vy + p2), __ldg(vz + p2),
+                        __ldg(vx + p3), __ldg(vy + p3), __ldg(vz + p3), n);
+        }
+        if (texture_image != nullptr) {
+          const float* tex = texture + (size_t)b * texture_batch_stride;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-              tx[c] = fr_tri_mean(__ldg(tex + (size_t)c * nver + p1), __ldg(tex + (size_t)c * nver + p2),
-                                  __ldg(tex + (size_t)c * nver + p3));
-          }
+          for (int c = 0; c < 3; ++c)
+            tx[c] = fr_tri_mean(__ldg(tex + (size_t)c * nver + p1), __ldg(tex + (size_t)c * nver + p2),
+                                __ldg(tex + (size_t)c * nver + p3));
         }
       }
     }

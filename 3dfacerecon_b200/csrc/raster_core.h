@@ -144,9 +144,11 @@ FR_HD void fr_tri_normal(float x1, float y1, float z1, float x2, float y2, float
 // The reference visits triangles in index order and overwrites a pixel iff depth < h (:295), so the
 // winner is (max h, then min index).  Packed as one u64 so a single atomicMax resolves it in any order:
 //   high 32 bits: order-preserving map of the float depth (with -0.0 folded onto +0.0, which compare equal)
-//   low  32 bits: 0xFFFFFFFF - triangle index (smaller index = larger key)
-// 0 is reserved for "background": a triangle only draws when h > background depth (NaN never draws),
-// and every such h maps to a non-zero high word.
+//   low  32 bits: (0x7FFFFFFF - triangle index) << 1 | (h is -0.0)       smaller index = larger key
+// The last bit keeps the sign of a zero depth, which the folded high word cannot (it never decides a comparison:
+// two keys with equal high words and equal index are the same triangle), so depth AND index decode from the
+// key alone.  0 is reserved for "background": a triangle only draws when h > background depth (NaN never
+// draws), and every such h maps to a non-zero high word.
 FR_HD uint32_t fr_float_order_bits(float h) {
   union { float f; uint32_t u; } c;
   c.f = h;
@@ -161,18 +163,20 @@ FR_HD bool fr_depth_draws(float h) {
 }
 
 FR_HD unsigned long long fr_pack_key(float h, int tri_index) {
-  return ((unsigned long long)fr_float_order_bits(h) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)tri_index);
+  union { float f; uint32_t u; } c;
+  c.f = h;
+  const uint32_t low = ((0x7FFFFFFFu - (uint32_t)tri_index) << 1) | ((c.u == 0x80000000u) ? 1u : 0u);
+  return ((unsigned long long)fr_float_order_bits(h) << 32) | (unsigned long long)low;
 }
 
-FR_HD int fr_key_triangle(unsigned long long key) { return (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)); }
+FR_HD int fr_key_triangle(unsigned long long key) { return (int)(0x7FFFFFFFu - ((uint32_t)(key & 0xFFFFFFFFull) >> 1)); }
 
-// Depth stored in a (non-zero) key.  The map is invertible except that -0.0 was folded onto +0.0: when the result
-// is +0.0 the caller must recompute the winner's depth from its vertices to recover the sign (*ambiguous = true).
-FR_HD float fr_key_depth(unsigned long long key, bool* ambiguous) {
+// Depth stored in a (non-zero) key, bit for bit (including the sign of a zero).
+FR_HD float fr_key_depth(unsigned long long key) {
   const uint32_t o = (uint32_t)(key >> 32);
   union { uint32_t u; float f; } c;
   c.u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-  *ambiguous = (c.u == 0u);
+  if (c.u == 0u && (key & 1ull)) c.u = 0x80000000u;
   return c.f;
 }
 

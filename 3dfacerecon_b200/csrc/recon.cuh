@@ -142,35 +142,36 @@ recon_prep_kernel(const float* __restrict__ params, int dparam, int batch, int b
   }
 }
 
-// Where the forward kernels put a projected vertex.  `planar` is the reference's vertex_proj [B,3,N] tensor
-// (nets/network.py:171); `rec` is the rasterizer's 16-byte vertex record array [B][N] {x, y, z, snap code}
-// (raster.cuh): the fused params -> depth-map call has the reconstruction epilogue write the records directly, which
-// saves the rasterizer's repack pass over the vertex tensor.  Either may be null.
+// Where the forward kernels put a projected vertex: `planar` is the reference's vertex_proj [B,3,N] tensor
+// (nets/network.py:171).  (The fused params -> depth-map call needs no such tensor: the tensor-core kernel hands the
+// vertices to its own rasterizer stage in shared memory, recon_f16.cuh.)
 struct ReconOut {
   float* planar;
-  float4* rec;
-  int width, height;   // image size the snap codes refer to (rec != nullptr)
-  unsigned long long* keys;   // fused call: the rasterizer's visibility keys [B][height*width], to be cleared before it runs
 };
 
 // Projection + y flip of one reconstructed vertex (nets/network.py:163-169).
+__device__ __forceinline__ void project_vertex(const float* __restrict__ P, float x, float y, float z, float im_size,
+                                               unsigned flags, float* X, float* Y, float* Z) {
+  *X = fmaf(P[2], z, fmaf(P[1], y, P[0] * x)) + P[9];
+  float yy = fmaf(P[5], z, fmaf(P[4], y, P[3] * x)) + P[10];
+  *Z = fmaf(P[8], z, fmaf(P[7], y, P[6] * x)) + P[11];
+  if (!(flags & FR_YFLIP_NONE)) {
+    yy = __fsub_rn(im_size, yy);                        // S - y
+    if (!(flags & FR_YFLIP_S_Y)) yy = __fsub_rn(yy, 1.0f);  // ... - 1
+  }
+  *Y = yy;
+}
+__device__ __forceinline__ void store_planar(float* __restrict__ planar, int b, int nver, int n, float X, float Y, float Z) {
+  float* o = planar + (size_t)b * 3 * nver;
+  o[n] = X;
+  o[(size_t)nver + n] = Y;
+  o[2 * (size_t)nver + n] = Z;
+}
 __device__ __forceinline__ void project_store(const float* __restrict__ P, float x, float y, float z, float im_size,
                                               unsigned flags, const ReconOut& out, int b, int nver, int n) {
-  const float X = fmaf(P[2], z, fmaf(P[1], y, P[0] * x)) + P[9];
-  float Y = fmaf(P[5], z, fmaf(P[4], y, P[3] * x)) + P[10];
-  const float Z = fmaf(P[8], z, fmaf(P[7], y, P[6] * x)) + P[11];
-  if (!(flags & FR_YFLIP_NONE)) {
-    Y = __fsub_rn(im_size, Y);                        // S - y
-    if (!(flags & FR_YFLIP_S_Y)) Y = __fsub_rn(Y, 1.0f);  // ... - 1
-  }
-  if (out.planar != nullptr) {
-    float* o = out.planar + (size_t)b * 3 * nver;
-    o[n] = X;
-    o[(size_t)nver + n] = Y;
-    o[2 * (size_t)nver + n] = Z;
-  }
-  if (out.rec != nullptr)
-    out.rec[(size_t)b * nver + n] = make_float4(X, Y, Z, __uint_as_float(fr_snap_code(X, Y, out.width, out.height)));
+  float X, Y, Z;
+  project_vertex(P, x, y, z, im_size, flags, &X, &Y, &Z);
+  store_planar(out.planar, b, nver, n, X, Y, Z);
 }
 
 // ---------------------------------------------------------------------------------------------- forward (SIMT)

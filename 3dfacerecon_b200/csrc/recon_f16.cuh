@@ -6,16 +6,20 @@
 //              ~= 2^-t_b * sum_k (Phi + Plo)[(c,n), k] * (b0 + b1)[b, k]          (dropping Plo*b1, 2^-22 relative)
 //   P 2^s_k = Phi + Plo (fp16 each),  coef 2^-s_k 2^t_b = b0 + b1 (fp16 each),  products accumulated in fp32 (TMEM)
 //
-// Per CTA (persistent, one per SM, 10 warps):
-//   warp 8   producer    cp.async.bulk (TMA engine): the two resident coefficient operands of this 64-face batch tile
+// Per CTA (persistent, one per SM):
+//   producer    1 warp   cp.async.bulk (TMA engine): the two resident coefficient operands of this 64-face batch tile
 //                        once, then 24 KB stages (3 chunks of 16 k: hi tile + lo tile each) of the basis into a
 //                        shared-memory ring -- a tile's 3 coordinate rows are one contiguous run of the packed file
-//   warp 9   MMA issuer  whole warp converged, one elected lane: per chunk  D += Phi.b0 + Plo.b0 + Phi.b1
+//   MMA issuer  1 warp   whole warp converged, one elected lane: per chunk  D += Phi.b0 + Plo.b0 + Phi.b1
 //                        (tcgen05.mma kind::f16, M128 N64 K16, BOTH operands from shared memory); a tcgen05.commit per
 //                        stage hands the shared-memory stage back to the producer when its MMAs have retired
-//   warps 0-7 epilogue   tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices), (2^-t f.R).v + t,
-//                        y flip, coalesced stores (planar vertex_proj and / or rasterizer records); double-buffered
-//                        against the next tile's MMAs
+//   epilogue    8 / 16 warps: tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices),
+//                        (2^-t f.R).v + t, y flip; double-buffered against the next tile's MMAs.  Two flavours:
+//       planar  (8 warps)   coalesced stores of vertex_proj [B,3,N]                  (fr_recon_project_forward)
+//       raster  (16 warps)  the row tile is a CLUSTER of the mesh table (mesh_table.h): the projected vertices go
+//                           to a shared-memory stage and the same warps rasterize the cluster's triangles from there
+//                           (raster_cluster.cuh) while the tensor pipe works on the next cluster -- the vertices of the
+//                           fused params -> depth-map call never touch global memory   (fr_recon_render_forward)
 // Measured on B200 (tools/mma_bench3.cu): an SS-form M128 N64 MMA takes 48 cycles (operand reads at 128 B/clk), K8 tf32
 // and K16 f16 alike, so a 16-k chunk costs 144 tensor cycles here against 192 for the 3xTF32 TS-form kernel
 // (tools/experiments/recon_tc_3xtf32.cuh) -- and that kernel also needs 8 converter warps and a TMEM operand ring only 4 chunks deep.
@@ -24,6 +28,7 @@
 
 #include <cuda_fp16.h>
 
+#include "raster_cluster.cuh"
 #include "recon.cuh"
 #include "tcgen05_common.cuh"
 
@@ -52,21 +57,30 @@ constexpr uint32_t kHalfBytes = kTileVerts * kChunkK * 2;   // one operand tile 
 constexpr uint32_t kChunkBytes = 2 * kHalfBytes;            // hi tile + lo tile
 constexpr int kStageChunks = 3;        // chunks per bulk copy: a tile has 3 * nch16 chunks, always a multiple of 3
 constexpr uint32_t kStageBytes = kStageChunks * kChunkBytes;
-constexpr int kStages = 4;             // 96 KB of basis in flight per SM
+constexpr int kMaxStages = 4;          // ring depth of the planar flavour: 96 KB of basis in flight per SM
 constexpr int kDBufs = 2;
 constexpr int kDCols = 3 * kN;
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8, kProducerWarp = 8, kMmaWarp = 9;
-constexpr int kThreads = (kMmaWarp + 1) * 32;
 constexpr int kPose16Stride = 16;      // floats per face: 2^-t f.R [9] | t [3] | pad
+
+// Flavour of the forward kernel (see the header comment).
+template <bool kRaster>
+struct Cfg {
+  static constexpr int kEpiWarps = kRaster ? 16 : 8;
+  static constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+  static constexpr int kThreads = (kEpiWarps + 2) * 32;
+  static constexpr int kStages = kRaster ? 3 : kMaxStages;     // the raster flavour needs 77 KB for its stage and queues
+  static constexpr int kStageFaces = 32;                         // faces per rasterizer stage
+  static constexpr int kFacesPerWarp = kRaster ? kStageFaces / (kEpiWarps / 4) : 16;   // faces a warp drains per step
+};
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 at [4,6), a = b = F16 (0) at [7,10) / [10,13), K-major
 // A and B, n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((128u >> 4) << 24);
 
 struct Barriers {
-  uint64_t raw_full[kStages];
-  uint64_t raw_empty[kStages];
+  uint64_t raw_full[kMaxStages];
+  uint64_t raw_empty[kMaxStages];
   uint64_t d_full[kDBufs];
   uint64_t d_empty[kDBufs];
   uint64_t b_full;
@@ -74,10 +88,17 @@ struct Barriers {
   uint32_t pad;
 };
 
+struct RasterSmem {                    // raster flavour only
+  rc::Stage<Cfg<true>::kStageFaces> stage;
+  rc::TriList tris;
+  rc::WarpQueue queue[Cfg<true>::kEpiWarps];
+};
+
 struct SmemLayout {
-  uint32_t b0, b1, raw, pose, bars, total;
+  uint32_t b0, b1, raw, pose, bars, raster, total;
   uint32_t sbo;  // bytes between 8-face groups of a coefficient operand
 };
+template <bool kRaster>
 __host__ __device__ inline SmemLayout smem_layout(int nch16) {
   SmemLayout L;
   L.sbo = (uint32_t)nch16 * 2u * 128u;            // 2 core matrices (8 faces x 8 k fp16 = 128 B) per chunk
@@ -85,9 +106,10 @@ __host__ __device__ inline SmemLayout smem_layout(int nch16) {
   L.b0 = 0;
   L.b1 = bsz;
   L.raw = (2 * bsz + 1023u) / 1024u * 1024u;
-  L.pose = L.raw + kStages * kStageBytes;
+  L.pose = L.raw + Cfg<kRaster>::kStages * kStageBytes;
   L.bars = L.pose + kN * kPose16Stride * 4;
-  L.total = L.bars + (uint32_t)sizeof(Barriers);
+  L.raster = (L.bars + (uint32_t)sizeof(Barriers) + 15u) / 16u * 16u;
+  L.total = L.raster + (kRaster ? (uint32_t)sizeof(RasterSmem) : 0u);
   return L;
 }
 
@@ -136,13 +158,13 @@ __global__ void basis_colscale_kernel(float* __restrict__ scale, int kreal, int 
   scale[k] = inv;
 }
 
-// fp16 operand tiles: for every (tile, coordinate) row, nch16 chunks of [hi tile | lo tile]; a tile is the canonical
+// fp16 operand tiles: for every (tile = cluster, coordinate) row, nch16 chunks of [hi tile | lo tile]; a tile is the canonical
 // K-major no-swizzle layout of a 128 x 16 fp16 operand: [k / 8][row][k % 8], i.e. 8-row x 16-byte core matrices, 128 B
 // between 8-row groups (SBO) and 2048 B between the two K halves (LBO).  One thread writes one 16-byte row piece.
 __global__ void __launch_bounds__(256)
 pack_basis_f16_kernel(const float* __restrict__ mu, const float* __restrict__ pc_shape, const float* __restrict__ pc_exp,
                       const float* __restrict__ inv_scale, int nver, int ks, int ke, int nch16, int ntiles, unsigned flags,
-                      uint4* __restrict__ tiles) {
+                      const int32_t* __restrict__ cluster_vert, uint4* __restrict__ tiles) {
   const size_t total = (size_t)ntiles * 3 * nch16 * 2 * kTileVerts;      // (tile, c, chunk, k half, row)
   const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
@@ -151,7 +173,12 @@ pack_basis_f16_kernel(const float* __restrict__ mu, const float* __restrict__ pc
   const int ci = (int)((idx / (2 * kTileVerts)) % nch16);
   const int c = (int)((idx / ((size_t)2 * kTileVerts * nch16)) % 3);
   const int tile = (int)(idx / ((size_t)2 * kTileVerts * nch16 * 3));
-  const int n = tile * kTileVerts + v;
+  // row v of tile `tile`: the cluster's vertex in slot v (mesh_table.h), or the tile's v-th consecutive vertex
+  int n = tile * kTileVerts + v;
+  if (cluster_vert != nullptr) {
+    const int32_t raw = cluster_vert[(size_t)tile * kTileVerts + v];
+    n = raw < 0 ? nver : (int)((uint32_t)raw & kVertIdMask);
+  }
   __half hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -184,13 +211,25 @@ pack_basis_f16_kernel(const float* __restrict__ mu, const float* __restrict__ pc
 __global__ void __launch_bounds__(256)
 recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict__ inv_scale, int dparam, int batch, int ks,
                       int ke, int kpad16, unsigned flags, float im_size, unsigned char* __restrict__ bsplit,
-                      float* __restrict__ pose16) {
+                      float* __restrict__ pose16, unsigned long long* __restrict__ keys, int npix) {
   __shared__ float red[8];
   __shared__ float s_pose[kPoseStride];
   __shared__ double s_sc[6];
   pdl_trigger();                                   // the reconstruction kernel may become resident (it waits before reading our output)
   const int b = blockIdx.x, tid = threadIdx.x;
   const bool live = b < batch;
+  // fused call: this CTA also clears the visibility keys of its face for the rasterizer stage of the next kernel
+  // (which waits for this grid before its first atomicMax)
+  if (keys != nullptr && live) {
+    unsigned long long* kb = keys + (size_t)b * npix;
+    int i = tid;
+    if ((npix & 1) == 0) {        // 16-byte stores (a face's keys are 16-byte aligned when npix is even)
+      uint4* kv = reinterpret_cast<uint4*>(kb);
+      for (; i < npix / 2; i += 256) kv[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (; i < npix; i += 256) kb[i] = 0ull;
+    }
+  }
   float cmax = 0.0f;
   for (int k = tid; k < kpad16; k += 256) {
     float v = 0.0f;
@@ -252,12 +291,48 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(kThreads, 1)
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// What the raster flavour draws into (fused params -> depth-map call).
+struct RasterTarget {
+  const unsigned char* table;        // mesh table blob (device)
+  unsigned long long* keys;          // visibility keys [B][height*width], cleared by the prep kernel
+  int width, height;
+};
+
+// tiles: fp16 operand tiles in cluster order; cluster_vert: [nclusters][128] vertex ids (null = consecutive tiles).
+template <bool kRaster>
+__global__ void __launch_bounds__(Cfg<kRaster>::kThreads, 1)
 recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned char* __restrict__ bsplit,
-                     const float* __restrict__ pose16, ReconOut out, int batch, int nver, int nch16, int ntiles,
-                     float im_size, unsigned flags, int key_vec_per_face) {
+                     const float* __restrict__ pose16, const int32_t* __restrict__ cluster_vert, ReconOut out,
+                     RasterTarget target, int batch, int nver, int nch16, int nclusters, float im_size, unsigned flags) {
+  using C = Cfg<kRaster>;
+  constexpr int kStages = C::kStages, kEpiWarps = C::kEpiWarps, kProducerWarp = C::kProducerWarp, kMmaWarp = C::kMmaWarp;
   extern __shared__ __align__(1024) unsigned char smem[];
-  const SmemLayout L = smem_layout(nch16);
+  const SmemLayout L = smem_layout<kRaster>(nch16);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + L.bars);
   float* s_pose = reinterpret_cast<float*>(smem + L.pose);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -283,10 +358,10 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  pdl_trigger();                                   // the rasterizer's blocks may become resident (they wait before reading records / keys)
-  // No pdl_wait() here: only the coefficient operands and the poses come from the prep kernel.  The basis stream, the key
-  // clearing, the TMEM allocation start at once and overlap the prep kernel; the producer waits before it loads the
-  // coefficient operands, the epilogue warps before they read the poses.
+  pdl_trigger();                                   // the next kernel's blocks may become resident (they wait before reading our output)
+  // No pdl_wait() here: only the coefficient operands, the poses and the cleared keys come from the prep kernel.  The
+  // basis stream and the TMEM allocation start at once and overlap the prep kernel; the producer waits before it loads
+  // the coefficient operands, the epilogue warps before they read the poses / touch the keys.
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -308,7 +383,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
 #if FR_BASIS_EVICT_FIRST
       const uint64_t stream_policy = tc::l2_evict_first_policy();
 #endif
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < nclusters; tile += gridDim.x) {
         const unsigned char* src = tiles + (size_t)tile * tile_bytes;
         for (int sg = 0; sg < nch16; ++sg, ++it) {             // nch16 stages of 3 chunks per tile
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
@@ -332,7 +407,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     const uint64_t db1 = tc::make_smem_desc(smem_u32(smem + L.b1), 128u, L.sbo);
     const uint64_t da0 = tc::make_smem_desc(smem_u32(smem + L.raw), 2048u, 128u);   // same descriptor format for A
     uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int tile = blockIdx.x; tile < nclusters; tile += gridDim.x, ++tcount) {
       const uint32_t dbuf = tcount % kDBufs;
       mbar_wait(&bars->d_empty[dbuf], ((tcount / kDBufs) & 1u) ^ 1u);          // epilogue has drained this accumulator set
       tc_fence_after();
@@ -367,52 +442,79 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       }
     }
   } else {
-    // ================================================================== epilogue (warps 0..7)
-    const int qd = warp & 3;                                      // TMEM lane quarter == warp % 4
-    const int jb0 = (warp >> 2) * (kN / (kEpiWarps / 4)), jb1 = jb0 + kN / (kEpiWarps / 4);   // this warp's faces
-    const int v = qd * 32 + lane;
+    // ================================================================== epilogue (warps 0 .. kEpiWarps-1)
+    constexpr int kFPW = C::kFacesPerWarp;                        // faces this warp drains per step
+    constexpr int kStepFaces = kFPW * (kEpiWarps / 4);            // faces all epilogue warps drain per step (raster: one stage)
+    const int qd = warp & 3, wq = warp >> 2;                      // TMEM lane quarter == warp % 4; face group within a step
+    const int v = qd * 32 + lane;                                 // row of the tile == vertex slot of the cluster
     const uint32_t lane_field = (uint32_t)(qd * 32) << 16;
-    // fused call: while the first tile's MMAs run these warps have nothing to drain -- clear this batch tile's visibility keys
-    // for the rasterizer that follows (16-byte vectors; the CTAs of the batch tile share the range)
-    if (key_vec_per_face > 0) {
-      uint4* kv = reinterpret_cast<uint4*>(out.keys) + (size_t)b0 * key_vec_per_face;
-      const size_t nvec = (size_t)min(kN, batch - b0) * key_vec_per_face;
-      for (size_t i = (size_t)blockIdx.x * (kEpiWarps * 32) + threadIdx.x; i < nvec; i += (size_t)gridDim.x * (kEpiWarps * 32))
-        kv[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    pdl_wait();                                                   // the prep kernel's poses
+    const int nfaces_tile = min(kN, batch - b0);                  // live faces of this batch tile (>= 1)
+    const int nsteps = (nfaces_tile + kStepFaces - 1) / kStepFaces;
+    RasterSmem* rs = reinterpret_cast<RasterSmem*>(smem + L.raster);
+    rc::TableView tv = {nullptr, nullptr, nullptr, 0};
+    if (kRaster) tv = rc::table_view(target.table);
+    const int npix = target.width * target.height;
+    pdl_wait();                                                   // the prep kernel's poses (and the cleared keys)
     for (int i = threadIdx.x; i < kN * kPose16Stride; i += kEpiWarps * 32) s_pose[i] = pose16[(size_t)b0 * kPose16Stride + i];
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // the epilogue warps only (threads 0 .. 255)
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // the epilogue warps only
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int tile = blockIdx.x; tile < nclusters; tile += gridDim.x, ++tcount) {
       const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
-      const int n = tile * kTileVerts + v;
+      // vertex of this row, and whether this cluster is the one that writes it to the planar tensor
+      int n = tile * kTileVerts + v;
+      bool owner = n < nver;
+      if (cluster_vert != nullptr) {
+        const int32_t raw = __ldg(cluster_vert + (size_t)tile * kTileVerts + v);
+        n = (int)((uint32_t)raw & kVertIdMask);
+        owner = raw >= 0 && ((uint32_t)raw & kVertOwner) != 0u;
+      }
+      const bool store = out.planar != nullptr && owner;
+      int ntri_c = 0;
+      if (kRaster) {                                              // the cluster's triangle list (the previous tile's last
+        const int tb = __ldg(tv.tri_begin + tile);                // barrier has released tris and stage)
+        ntri_c = __ldg(tv.tri_begin + tile + 1) - tb;
+        rc::load_tri_list(rs->tris, tv.tri_entry + tb, ntri_c, threadIdx.x, kEpiWarps * 32);
+      }
       mbar_wait(&bars->d_full[dbuf], dph);
       tc_fence_after();
       const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
 #pragma unroll 1
-      for (int jb = jb0; jb < jb1; jb += 16) {
-        float x[16], y[16], z[16];
-        tmem_ld16(d_addr + 0 * kN + jb, x);
-        tmem_ld16(d_addr + 1 * kN + jb, y);
-        tmem_ld16(d_addr + 2 * kN + jb, z);
+      for (int step = 0; step < nsteps; ++step) {
+        const int jb = step * kStepFaces + wq * kFPW;             // first face (within the batch tile) of this warp
+        float x[kFPW], y[kFPW], z[kFPW];
+        tmem_ld<kFPW>(d_addr + 0 * kN + jb, x);
+        tmem_ld<kFPW>(d_addr + 1 * kN + jb, y);
+        tmem_ld<kFPW>(d_addr + 2 * kN + jb, z);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (n < nver) {
+        if (step == nsteps - 1) {                                 // accumulators drained: the tensor pipe may reuse them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+        }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int b = b0 + jb + j;
-            if (b < batch) {
-              const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPose16Stride);
-              const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
-              const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
-              project_store(P, x[j], y[j], z[j], im_size, flags, out, b, nver, n);
-            }
+        for (int j = 0; j < kFPW; ++j) {
+          const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPose16Stride);
+          const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+          const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+          float X, Y, Z;
+          project_vertex(P, x[j], y[j], z[j], im_size, flags, &X, &Y, &Z);
+          if (store && b0 + jb + j < batch) store_planar(out.planar, b0 + jb + j, nver, n, X, Y, Z);
+          if (kRaster) {
+            const int fl = wq * kFPW + j;                         // face of the stage
+            rs->stage.x[fl][v] = X;
+            rs->stage.y[fl][v] = Y;
+            rs->stage.z[fl][v] = Z;
+            rs->stage.code[fl][v] = fr_snap_code(X, Y, target.width, target.height);
           }
         }
+        if (kRaster) {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // stage (and triangle list) complete
+          const int fb = b0 + step * kStepFaces;                                // first face of the stage
+          rc::raster_stage(rs->stage, rs->tris, rs->queue[warp], ntri_c, min(kStepFaces, batch - fb), warp, kEpiWarps, lane,
+                           target.keys + (size_t)fb * npix, npix, target.width, target.height);
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // stage free again
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
     }
   }
 
@@ -433,30 +535,43 @@ inline size_t recon_f16_bsplit_bytes(int batch, const BasisGeom& g) {
 }
 inline size_t recon_f16_pose_bytes(int batch) { return sizeof(float) * (size_t)batch_padded(batch) * f16::kPose16Stride; }
 
-inline bool recon_f16_fits(const BasisGeom& g) { return f16::smem_layout(g.nch16).total <= 227u * 1024u; }
+inline bool recon_f16_fits(const BasisGeom& g, bool raster) {
+  return (raster ? f16::smem_layout<true>(g.nch16).total : f16::smem_layout<false>(g.nch16).total) <= 227u * 1024u;
+}
 
-// keys / key_vec_per_face: when the visibility keys of the fused call can be cleared by the kernel's idle epilogue warps
-// (16-byte vectors per face), else nullptr / 0.
-inline int launch_recon_fwd_f16(const float* params, const float* packed, void* bsplit, float* pose16, ReconOut out, int batch,
-                                int nver, const BasisGeom& g, float im_size, unsigned flags, int nsm, cudaStream_t st,
-                                void* keys, int key_vec_per_face) {
+// Prep + tensor-core forward.  target == nullptr: the planar flavour (out.planar required); else the raster flavour
+// (fused call: the prep kernel clears the visibility keys, the epilogue rasterizes; out.planar optional).
+// cluster_vert: device pointer to the mesh table's vertex lists the basis was packed with, or null (consecutive tiles).
+inline int launch_recon_fwd_f16(const float* params, const float* packed, void* bsplit, float* pose16, ReconOut out,
+                                const f16::RasterTarget* target, const int32_t* cluster_vert, int batch, int nver,
+                                const BasisGeom& g, float im_size, unsigned flags, int nsm, cudaStream_t st) {
   static_assert(f16::kN == kBatchPad, "batch tiles are kBatchPad faces");
   const unsigned char* base = reinterpret_cast<const unsigned char*>(packed);
   const float* inv_scale = reinterpret_cast<const float*>(base + g.scale_offset());
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + g.ks + g.ke;
   f16::recon_prep_f16_kernel<<<bpad, 256, 0, st>>>(params, inv_scale, dparam, batch, g.ks, g.ke, g.kpad16, flags, im_size,
-                                                  static_cast<unsigned char*>(bsplit), pose16);   // normal launch: waits for everything before
+                                                  static_cast<unsigned char*>(bsplit), pose16, target ? target->keys : nullptr,
+                                                  target ? target->width * target->height : 0);   // normal launch: waits for everything before
   FR_LAUNCHED("recon_prep_f16_kernel");
-  const f16::SmemLayout L = f16::smem_layout(g.nch16);
   const int nbt = ceil_div(batch, f16::kN);
   int ctas = nsm / nbt;
   if (ctas < 1) ctas = 1;
-  if (ctas > g.ntiles) ctas = g.ntiles;
-  FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel, dim3(ctas, nbt), dim3(f16::kThreads), L.total, st, pdl_enabled(),
-                     base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), out, batch, nver,
-                     g.nch16, g.ntiles, im_size, flags, keys != nullptr ? key_vec_per_face : 0));
+  if (ctas > g.nclusters) ctas = g.nclusters;
+  const f16::RasterTarget none = {nullptr, nullptr, 0, 0};
+  if (target != nullptr) {
+    const f16::SmemLayout L = f16::smem_layout<true>(g.nch16);
+    FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<true>, dim3(ctas, nbt), dim3(f16::Cfg<true>::kThreads), L.total, st, pdl_enabled(),
+                       base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
+                       out, *target, batch, nver, g.nch16, g.nclusters, im_size, flags));
+  } else {
+    const f16::SmemLayout L = f16::smem_layout<false>(g.nch16);
+    FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<false>, dim3(ctas, nbt), dim3(f16::Cfg<false>::kThreads), L.total, st, pdl_enabled(),
+                       base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
+                       out, none, batch, nver, g.nch16, g.nclusters, im_size, flags));
+  }
   FR_LAUNCHED("recon_fwd_f16_kernel");
   return FR_OK;
 }

@@ -26,7 +26,7 @@ import torch
 from .. import _lib
 from .._lib import check, lib
 from ..model import DeviceModel
-from ..rendering_layer.ops import _workspace, render_depth
+from ..rendering_layer.ops import _mesh_handle, _workspace, render_depth
 
 
 class _ReconProject(torch.autograd.Function):
@@ -48,7 +48,7 @@ class _ReconProject(torch.autograd.Function):
         with torch.cuda.device(dev):
             nbytes = lib().fr_recon_workspace_bytes(B, model.nver, model.ndim_shape, model.ndim_exp)
             ws = _workspace(dev, nbytes)
-            check(lib().fr_recon_project_forward(params.data_ptr(), model.packed.data_ptr(), out.data_ptr(), B, model.nver,
+            check(lib().fr_recon_project_forward(params.data_ptr(), model.packed.data_ptr(), model.mesh.handle, out.data_ptr(), B, model.nver,
                                                  model.ndim_shape, model.ndim_exp, float(im_size), flags, ws.data_ptr(),
                                                  ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         ctx.save_for_backward(params)
@@ -79,12 +79,22 @@ class _RenderingLayer(torch.autograd.Function):
     the reference (the op registers no gradient for texture / normal, ``rendering_layer/ops.py:95``)."""
 
     @staticmethod
-    def forward(ctx, vertex_proj, tri, texture, im_gray, height, width):
+    def forward(ctx, vertex_proj, tri, texture, im_gray, height, width, mesh="auto"):
         if not vertex_proj.is_cuda:
             raise RuntimeError("vertex_proj is on %s: rendering_layer has no CPU path" % vertex_proj.device)
+        if vertex_proj.dim() != 3 or vertex_proj.shape[1] != 3:
+            raise ValueError("The vertex is not Batch x 3 x nver")                # render_depth_op.cc:411
+        if tri.dim() != 2 or tri.shape[0] != 3:
+            raise ValueError("The tri is not 3 x ntri")                           # :414
         ver, tri = vertex_proj.float().contiguous(), tri.float().contiguous()
         B, N, T = int(ver.shape[0]), int(ver.shape[2]), int(tri.shape[1])
         dev = ver.device
+        if texture.dim() not in (2, 3) or texture.shape[-2] != 3 or texture.shape[-1] != N or (texture.dim() == 3 and texture.shape[0] != B):
+            raise ValueError("colors must be [3,N] or [B,3,N] like vertex_proj (got %s)" % (tuple(texture.shape),))
+        if im_gray is not None and tuple(im_gray.shape) != (B, height, width, 1):
+            raise ValueError("im_gray must be [B,%d,%d,1] (got %s)" % (height, width, tuple(im_gray.shape)))
+        if not tri.is_cuda or not texture.is_cuda or (im_gray is not None and not im_gray.is_cuda):
+            raise RuntimeError("rendering_layer has no CPU path: tri, colors and im_gray must be CUDA tensors")
         if texture.dim() == 2 or (texture.stride(0) == 0 and texture[0].is_contiguous()):
             tex = (texture if texture.dim() == 2 else texture[0]).float().contiguous()
             tex_ptr, tex_stride, keep = tex.data_ptr(), 0, tex
@@ -94,12 +104,14 @@ class _RenderingLayer(torch.autograd.Function):
         gray = None if im_gray is None else im_gray.float().contiguous()
         new = lambda c: torch.empty((B, height, width, c), dtype=torch.float32, device=dev)
         pncc, normalimg, maskimg, depthimg, raw, tri_ind = new(3), new(3), new(1), new(1), new(1), new(1)
+        mesh_h = _mesh_handle(tri, N, ver, mesh)
         with torch.cuda.device(dev):
-            ws = _workspace(dev, lib().fr_render_workspace_bytes(B, N, height, width))
+            ws = _workspace(dev, lib().fr_render_workspace_bytes(B, N, height, width, mesh_h))
             check(lib().fr_rendering_layer_forward(ver.data_ptr(), tri.data_ptr(), tex_ptr, tex_stride,
                                                    None if gray is None else gray.data_ptr(), pncc.data_ptr(), normalimg.data_ptr(),
                                                    maskimg.data_ptr(), depthimg.data_ptr(), raw.data_ptr(), tri_ind.data_ptr(), B, N, T,
-                                                   height, width, ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+                                                   height, width, mesh_h, ws.data_ptr(), ws.numel(),
+                                                   torch.cuda.current_stream(dev).cuda_stream))
         del keep
         ctx.save_for_backward(tri, tri_ind, raw, gray if gray is not None else raw.new_empty(0))
         ctx.dims = (B, N, T, height, width)
@@ -115,14 +127,14 @@ class _RenderingLayer(torch.autograd.Function):
         g_depth = None if g_depth is None else g_depth.float().contiguous()
         vertex_grad = torch.empty((B, 3, N), dtype=torch.float32, device=dev)
         if g_mask is None and g_depth is None:
-            return vertex_grad.zero_(), None, None, None, None, None
+            return vertex_grad.zero_(), None, None, None, None, None, None
         with torch.cuda.device(dev):
             check(lib().fr_rendering_layer_backward(None if g_depth is None else g_depth.data_ptr(),
                                                     None if g_mask is None else g_mask.data_ptr(),
                                                     gray.data_ptr() if gray.numel() else None, raw.data_ptr(), tri.data_ptr(),
                                                     tri_ind.data_ptr(), vertex_grad.data_ptr(), B, N, T, H, W,
                                                     torch.cuda.current_stream(dev).cuda_stream))
-        return vertex_grad, None, None, None, None, None
+        return vertex_grad, None, None, None, None, None, None
 
 
 def recon_project(params, model: DeviceModel, im_size=200, flags=None, raw=False):
@@ -142,7 +154,10 @@ class FaceRecNet:
         self.params_label = params_label
         self.nIter = nIter
         self.batch_size = batch_size
-        self.im_size = im_size
+        self.im_size = im_size                  # kept as given (the y flip uses the float value, network.py:168)
+        self._hw = int(im_size)                 # image height == width in pixels
+        if self._hw != im_size or self._hw <= 0:
+            raise ValueError("im_size must be a positive whole number of pixels (got %r)" % (im_size,))
         self.model = mesh_data if isinstance(mesh_data, DeviceModel) else DeviceModel(mesh_data, device, convention)
         self.vertex_code = self.model.vertex_code          # network.py:39
         self.tri = self.model.tri                           # network.py:40
@@ -174,13 +189,13 @@ class FaceRecNet:
     def rendering_layer(self, vertex_proj, triangles, colors):
         """network.py:174-201 in one kernel pass after the rasterizer; ``rendering_layer_unfused`` is the
         literal transcription it is tested against."""
-        return _RenderingLayer.apply(vertex_proj, triangles, colors, self.im_gray, self.im_size, self.im_size)
+        return _RenderingLayer.apply(vertex_proj, triangles, colors, self.im_gray, self._hw, self._hw)
 
     def rendering_layer_unfused(self, vertex_proj, triangles, colors):
         B = vertex_proj.shape[0]
         texture = colors if colors.dim() == 3 else colors.unsqueeze(0).expand(B, -1, -1)      # tf.tile, network.py:179
         im_gray = self.im_gray
-        image = vertex_proj.new_empty((B, self.im_size, self.im_size, 3)) if im_gray is None else im_gray.expand(-1, -1, -1, 3)
+        image = vertex_proj.new_empty((B, self._hw, self._hw, 3)) if im_gray is None else im_gray.expand(-1, -1, -1, 3)
         tf_depth, tf_tex, tf_normal, _ = render_depth(ver=vertex_proj, tri=triangles, texture=texture, image=image)
         pncc_batch = torch.clamp(tf_tex, 1e-6, 1.0)                                            # :185
         flip = (tf_normal[..., 2:3] < 0)                                                       # :188

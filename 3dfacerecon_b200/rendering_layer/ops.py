@@ -17,21 +17,42 @@ from __future__ import annotations
 
 import torch
 
+from .. import mesh as _mesh
 from .._lib import check, lib
 
 OP_NAMES = ["render_depth"]          # rendering_layer/ops.py:13
 
 _workspaces = {}
+_MAX_WORKSPACES = 16
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
-    """Grow-only scratch per (device, stream); the library itself never allocates (include/facerecon_b200.h)."""
+    """Scratch per (device, stream), grown on demand; the library itself never allocates (include/facerecon_b200.h).
+    The cache is bounded: the least recently used entry goes when more than ``_MAX_WORKSPACES`` streams have asked, and
+    ``release_workspaces()`` drops everything (e.g. after a one-off large batch)."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _workspaces.get(key)
+    ws = _workspaces.pop(key, None)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+    _workspaces[key] = ws                       # (re-)inserted last: dict order is the LRU order
+    while len(_workspaces) > _MAX_WORKSPACES:
+        _workspaces.pop(next(iter(_workspaces)))
     return ws
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def _mesh_handle(tri, nver, ver, mesh):
+    """``mesh`` keyword of render_depth -> fr_mesh_table handle or None: "auto" (registry, csrc/mesh_table.h), a
+    ``MeshTable``, or None / False for the generic kernels."""
+    if mesh is None or mesh is False:
+        return None
+    if isinstance(mesh, _mesh.MeshTable):
+        return mesh.handle
+    table = _mesh.table_for(tri, nver, ver, build="now" if mesh == "now" else "auto")
+    return None if table is None else table.handle
 
 
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -46,7 +67,7 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 class _RenderDepth(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ver, tri, texture, image):
+    def forward(ctx, ver, tri, texture, image, mesh):
         ver, tri, texture = _f32c(ver, "ver"), _f32c(tri, "tri"), _f32c(texture, "texture")
         if ver.dim() != 3 or tri.dim() != 2 or texture.dim() != 3 or image.dim() != 4:
             raise ValueError("render_depth expects ver [B,3,N], tri [3,T], texture [B,3,N], image [B,H,W,C]")
@@ -65,6 +86,7 @@ class _RenderDepth(torch.autograd.Function):
             raise ValueError("texture must be [B,3,N] like ver")
         dev = ver.device
         ver, tri = ver.contiguous(), tri.contiguous()
+        mesh_h = _mesh_handle(tri, N, ver, mesh)
         if texture.stride(0) == 0 and texture[0].is_contiguous():
             tex_ptr, tex_stride = texture.data_ptr(), 0          # tiled texture (network.py:179) without the copy
         else:
@@ -75,11 +97,11 @@ class _RenderDepth(torch.autograd.Function):
         normal = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
         tri_ind = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            nbytes = lib().fr_render_workspace_bytes(B, N, H, W)
+            nbytes = lib().fr_render_workspace_bytes(B, N, H, W, mesh_h)
             ws = _workspace(dev, nbytes)
             check(lib().fr_render_depth_forward(ver.data_ptr(), tri.data_ptr(), tex_ptr, tex_stride, depth.data_ptr(),
                                                 texture_image.data_ptr(), normal.data_ptr(), tri_ind.data_ptr(), B, N, T,
-                                                H, W, ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+                                                H, W, mesh_h, ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         ctx.save_for_backward(tri, tri_ind)
         ctx.dims = (B, N, T, H, W)
         ctx.mark_non_differentiable(texture_image, normal, tri_ind)   # ops.py:95: only `ver` gets a gradient
@@ -96,12 +118,16 @@ class _RenderDepth(torch.autograd.Function):
             check(lib().fr_render_depth_backward(depth_grad.data_ptr(), tri.data_ptr(), tri_ind.data_ptr(),
                                                  vertex_grad.data_ptr(), B, N, T, H, W,
                                                  torch.cuda.current_stream(dev).cuda_stream))
-        return vertex_grad, None, None, None
+        return vertex_grad, None, None, None, None
 
 
-def render_depth(ver, tri, texture, image, **kwargs):
-    """``rendering_layer/ops.py:78-81``.  Extra keyword arguments (TF's ``name=``) are accepted and ignored."""
-    return _RenderDepth.apply(ver, tri, texture, image)
+def render_depth(ver, tri, texture, image, mesh="auto", **kwargs):
+    """``rendering_layer/ops.py:78-81``.  Extra keyword arguments (TF's ``name=``) are accepted and ignored.
+
+    ``mesh`` selects the rasterizer's side table for ``tri`` (same outputs either way): "auto" (default) uses the table
+    registered for this ``tri`` tensor -- ``DeviceModel`` registers one at model load, any other tensor gets one the
+    second time it is seen --, "now" builds one immediately, a ``MeshTable`` is used as given, None = generic kernels."""
+    return _RenderDepth.apply(ver, tri, texture, image, mesh)
 
 
 def render_depth_grad(depth_grad, vertex, tri, depth, tri_ind, image):

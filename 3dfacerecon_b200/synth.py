@@ -38,13 +38,16 @@ def _smooth_basis(rng, u, w, ncomp, rms, noise):
     return out
 
 
-def make_synthetic_model(grid=BFM_GRID, ndim_shape=NDIM_SHAPE, ndim_exp=NDIM_EXP, ntri=None, seed=0, jitter=0.2):
+def make_synthetic_model(grid=BFM_GRID, ndim_shape=NDIM_SHAPE, ndim_exp=NDIM_EXP, ntri=None, seed=0, jitter=0.2, permute=False):
     """Return a model dict with the keys of ``read_3dmm_model`` (``utils/parser_3dmm.py:50-60``).
 
     ``mu`` [3N,1] is PLANAR (x block, y block, z block) as ``nets/network.py:157`` reads it.
     ``tri`` [3,T] float32 holds 0-based vertex indices.
     ``jitter`` displaces each mean vertex by U(-jitter, jitter) grid cells (0 = exact grid, the
     stress case where many pixel centres fall exactly on shared edges).
+    ``permute`` renumbers the vertices with a random permutation (applied consistently to ``mu``, the bases, the
+    per-vertex textures and ``tri``) and shuffles the triangle order: the same surface, but without the generator's
+    grid order, in which triangle i touches vertices ~ i/2 (best-case gather locality that a real BFM file does not have).
     """
     gx, gy = int(grid[0]), int(grid[1])
     n = gx * gy
@@ -81,11 +84,21 @@ def make_synthetic_model(grid=BFM_GRID, ndim_shape=NDIM_SHAPE, ndim_exp=NDIM_EXP
 
     pc_shape = _smooth_basis(rng, u, w, ndim_shape, 2.5e-2, 2.5e-4)
     pc_exp = _smooth_basis(rng, u, w, ndim_exp, 1.0e3, 10.0)
+    vertex_code = rng.uniform(0.0, 1.0, (3, n)).astype(np.float32)
+    mu_tex = rng.uniform(0.0, 255.0, (3, n)).astype(np.float32)
+    if permute:
+        prng = np.random.default_rng(seed + 7919)
+        new_id = prng.permutation(n)                    # new_id[old vertex] = its new number
+        old_of = np.argsort(new_id)                     # old_of[new vertex] = old number
+        rows = (np.arange(3)[:, None] * n + old_of[None, :]).ravel()      # planar 3N rows in the new numbering
+        mu, pc_shape, pc_exp = mu[rows], pc_shape[rows], pc_exp[rows]
+        vertex_code, mu_tex = vertex_code[:, old_of], mu_tex[:, old_of]
+        tri = new_id[tri.astype(np.int64)][:, prng.permutation(tri.shape[1])].astype(np.float32)
     return {
-        "vertex": rng.uniform(0.0, 1.0, (3, n)).astype(np.float32),      # PNCC code
+        "vertex": vertex_code,                                           # PNCC code
         "tri": tri,
         "mu": mu,
-        "mu_tex": rng.uniform(0.0, 255.0, (3, n)).astype(np.float32),
+        "mu_tex": mu_tex,
         "pc_tex": np.zeros((3 * n, 1), np.float32),                      # not on the hot path
         "param_tex": np.zeros((1, 1), np.float32),
         "pc_shape": pc_shape,

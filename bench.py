@@ -221,29 +221,33 @@ def run_ours(args):
     depth = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
     tri_ind = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
     rbytes = lib.fr_recon_workspace_bytes(B, nver, ks, ke)
-    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, nver, ks, ke, H, W), dtype=torch.uint8, device=dev)
+    mesh = dm.mesh.handle
+    ws = torch.empty(max(lib.fr_pipeline_workspace_bytes(B, nver, ks, ke, H, W, mesh),
+                         rbytes + lib.fr_render_workspace_bytes(B, nver, H, W, mesh)), dtype=torch.uint8, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
-    def step_full(vertex_ptr=None):
+    def step_full(vertex_ptr=None, events=None):
         """The north-star call: params -> depth + tri_ind.  The intermediate vertex tensor is an optional output of the fused
-        call (the reconstruction epilogue feeds the rasterizer's vertex records directly); the timed loop does not ask for it."""
-        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), vertex_ptr,
+        call (the reconstruction epilogue hands the vertices to its rasterizer stage in shared memory); the timed loop does
+        not ask for it."""
+        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), mesh, vertex_ptr,
                                           depth.data_ptr(), tri_ind.data_ptr(), B, nver, ntri, ks, ke, H, W, IM_SIZE,
-                                          dm.run_flags, ws.data_ptr(), ws.numel(), sp))
+                                          dm.run_flags, ws.data_ptr(), ws.numel(), sp, events))
 
     def step_recon():
-        check(lib.fr_recon_project_forward(params.data_ptr(), dm.packed.data_ptr(), vertex.data_ptr(), B, nver, ks, ke, IM_SIZE,
+        check(lib.fr_recon_project_forward(params.data_ptr(), dm.packed.data_ptr(), mesh, vertex.data_ptr(), B, nver, ks, ke, IM_SIZE,
                                            dm.run_flags, ws.data_ptr(), rbytes, sp))
 
     def step_render():
         check(lib.fr_render_depth_forward(vertex.data_ptr(), dm.tri.data_ptr(), None, 0, depth.data_ptr(), None, None,
-                                          tri_ind.data_ptr(), B, nver, ntri, H, W, ws.data_ptr() + rbytes, ws.numel() - rbytes, sp))
+                                          tri_ind.data_ptr(), B, nver, ntri, H, W, mesh, ws.data_ptr() + rbytes, ws.numel() - rbytes, sp))
 
     def timed_parts(steps, warmup):
-        """The fused step with an event recorded by the library between its reconstruction and rasterizer kernels
-        (fr_debug_set_mid_event): device time of the two parts of the same real step, L2 flushed before every step."""
+        """The fused step with an event recorded by the library between its reconstruction(+rasterizer) kernels and the resolve
+        pass (stage_events argument): device time of the two parts of the same real step, L2 flushed before every step."""
+        import ctypes
         for _ in range(warmup):
             flush.zero_()
             step_full()
@@ -254,10 +258,8 @@ def run_ours(args):
             m.record(stream)                                           # creates the underlying cudaEvent
             flush.zero_()
             a.record(stream)
-            check(lib.fr_debug_set_mid_event(m.cuda_event))
-            step_full()
+            step_full(None, (ctypes.c_void_p * 2)(m.cuda_event, None))
             b.record(stream)
-        check(lib.fr_debug_set_mid_event(None))
         torch.cuda.synchronize(dev)
         recon = sum(a.elapsed_time(m) for (a, _), m in zip(evs, mids)) / steps
         render = sum(m.elapsed_time(b) for (_, b), m in zip(evs, mids)) / steps
@@ -379,12 +381,12 @@ def run_ours(args):
             p3 = torch.from_numpy(synth.sample_params_constrained(B3, seed=3)).to(dev)
             d3 = torch.empty((B3, H, W, 1), dtype=torch.float32, device=dev)
             t3 = torch.empty((B3, H, W, 1), dtype=torch.float32, device=dev)
-            ws3 = torch.empty(lib.fr_pipeline_workspace_bytes(B3, nver, ks, ke, H, W), dtype=torch.uint8, device=dev)
+            ws3 = torch.empty(lib.fr_pipeline_workspace_bytes(B3, nver, ks, ke, H, W, mesh), dtype=torch.uint8, device=dev)
 
             def fwd3():
-                check(lib.fr_recon_render_forward(p3.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), None, d3.data_ptr(),
+                check(lib.fr_recon_render_forward(p3.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), mesh, None, d3.data_ptr(),
                                                   t3.data_ptr(), B3, nver, ntri, ks, ke, H, W, IM_SIZE, dm.run_flags, ws3.data_ptr(),
-                                                  ws3.numel(), sp))
+                                                  ws3.numel(), sp, None))
             ms3 = time_torch(fwd3, 5)
             big["config3_b%d_fwd" % B3] = {"ms": ms3, "faces_per_s": B3 / (ms3 * 1e-3), "api": "fr_recon_render_forward, one call"}
             del p3, d3, t3, ws3
@@ -447,8 +449,8 @@ def run_ours(args):
         peak, peak_src = _peak_hbm()
         rb, nb = algorithmic_bytes(B, nver, ntri, K)
         # dominant part of the timed (fused) step: reconstruction (prep + tcgen05 kernel) vs rasterizer (keys + resolve)
-        parts = {"recon_part_of_step (recon_prep_f16 + recon_fwd_f16 kernels)": (rb, ms_part_recon_max),
-                 "render_part_of_step (raster_keys + raster_resolve kernels)": (nb, ms_part_render_max)}
+        parts = {"recon_raster_part_of_step (recon_prep_f16 + recon_fwd_f16<raster> kernels)": (rb + nb - 8 * B * H * W, ms_part_recon_max),
+                 "render_resolve_part_of_step (raster_resolve kernel)": (8 * B * H * W, ms_part_render_max)}
         dom = max(parts, key=lambda k: parts[k][1])
         dbytes, dms = parts[dom]
         achieved = dbytes / (dms * 1e-3) / 1e9

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FR_VERSION 100
+#define FR_VERSION 200
 
 /* status codes */
 #define FR_OK 0
@@ -59,22 +59,48 @@ extern "C" {
 const char* fr_last_error(void);
 int fr_version(void);
 
+/* ---- mesh table: the triangle list of a model, clustered once for the rasterizer ------------------
+ * The reference walks `tri` [3,ntri] triangle by triangle, converting three float indices and gathering nine vertex
+ * floats per triangle and face (render_depth_op.cc:204-213; render_depth_op.cu.cc:84-92).  A mesh table partitions the
+ * triangles ONCE per model (host side) into clusters of <= 128 unique vertices / <= 256 triangles with pre-validated
+ * 8-bit local indices; the rasterizer then stages a cluster's vertices in shared memory once per face, and the
+ * tensor-core reconstruction uses the clusters as its row tiles, so that in the fused params -> depth-map call the
+ * vertices never pass through global memory (3dfacerecon_b200/csrc/mesh_table.h, raster_cluster.cuh).
+ *   tri        HOST pointer, [3,ntri] float 0-based indices as rendering_layer/ops.py:78 takes them; triangles with an
+ *              index outside [0,nver) are dropped (the reference reads out of bounds)
+ *   positions  HOST pointer or NULL: any vertex positions that reflect the mesh's locality -- the mean shape `mu`
+ *              ([3,nver] planar, or [nver,3] with positions_interleaved != 0) or one face of a vertex tensor; only the
+ *              quality of the partition depends on them, never a result
+ *   device     CUDA device that receives a copy of the table, or -1 for a host-only table (inspection, tests)
+ * The table replaces nothing in the results: every entry point below gives bit-identical outputs with and without it. */
+typedef struct fr_mesh_table fr_mesh_table;
+int fr_mesh_table_create(const float* tri, int ntri, int nver, const float* positions, int positions_interleaved, int device,
+                         fr_mesh_table** out);
+/* Re-creates a table from the bytes fr_mesh_table_blob returned earlier (an on-disk cache); validates header and hash. */
+int fr_mesh_table_from_blob(const void* blob, size_t bytes, int device, fr_mesh_table** out);
+void fr_mesh_table_destroy(fr_mesh_table* mesh);
+const void* fr_mesh_table_blob(const fr_mesh_table* mesh, size_t* bytes);   /* host copy (layout: mesh_table.h) */
+int fr_mesh_table_clusters(const fr_mesh_table* mesh);
+int fr_mesh_table_vertex_slots(const fr_mesh_table* mesh);   /* vertices counted once per member cluster */
+
 /* ---- model packing: utils/parser_3dmm.py dict -> one device buffer ------------------------------
  * Packs [pc_shape | pc_exp | mu | 0-pad] into the layouts the kernels stream (DESIGN.md "Packed basis"):
- * an fp32 float4-tiled section (FFMA kernels), fp16 hi/lo tcgen05 operand tiles of the column-scaled basis
- * for the forward and, transposed, for the backward contraction, the column scales and an fp32 copy of
- * the mean.  mu [3N], pc_shape [3N,ndim_shape], pc_exp [3N,ndim_exp] are device pointers in the
- * reference's layouts (nets/network.py:41-43).  One-off, at model load. */
-size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp);
+ * an fp32 float4-tiled section (FFMA kernels), the column scales, fp16 hi/lo tcgen05 operand tiles of the
+ * column-scaled basis transposed for the backward contraction, an fp32 copy of the mean, and the fp16 hi/lo
+ * operand tiles of the forward pass with ONE ROW TILE PER CLUSTER of `mesh` (NULL: tiles of 128 consecutive
+ * vertices).  mu [3N], pc_shape [3N,ndim_shape], pc_exp [3N,ndim_exp] are device pointers in the reference's layouts
+ * (nets/network.py:41-43).  One-off, at model load.  Every later call that takes this packed basis must be given the
+ * same `mesh` (or NULL if it was packed with NULL). */
+size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp, const fr_mesh_table* mesh);
 int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, int nver, int ndim_shape, int ndim_exp,
-                  unsigned layout_flags, float* packed, void* stream);
+                  unsigned layout_flags, const fr_mesh_table* mesh, float* packed, void* stream);
 
 /* ---- FaceRecNet.vertices_transform (nets/network.py:140-171) ------------------------------------
  * params [batch, 7+ndim_shape+ndim_exp] (layout nets/network.py:143-145,258-262) -> vertex_proj [batch,3,nver].
  * Rotation (network.py:266-297, a host py_func in the reference) is computed on the device. */
 size_t fr_recon_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp);
-int fr_recon_project_forward(const float* params, const float* packed, float* vertex_proj, int batch, int nver,
-                             int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
+int fr_recon_project_forward(const float* params, const float* packed, const fr_mesh_table* mesh, float* vertex_proj, int batch,
+                             int nver, int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                              size_t workspace_bytes, void* stream);
 
 /* Gradient of the above as TF autodiff produces it: vertex_grad [batch,3,nver]
@@ -91,11 +117,14 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
  * its `image` input (:397-403), whose values it never reads.
  * Outputs: depth [batch,H,W,1], texture_image [batch,H,W,3], normal [batch,H,W,3], tri_ind [batch,H,W,1]
  * (float, -1 = background).  texture_image and normal may be NULL to skip them (texture may then be NULL).
- * Triangles whose indices fall outside [0,nver) are skipped (the reference reads out of bounds). */
-size_t fr_render_workspace_bytes(int batch, int nver, int height, int width);
+ * Triangles whose indices fall outside [0,nver) are skipped (the reference reads out of bounds).
+ * mesh: the mesh table of `tri` (cluster rasterizer) or NULL (generic per-triangle path); same outputs either way.
+ * At most 65535 faces per call. */
+size_t fr_render_workspace_bytes(int batch, int nver, int height, int width, const fr_mesh_table* mesh);
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                             float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
-                            int ntri, int height, int width, void* workspace, size_t workspace_bytes, void* stream);
+                            int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
+                            void* stream);
 
 /* ---- TF op "RenderDepthGrad" (render_depth_op.cc:470-528, :571-589; functor :325-368) -----------
  * depth_grad [batch,H,W,1], tri [3,ntri], tri_ind [batch,H,W,1] -> vertex_grad [batch,3,nver], fully
@@ -113,7 +142,7 @@ int fr_render_depth_backward(const float* depth_grad, const float* tri, const fl
 int fr_rendering_layer_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                                const float* im_gray, float* pncc, float* normalimg, float* maskimg, float* depthimg,
                                float* raw_depth, float* tri_ind, int batch, int nver, int ntri, int height, int width,
-                               void* workspace, size_t workspace_bytes, void* stream);
+                               const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes, void* stream);
 /* Its gradient as autodiff composes it: depth_grad of the op = depthimg_grad where depth >= 1e-6, plus maskimg_grad * im_gray
  * where 1e-6 <= depth <= 1 (either gradient may be NULL), then RenderDepthGrad. */
 int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg_grad, const float* im_gray, const float* raw_depth,
@@ -121,14 +150,20 @@ int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg
                                 int height, int width, void* stream);
 
 /* ---- fused: params -> depth map (the north-star path in one call) -------------------------------
- * Same results as fr_recon_project_forward followed by fr_render_depth_forward (depth + tri_ind only), but the
- * reconstruction epilogue writes the rasterizer's vertex records directly, so the rasterizer's repack pass over the
- * vertex tensor is skipped.  vertex_proj [batch,3,nver] is optional here (NULL = do not materialise it). */
-size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width);
-int fr_recon_render_forward(const float* params, const float* packed, const float* tri, float* vertex_proj, float* depth,
-                            float* tri_ind, int batch, int nver, int ntri, int ndim_shape, int ndim_exp, int height,
-                            int width, float im_size, unsigned flags, void* workspace, size_t workspace_bytes,
-                            void* stream);
+ * Same results as fr_recon_project_forward followed by fr_render_depth_forward (depth + tri_ind only).  With a mesh
+ * table and more than 8 faces it runs as three kernels: parameter prep (which also clears the visibility keys), the
+ * tensor-core reconstruction whose epilogue projects each cluster's vertices into shared memory and rasterizes the
+ * cluster's triangles from there, and the resolve pass -- the vertices never reach global memory.  vertex_proj
+ * [batch,3,nver] is optional (NULL = do not materialise it).  Small batches / mesh == NULL run the two stages one after
+ * the other through a planar vertex buffer in the workspace.
+ * stage_events: NULL, or two cudaEvent_t (either may be NULL) recorded on `stream` after the reconstruction(+raster)
+ * kernels and after the last kernel -- lets a benchmark split the device time of one real call. */
+size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width,
+                                   const fr_mesh_table* mesh);
+int fr_recon_render_forward(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
+                            float* vertex_proj, float* depth, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
+                            int ndim_exp, int height, int width, float im_size, unsigned flags, void* workspace,
+                            size_t workspace_bytes, void* stream, void* const* stage_events);
 
 /* ---- host-buffer session (what a non-GPU caller binds) ----------------------
  * A session owns the device copy of the model, device staging for `max_batch` faces and one stream.
@@ -155,10 +190,6 @@ int fr_session_wait(fr_session* s, int slot);
 int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float* params_grad);
 /* counters: kernels launched by this library since load (for bench.py's gpu_launches) */
 unsigned long long fr_launch_count(void);
-/* measurement hook: a cudaEvent_t that fr_recon_render_forward records between its reconstruction and its rasterizer
- * kernels (NULL = off), so a benchmark can split the device time of one real step; process-global, not thread-safe. */
-int fr_debug_set_mid_event(void* cuda_event);
-
 #ifdef __cplusplus
 }
 #endif

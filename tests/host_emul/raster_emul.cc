@@ -4,8 +4,10 @@
 // Built by tests/test_raster_core_host.py with g++ -O2 -ffp-contract=off.
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
+#include "../../3dfacerecon_b200/csrc/mesh_table.h"
 #include "../../3dfacerecon_b200/csrc/raster_core.h"
 
 static bool vidx(float f, int nver, int* out) {
@@ -92,10 +94,13 @@ extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, con
       if (keys[p] != 0ull) {
         const int t = fr_key_triangle(keys[p]);
         const int p1 = (int)tri[t], p2 = (int)tri[ntri + t], p3 = (int)tri[2 * (size_t)ntri + t];
-        bool ambiguous;
-        d = fr_key_depth(keys[p], &ambiguous);
-        if (ambiguous) d = fr_tri_depth(vz[p1], vz[p2], vz[p3]);
-        else if (d != fr_tri_depth(vz[p1], vz[p2], vz[p3])) return 102;  // decoded depth must equal the recomputed one
+        d = fr_key_depth(keys[p]);
+        {  // the decoded depth must equal the recomputed one bit for bit (including the sign of a zero)
+          union { float f; uint32_t u; } a, r;
+          a.f = d;
+          r.f = fr_tri_depth(vz[p1], vz[p2], vz[p3]);
+          if (a.u != r.u) return 102;
+        }
         ti = (float)t;
         fr_tri_normal(vx[p1], vy[p1], vz[p1], vx[p2], vy[p2], vz[p2], vx[p3], vy[p3], vz[p3], n);
         const float* tex = texture + (size_t)b * tex_stride;
@@ -107,6 +112,69 @@ extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, con
         normal[3 * o + c] = n[c];
         teximg[3 * o + c] = tx[c];
       }
+    }
+  }
+  return 0;
+}
+
+// Data flow of the CLUSTER rasterizer (raster_cluster.cuh / the fused reconstruction epilogue): walk the mesh table
+// cluster by cluster, "stage" the cluster's vertices with their snap codes, cull every triangle on the codes of its
+// three LOCAL slots, draw the survivors from the staged coordinates with the packed-key maximum, then resolve depth and
+// index from the keys alone.  Outputs: depth and tri_ind.
+extern "C" int fr_emul_render_forward_clustered(const float* vertex, const unsigned char* table, int batch, int nver, int height,
+                                                int width, float* depth, float* tri_ind) {
+  fr::MeshTableHeader h;
+  std::memcpy(&h, table, sizeof(h));
+  if (h.magic != fr::kMeshMagic || h.nver != nver) return 200;
+  const int32_t* cv = reinterpret_cast<const int32_t*>(table + h.off_vert);
+  const int32_t* tb = reinterpret_cast<const int32_t*>(table + h.off_tri_begin);
+  const uint32_t* te = reinterpret_cast<const uint32_t*>(table + h.off_tri);
+  const size_t npix = (size_t)height * width;
+  const uint32_t limit = (uint32_t)width | ((uint32_t)height << 16);
+  std::vector<unsigned long long> keys(npix);
+  for (int b = 0; b < batch; ++b) {
+    const float* vx = vertex + (size_t)b * 3 * nver;
+    const float* vy = vx + nver;
+    const float* vz = vy + nver;
+    for (auto& k : keys) k = 0ull;
+    for (int c = h.nclusters - 1; c >= 0; --c) {             // any cluster order gives the same keys
+      float sx[fr::kClusterVerts], sy[fr::kClusterVerts], sz[fr::kClusterVerts];
+      uint32_t code[fr::kClusterVerts];
+      for (int v = 0; v < fr::kClusterVerts; ++v) {
+        const int32_t raw = cv[(size_t)c * fr::kClusterVerts + v];
+        const int n = raw < 0 ? -1 : (int)((uint32_t)raw & fr::kVertIdMask);
+        sx[v] = n < 0 ? 0.0f : vx[n];
+        sy[v] = n < 0 ? 0.0f : vy[n];
+        sz[v] = n < 0 ? 0.0f : vz[n];
+        code[v] = fr_snap_code(sx[v], sy[v], width, height);
+      }
+      for (int i = tb[c]; i < tb[c + 1]; ++i) {
+        const uint32_t w = te[2 * (size_t)i];
+        const int t = (int)te[2 * (size_t)i + 1];
+        const unsigned l1 = w & 0xFFu, l2 = (w >> 8) & 0xFFu, l3 = (w >> 16) & 0xFFu;
+        uint32_t lo, hi;
+        if (!fr_code_keep(code[l1], code[l2], code[l3], limit, &lo, &hi)) continue;
+        const float hgt = fr_tri_depth(sz[l1], sz[l2], sz[l3]);
+        if (!fr_depth_draws(hgt)) continue;
+        FrTriEdge e;
+        fr_tri_edge_setup(sx[l1], sy[l1], sx[l2], sy[l2], sx[l3], sy[l3], &e);
+        const unsigned long long key = fr_pack_key(hgt, t);
+        FrBBox bb;
+        fr_snap_bbox(lo, hi, &bb);
+        for (int y = bb.y_min; y <= bb.y_max; ++y)
+          for (int x = bb.x_min; x <= bb.x_max; ++x)
+            if (fr_point_in_tri(&e, x, y)) {
+              unsigned long long& k = keys[(size_t)y * width + x];
+              if (key > k) k = key;
+            }
+      }
+    }
+    for (size_t p = 0; p < npix; ++p) {
+      union { uint32_t u; float f; } bg;
+      bg.u = FR_BACKGROUND_DEPTH_BITS;
+      const size_t o = (size_t)b * npix + p;
+      depth[o] = keys[p] ? fr_key_depth(keys[p]) : bg.f;
+      tri_ind[o] = keys[p] ? (float)fr_key_triangle(keys[p]) : -1.0f;
     }
   }
   return 0;

@@ -148,25 +148,25 @@ def test_session_host_buffers_match_tensor_path(bfm):
 
 @pytest.mark.parametrize("B", [3, 20])
 def test_fused_call_matches_separate_calls(bfm, B):
-    """fr_recon_render_forward (records written by the reconstruction epilogue, SIMT path at B=3 and tcgen05 path at
-    B=20) == fr_recon_project_forward + fr_render_depth_forward bit for bit, with and without the vertex tensor."""
+    """fr_recon_render_forward (un-fused SIMT path at B=3; at B=20 the tcgen05 kernel with the cluster rasterizer in its
+    epilogue) == fr_recon_project_forward + fr_render_depth_forward bit for bit, with and without the vertex tensor."""
     lib, check = fr("_lib").lib(), fr("_lib").check
     p = fr("synth").sample_params_constrained(B, seed=60 + B)
     dm, vp = _gpu_vertices(bfm, p, 200)
     image = torch.empty((B, 200, 200, 3), device=DEV)
     want = fr("rendering_layer.ops").render_depth(torch.from_numpy(vp).to(DEV), dm.tri, dm.vertex_code.unsqueeze(0).expand(B, -1, -1), image)
     pt = torch.from_numpy(p).to(DEV)
-    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, dm.ndim_shape, dm.ndim_exp, 200, 200), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, dm.ndim_shape, dm.ndim_exp, 200, 200, dm.mesh.handle), dtype=torch.uint8, device=DEV)
     sp = torch.cuda.current_stream().cuda_stream
     for with_vertex in (True, False):
         ws.fill_(0xAB)                                                    # stale workspace contents must not matter
         vertex = torch.full((B, 3, dm.nver), float("nan"), device=DEV)
         depth = torch.empty((B, 200, 200, 1), device=DEV)
         tri_ind = torch.empty((B, 200, 200, 1), device=DEV)
-        check(lib.fr_recon_render_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(),
+        check(lib.fr_recon_render_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), dm.mesh.handle,
                                           vertex.data_ptr() if with_vertex else None, depth.data_ptr(), tri_ind.data_ptr(), B,
                                           dm.nver, dm.ntri, dm.ndim_shape, dm.ndim_exp, 200, 200, 200.0, dm.run_flags,
-                                          ws.data_ptr(), ws.numel(), sp))
+                                          ws.data_ptr(), ws.numel(), sp, None))
         torch.cuda.synchronize()
         assert depth.cpu().numpy().tobytes() == want[0].cpu().numpy().tobytes(), with_vertex
         assert tri_ind.cpu().numpy().tobytes() == want[3].cpu().numpy().tobytes(), with_vertex
@@ -186,18 +186,20 @@ def test_fused_call_small_model_odd_shapes(small_model, B, H, W):
     dm = fr("model").DeviceModel(small_model, DEV)
     pt = torch.from_numpy(p).to(DEV)
     sp = torch.cuda.current_stream().cuda_stream
-    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, H, W), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, H, W, dm.mesh.handle), dtype=torch.uint8, device=DEV)
     rb = lib.fr_recon_workspace_bytes(B, dm.nver, ks, ke)
     vp = torch.empty((B, 3, dm.nver), device=DEV)
     want_d, want_t = torch.empty((B, H, W, 1), device=DEV), torch.empty((B, H, W, 1), device=DEV)
-    check(lib.fr_recon_project_forward(pt.data_ptr(), dm.packed.data_ptr(), vp.data_ptr(), B, dm.nver, ks, ke, float(max(H, W)),
-                                       dm.run_flags, ws.data_ptr(), rb, sp))
+    check(lib.fr_recon_project_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.mesh.handle, vp.data_ptr(), B, dm.nver, ks, ke,
+                                       float(max(H, W)), dm.run_flags, ws.data_ptr(), rb, sp))
+    ws2 = torch.empty(lib.fr_render_workspace_bytes(B, dm.nver, H, W, None), dtype=torch.uint8, device=DEV)
     check(lib.fr_render_depth_forward(vp.data_ptr(), dm.tri.data_ptr(), None, 0, want_d.data_ptr(), None, None, want_t.data_ptr(), B,
-                                      dm.nver, dm.ntri, H, W, ws.data_ptr() + rb, ws.numel() - rb, sp))
+                                      dm.nver, dm.ntri, H, W, None, ws2.data_ptr(), ws2.numel(), sp))      # generic rasterizer
     ws.fill_(0x5C)
     got_d, got_t = torch.empty_like(want_d), torch.empty_like(want_t)
-    check(lib.fr_recon_render_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), None, got_d.data_ptr(), got_t.data_ptr(),
-                                      B, dm.nver, dm.ntri, ks, ke, H, W, float(max(H, W)), dm.run_flags, ws.data_ptr(), ws.numel(), sp))
+    check(lib.fr_recon_render_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), dm.mesh.handle, None, got_d.data_ptr(),
+                                      got_t.data_ptr(), B, dm.nver, dm.ntri, ks, ke, H, W, float(max(H, W)), dm.run_flags, ws.data_ptr(),
+                                      ws.numel(), sp, None))
     torch.cuda.synchronize()
     assert (want_t >= 0).sum() > 0.05 * want_t.numel()                    # the faces are in frame
     assert got_d.cpu().numpy().tobytes() == want_d.cpu().numpy().tobytes()
@@ -238,13 +240,13 @@ def test_fused_call_is_cuda_graph_capturable(small_model):
     pa = torch.from_numpy(fr("synth").sample_params_constrained(B, ks, ke, S, seed=1)).to(DEV)
     pb = torch.from_numpy(fr("synth").sample_params_constrained(B, ks, ke, S, seed=2)).to(DEV)
     params = pa.clone()
-    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, S, S), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, S, S, dm.mesh.handle), dtype=torch.uint8, device=DEV)
     depth, tri_ind = torch.empty((B, S, S, 1), device=DEV), torch.empty((B, S, S, 1), device=DEV)
 
     def call(stream):
-        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), None, depth.data_ptr(),
-                                          tri_ind.data_ptr(), B, dm.nver, dm.ntri, ks, ke, S, S, float(S), dm.run_flags, ws.data_ptr(),
-                                          ws.numel(), stream.cuda_stream))
+        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), dm.mesh.handle, None,
+                                          depth.data_ptr(), tri_ind.data_ptr(), B, dm.nver, dm.ntri, ks, ke, S, S, float(S), dm.run_flags,
+                                          ws.data_ptr(), ws.numel(), stream.cuda_stream, None))
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):

@@ -24,27 +24,29 @@ def test_abi_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), n
     lib = lib_mod.lib()
-    assert lib.fr_version() == 100
+    assert lib.fr_version() == 200
     # size queries are pure host arithmetic: safe without a GPU
-    assert lib.fr_packed_basis_bytes(53215, 199, 29) == 416 * 3 * 58 * 128 * 16 + 416 * 3 * 15 * 8192 + 1024 + 416 * 3 * 8 * 16384 + 3 * 416 * 128 * 4   # fp32 + fp16-pair tiles + column scales + backward tiles + fp32 mean
-    assert lib.fr_render_workspace_bytes(64, 53215, 200, 200) == 64 * 200 * 200 * 8 + 64 * 53215 * 16   # keys + 16-byte vertex records
+    assert lib.fr_packed_basis_bytes(53215, 199, 29, None) == 416 * 3 * 58 * 128 * 16 + 416 * 3 * 15 * 8192 + 1024 + 416 * 3 * 8 * 16384 + 3 * 416 * 128 * 4   # fp32 + fp16-pair tiles + column scales + backward tiles + fp32 mean
+    assert lib.fr_render_workspace_bytes(64, 53215, 200, 200, None) == 64 * 200 * 200 * 8 + 64 * 53215 * 16   # keys + 16-byte vertex records
     assert lib.fr_recon_workspace_bytes(64, 53215, 199, 29) >= 232 * 64 * 4
-    assert lib.fr_packed_basis_bytes(0, 199, 29) == 0
+    assert lib.fr_packed_basis_bytes(0, 199, 29, None) == 0
 
 
 def test_abi_rejects_bad_arguments_without_a_gpu():
     """Validation happens before any CUDA call, so it is checkable here; messages follow the reference's."""
     lib_mod = fr("_lib")
     lib = lib_mod.lib()
-    rc = lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 1, 10, 10 * 1000 * 1000, 8, 8, None, 0, None)
+    rc = lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 1, 10, 10 * 1000 * 1000, 8, 8, None, None, 0, None)
     assert rc == lib_mod.FR_ERR_INVALID_ARGUMENT and "Too many triangular" in lib_mod.last_error()
-    rc = lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 1, 10, 5, 8, 8, None, 0, None)
+    rc = lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 1, 10, 5, 8, 8, None, None, 0, None)
     assert rc == lib_mod.FR_ERR_INVALID_ARGUMENT and "null pointer" in lib_mod.last_error()
-    rc = lib.fr_recon_project_forward(None, None, None, 1, 10, 0, 0, 200.0, 0, None, 0, None)
+    rc = lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 70000, 10, 5, 8, 8, None, None, 0, None)
+    assert rc == lib_mod.FR_ERR_INVALID_ARGUMENT and "65535" in lib_mod.last_error()
+    rc = lib.fr_recon_project_forward(None, None, None, None, 1, 10, 0, 0, 200.0, 0, None, 0, None)
     assert rc == lib_mod.FR_ERR_INVALID_ARGUMENT
     with pytest.raises(ValueError):
         lib_mod.check(rc)
-    assert lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 0, 10, 5, 8, 8, None, 0, None) == 0   # empty batch
+    assert lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 0, 10, 5, 8, 8, None, None, 0, None) == 0   # empty batch
 
 
 def test_product_has_no_oracle_or_cpu_path():
