@@ -79,7 +79,7 @@ class _RenderingLayer(torch.autograd.Function):
     the reference (the op registers no gradient for texture / normal, ``rendering_layer/ops.py:95``)."""
 
     @staticmethod
-    def forward(ctx, vertex_proj, tri, texture, im_gray, height, width, mesh="auto"):
+    def forward(ctx, vertex_proj, tri, texture, im_gray, height, width, mesh):
         if not vertex_proj.is_cuda:
             raise RuntimeError("vertex_proj is on %s: rendering_layer has no CPU path" % vertex_proj.device)
         if vertex_proj.dim() != 3 or vertex_proj.shape[1] != 3:
@@ -189,7 +189,7 @@ class FaceRecNet:
     def rendering_layer(self, vertex_proj, triangles, colors):
         """network.py:174-201 in one kernel pass after the rasterizer; ``rendering_layer_unfused`` is the
         literal transcription it is tested against."""
-        return _RenderingLayer.apply(vertex_proj, triangles, colors, self.im_gray, self._hw, self._hw)
+        return _RenderingLayer.apply(vertex_proj, triangles, colors, self.im_gray, self._hw, self._hw, "auto")
 
     def rendering_layer_unfused(self, vertex_proj, triangles, colors):
         B = vertex_proj.shape[0]
