@@ -292,13 +292,20 @@ FR_HD uint32_t fr_snap_code(float x, float y, int width, int height) {
   return fr_snap_code_axis(x, width) | (fr_snap_code_axis(y, height) << 16);
 }
 
+// Biased bounding box of a triangle from the snap codes of its three vertices
+// (x_min+1 | y_min+1 << 16, x_max+1 | y_max+1 << 16); meaningful for triangles fr_code_keep keeps.
+FR_HD void fr_code_box(uint32_t e1, uint32_t e2, uint32_t e3, uint32_t* lo_min, uint32_t* hi_max) {
+  const uint32_t mn = fr_min3_u16x2(e1, e2, e3);
+  const uint32_t mx = fr_max3_u16x2(e1, e2, e3);
+  *lo_min = (mn >> 1) & 0x7FFF7FFFu;
+  *hi_max = ((mx >> 1) & 0x7FFF7FFFu) - 0x00010001u + (mx & 0x00010001u);  // flag clear => ceil_biased >= 1: no borrow
+}
+
 // fr_snap_keep on snap codes: same decision, same biased bounding box.
 FR_HD bool fr_code_keep(uint32_t e1, uint32_t e2, uint32_t e3, uint32_t limit, uint32_t* lo_min, uint32_t* hi_max) {
   const uint32_t G = 0x80008000u;
-  const uint32_t mn = fr_min3_u16x2(e1, e2, e3);
-  const uint32_t mx = fr_max3_u16x2(e1, e2, e3);
-  const uint32_t lo = (mn >> 1) & 0x7FFF7FFFu;
-  const uint32_t hi = ((mx >> 1) & 0x7FFF7FFFu) - 0x00010001u + (mx & 0x00010001u);  // flag clear => ceil_biased >= 1: no borrow
+  uint32_t lo, hi;
+  fr_code_box(e1, e2, e3, &lo, &hi);
   const uint32_t nonempty = (hi | G) - lo;
   const uint32_t inside_lo = (lo | G) - 0x00010001u;
   const uint32_t inside_hi = (limit | G) - hi;

@@ -32,6 +32,9 @@
 #include "recon.cuh"
 #include "tcgen05_common.cuh"
 
+#ifndef FR_FUSED_EPI_WARPS
+#define FR_FUSED_EPI_WARPS 28    // epilogue warps of the raster flavour (16 of them read the accumulators); + producer + MMA issuer = 960 threads
+#endif
 #ifndef FR_BASIS_EVICT_FIRST
 #define FR_BASIS_EVICT_FIRST 1   // A/B on B200: 102.8 -> 101.6 us per step (the records / keys stay in L2 for the rasterizer)
 #endif
@@ -66,12 +69,17 @@ constexpr int kPose16Stride = 16;      // floats per face: 2^-t f.R [9] | t [3] 
 // Flavour of the forward kernel (see the header comment).
 template <bool kRaster>
 struct Cfg {
-  static constexpr int kEpiWarps = kRaster ? 16 : 8;
+  // Epilogue warps; every one of them reads accumulators (its TMEM lane quarter = warp % 4) and, in the raster flavour,
+  // rasterizes.  Planar: 8 warps, 16 consecutive faces per warp and step.  Raster: 28 warps (7 per lane quarter), a
+  // warp reads the faces wq, wq + 7, ... of the 32-face stage one column at a time.
+  static constexpr int kEpiWarps = kRaster ? FR_FUSED_EPI_WARPS : 8;
   static constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   static constexpr int kThreads = (kEpiWarps + 2) * 32;
-  static constexpr int kStages = kRaster ? 3 : kMaxStages;     // the raster flavour needs 77 KB for its stage and queues
-  static constexpr int kStageFaces = 32;                         // faces per rasterizer stage
-  static constexpr int kFacesPerWarp = kRaster ? kStageFaces / (kEpiWarps / 4) : 16;   // faces a warp drains per step
+  static constexpr int kStages = kRaster ? 3 : kMaxStages;     // the raster flavour needs 82 KB for its stage and survivor list
+  static constexpr int kStepFaces = 32;                          // faces per epilogue step (raster: one stage)
+  static constexpr int kWarpsPerQuarter = kEpiWarps / 4;
+  static constexpr int kFacesPerWarp = (kStepFaces + kWarpsPerQuarter - 1) / kWarpsPerQuarter;   // planar: 16; raster: up to 5
+  static_assert(kEpiWarps % 4 == 0, "whole lane quarters");
 };
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 at [4,6), a = b = F16 (0) at [7,10) / [10,13), K-major
@@ -89,9 +97,9 @@ struct Barriers {
 };
 
 struct RasterSmem {                    // raster flavour only
-  rc::Stage<Cfg<true>::kStageFaces> stage;
+  rc::Stage<Cfg<true>::kStepFaces> stage;
   rc::TriList tris;
-  rc::WarpQueue queue[Cfg<true>::kEpiWarps];
+  rc::StageQueue queue;
 };
 
 struct SmemLayout {
@@ -316,6 +324,46 @@ __device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Tile schedule of one CTA: the clusters are dealt round-robin to the gridDim.x CTAs of a batch tile.  When the last round
+// is short (nclusters % gridDim.x != 0) its clusters are SPLIT by epilogue steps (32-face halves of the batch tile) over
+// several CTAs, each of which repeats the cluster's (cheap) tensor-core pass but projects / rasterizes only its share of
+// the faces: the per-SM epilogue work, which bounds the raster flavour, then ends together instead of leaving most SMs idle
+// for a whole cluster time (510 clusters on 148 SMs: 3.5 cluster times instead of 4).
+struct TileWalk {
+  int tile, step0, step1;          // current cluster and its epilogue steps [step0, step1)
+  int g, j, nfullw, rem, split, nsteps, k;
+  __device__ TileWalk(int nclusters, int nsteps_) : g((int)gridDim.x), j((int)blockIdx.x), nsteps(nsteps_), k(-1) {
+    nfullw = nclusters / g;
+    rem = nclusters - nfullw * g;
+    split = (rem > 0) ? min(nsteps, g / rem) : 1;
+    if (split < 1) split = 1;
+    tile = step0 = step1 = 0;
+  }
+  __device__ bool next() {
+    ++k;
+    if (k < nfullw) {
+      tile = j + k * g;
+      step0 = 0;
+      step1 = nsteps;
+      return true;
+    }
+    if (k == nfullw && j < rem * split) {
+      tile = nfullw * g + j / split;
+      const int part = j - (j / split) * split;
+      step0 = part * nsteps / split;
+      step1 = (part + 1) * nsteps / split;
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float* v) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  *v = __uint_as_float(r);
+}
+
 // What the raster flavour draws into (fused params -> depth-map call).
 struct RasterTarget {
   const unsigned char* table;        // mesh table blob (device)
@@ -330,7 +378,8 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
                      const float* __restrict__ pose16, const int32_t* __restrict__ cluster_vert, ReconOut out,
                      RasterTarget target, int batch, int nver, int nch16, int nclusters, float im_size, unsigned flags) {
   using C = Cfg<kRaster>;
-  constexpr int kStages = C::kStages, kEpiWarps = C::kEpiWarps, kProducerWarp = C::kProducerWarp, kMmaWarp = C::kMmaWarp;
+  constexpr int kStages = C::kStages, kEpiWarps = C::kEpiWarps;
+  constexpr int kProducerWarp = C::kProducerWarp, kMmaWarp = C::kMmaWarp;
   extern __shared__ __align__(1024) unsigned char smem[];
   const SmemLayout L = smem_layout<kRaster>(nch16);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + L.bars);
@@ -338,6 +387,8 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int b0 = blockIdx.y * kN;
   const size_t tile_bytes = (size_t)3 * nch16 * kChunkBytes;
+  constexpr int kStepFaces = C::kStepFaces;                        // faces the epilogue warps read per step (raster: one stage)
+  const int nsteps = (min(kN, batch - b0) + kStepFaces - 1) / kStepFaces;
 
   // ---- one-time setup: barriers, TMEM, poses
   if (threadIdx.x == 0) {
@@ -383,8 +434,8 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
 #if FR_BASIS_EVICT_FIRST
       const uint64_t stream_policy = tc::l2_evict_first_policy();
 #endif
-      for (int tile = blockIdx.x; tile < nclusters; tile += gridDim.x) {
-        const unsigned char* src = tiles + (size_t)tile * tile_bytes;
+      for (TileWalk tw(nclusters, nsteps); tw.next();) {
+        const unsigned char* src = tiles + (size_t)tw.tile * tile_bytes;
         for (int sg = 0; sg < nch16; ++sg, ++it) {             // nch16 stages of 3 chunks per tile
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
           if (it == (uint32_t)kStages) load_b();               // the ring is full of basis stages: the MMAs need the operands now
@@ -407,7 +458,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     const uint64_t db1 = tc::make_smem_desc(smem_u32(smem + L.b1), 128u, L.sbo);
     const uint64_t da0 = tc::make_smem_desc(smem_u32(smem + L.raw), 2048u, 128u);   // same descriptor format for A
     uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < nclusters; tile += gridDim.x, ++tcount) {
+    for (TileWalk tw(nclusters, nsteps); tw.next(); ++tcount) {
       const uint32_t dbuf = tcount % kDBufs;
       mbar_wait(&bars->d_empty[dbuf], ((tcount / kDBufs) & 1u) ^ 1u);          // epilogue has drained this accumulator set
       tc_fence_after();
@@ -443,27 +494,31 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     }
   } else {
     // ================================================================== epilogue (warps 0 .. kEpiWarps-1)
-    constexpr int kFPW = C::kFacesPerWarp;                        // faces this warp drains per step
-    constexpr int kStepFaces = kFPW * (kEpiWarps / 4);            // faces all epilogue warps drain per step (raster: one stage)
-    const int qd = warp & 3, wq = warp >> 2;                      // TMEM lane quarter == warp % 4; face group within a step
+    constexpr int kFPW = C::kFacesPerWarp, kWPQ = C::kWarpsPerQuarter;
+    const int qd = warp & 3, wq = warp >> 2;                      // TMEM lane quarter == warp % 4; position within the quarter
     const int v = qd * 32 + lane;                                 // row of the tile == vertex slot of the cluster
     const uint32_t lane_field = (uint32_t)(qd * 32) << 16;
-    const int nfaces_tile = min(kN, batch - b0);                  // live faces of this batch tile (>= 1)
-    const int nsteps = (nfaces_tile + kStepFaces - 1) / kStepFaces;
     RasterSmem* rs = reinterpret_cast<RasterSmem*>(smem + L.raster);
     rc::TableView tv = {nullptr, nullptr, nullptr, 0};
-    if (kRaster) tv = rc::table_view(target.table);
+    if (kRaster) {
+      tv = rc::table_view(target.table);
+      if (threadIdx.x == 0) {
+        rs->queue.count = 0u;
+        rs->queue.next = 0u;
+      }
+    }
     const int npix = target.width * target.height;
     pdl_wait();                                                   // the prep kernel's poses (and the cleared keys)
     for (int i = threadIdx.x; i < kN * kPose16Stride; i += kEpiWarps * 32) s_pose[i] = pose16[(size_t)b0 * kPose16Stride + i];
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // the epilogue warps only
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < nclusters; tile += gridDim.x, ++tcount) {
+    for (TileWalk tw(nclusters, nsteps); tw.next(); ++tcount) {
+      const int tile = tw.tile;
       const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
       // vertex of this row, and whether this cluster is the one that writes it to the planar tensor
       int n = tile * kTileVerts + v;
       bool owner = n < nver;
-      if (cluster_vert != nullptr) {
+      if (cluster_vert != nullptr && out.planar != nullptr) {
         const int32_t raw = __ldg(cluster_vert + (size_t)tile * kTileVerts + v);
         n = (int)((uint32_t)raw & kVertIdMask);
         owner = raw >= 0 && ((uint32_t)raw & kVertOwner) != 0u;
@@ -479,28 +534,41 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       tc_fence_after();
       const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
 #pragma unroll 1
-      for (int step = 0; step < nsteps; ++step) {
-        const int jb = step * kStepFaces + wq * kFPW;             // first face (within the batch tile) of this warp
+      for (int step = tw.step0; step < tw.step1; ++step) {
+        // faces of this warp within the step: planar -- kFPW consecutive ones; raster -- wq, wq + kWPQ, ...
         float x[kFPW], y[kFPW], z[kFPW];
-        tmem_ld<kFPW>(d_addr + 0 * kN + jb, x);
-        tmem_ld<kFPW>(d_addr + 1 * kN + jb, y);
-        tmem_ld<kFPW>(d_addr + 2 * kN + jb, z);
+        if constexpr (kRaster) {
+#pragma unroll
+          for (int j = 0; j < kFPW; ++j) {
+            const int fl = min(wq + j * kWPQ, kStepFaces - 1);    // (clamped: the last round is short for some warps)
+            tmem_ld1(d_addr + 0 * kN + step * kStepFaces + fl, &x[j]);
+            tmem_ld1(d_addr + 1 * kN + step * kStepFaces + fl, &y[j]);
+            tmem_ld1(d_addr + 2 * kN + step * kStepFaces + fl, &z[j]);
+          }
+        } else {
+          const int jb = step * kStepFaces + wq * kFPW;
+          tmem_ld<kFPW>(d_addr + 0 * kN + jb, x);
+          tmem_ld<kFPW>(d_addr + 1 * kN + jb, y);
+          tmem_ld<kFPW>(d_addr + 2 * kN + jb, z);
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (step == nsteps - 1) {                                 // accumulators drained: the tensor pipe may reuse them
+        if (step == tw.step1 - 1) {                               // accumulators drained: the tensor pipe may reuse them
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
         }
 #pragma unroll
         for (int j = 0; j < kFPW; ++j) {
-          const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPose16Stride);
+          const int fl = kRaster ? wq + j * kWPQ : wq * kFPW + j;                       // face of the step
+          if (kRaster && fl >= kStepFaces) continue;                                    // (warp-uniform: the last round is short)
+          const int jf = step * kStepFaces + fl;                                        // face of the batch tile
+          const float4* pp = reinterpret_cast<const float4*>(s_pose + jf * kPose16Stride);
           const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
           const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
           float X, Y, Z;
           project_vertex(P, x[j], y[j], z[j], im_size, flags, &X, &Y, &Z);
-          if (store && b0 + jb + j < batch) store_planar(out.planar, b0 + jb + j, nver, n, X, Y, Z);
+          if (store && b0 + jf < batch) store_planar(out.planar, b0 + jf, nver, n, X, Y, Z);
           if (kRaster) {
-            const int fl = wq * kFPW + j;                         // face of the stage
             rs->stage.x[fl][v] = X;
             rs->stage.y[fl][v] = Y;
             rs->stage.z[fl][v] = Z;
@@ -510,9 +578,8 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         if (kRaster) {
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // stage (and triangle list) complete
           const int fb = b0 + step * kStepFaces;                                // first face of the stage
-          rc::raster_stage(rs->stage, rs->tris, rs->queue[warp], ntri_c, min(kStepFaces, batch - fb), warp, kEpiWarps, lane,
+          rc::raster_stage(rs->stage, rs->tris, rs->queue, ntri_c, min(kStepFaces, batch - fb), warp, kEpiWarps, lane, 1,
                            target.keys + (size_t)fb * npix, npix, target.width, target.height);
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // stage free again
         }
       }
     }
