@@ -20,6 +20,7 @@ FR_ROT_XYZ, FR_ROT_ZYX = 0x0, 0x1
 FR_YFLIP_S_Y_1, FR_YFLIP_S_Y, FR_YFLIP_NONE = 0x0, 0x2, 0x4
 FR_MEAN_PLANAR, FR_MEAN_INTERLEAVED = 0x0, 0x10
 FR_BASIS_PLANAR, FR_BASIS_INTERLEAVED = 0x0, 0x20
+FR_CLUSTER_TILES = 0x40
 FR_PARAMS_RAW = 0x100
 FR_NDIM_POSE = 7
 FR_SESSION_SLOTS = 2
@@ -37,17 +38,17 @@ SIGNATURES = {
     "fr_mesh_table_blob": (_vp, [_vp, ctypes.POINTER(_sz)]),
     "fr_mesh_table_clusters": (_i, [_vp]),
     "fr_mesh_table_vertex_slots": (_i, [_vp]),
-    "fr_packed_basis_bytes": (_sz, [_i, _i, _i, _vp]),
+    "fr_packed_basis_bytes": (_sz, [_i, _i, _i, _u, _vp]),
     "fr_pack_basis": (_i, [_vp, _vp, _vp, _i, _i, _i, _u, _vp, _vp, _vp]),
     "fr_recon_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fr_recon_project_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
     "fr_recon_project_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
-    "fr_render_workspace_bytes": (_sz, [_i, _i, _i, _i, _vp]),
+    "fr_render_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fr_render_depth_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "fr_render_depth_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fr_rendering_layer_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "fr_rendering_layer_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "fr_pipeline_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _vp]),
+    "fr_pipeline_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "fr_recon_render_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp, _vp]),
     "fr_session_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u, _i, ctypes.POINTER(_vp)]),
     "fr_session_destroy": (None, [_vp]),

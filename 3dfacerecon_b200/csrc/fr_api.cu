@@ -123,25 +123,36 @@ bool use_f16_forward(const BasisGeom& g, int batch, bool raster) {
   return recon_f16_fits(g, raster) && (ov == 3 || (ov == 0 && batch > 8));
 }
 
-// fr_recon_project_forward; with `target` the tensor-core kernel also rasterizes (fused call, use_f16_forward(g, batch, true)
-// must hold) and out.planar becomes optional.
+// Row tiles of the packed basis: the mesh table's clusters when the caller says so (FR_CLUSTER_TILES), else consecutive vertices.
+int tile_clusters(const fr_mesh_table* mesh, unsigned flags) { return (mesh != nullptr && (flags & FR_CLUSTER_TILES)) ? mesh->hdr.nclusters : 0; }
+
+// fr_recon_project_forward with a choice of outputs (out.planar / out.rec).  With `target` the tensor-core kernel also
+// rasterizes (cluster tiles required, use_f16_forward(g, batch, true) must hold) and `out` becomes optional.
+// clear_keys / clear_bytes: visibility keys to be cleared on the side (by the prep kernel on the tensor-core path).
 int recon_project_forward_impl(const float* params, const float* packed, const fr_mesh_table* mesh, const ReconOut& out,
-                               const f16::RasterTarget* target, int batch, int nver, int ndim_shape, int ndim_exp, float im_size,
-                               unsigned flags, void* workspace, size_t workspace_bytes, void* stream) {
+                               const f16::RasterTarget* target, unsigned long long* clear_keys, size_t clear_bytes, int batch, int nver,
+                               int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
   if (int rc = check_mesh(mesh, nver, -1)) return rc;
+  FR_REQUIRE(!(flags & FR_CLUSTER_TILES) || mesh != nullptr, "FR_CLUSTER_TILES needs the mesh table the basis was packed with");
   if (batch == 0) return FR_OK;
-  FR_REQUIRE(params && packed && (out.planar || target), "null pointer argument");
-  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp, mesh ? mesh->hdr.nclusters : 0);
+  FR_REQUIRE(params && packed && (out.planar || out.rec || target), "null pointer argument");
+  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp, tile_clusters(mesh, flags));
   const ReconWorkspace w = carve_recon(workspace, batch, g);
   if (int rc = check_workspace(workspace, workspace_bytes, w.bytes)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
+  const int32_t* cluster_vert = (flags & FR_CLUSTER_TILES) ? mesh_cluster_vert(mesh) : nullptr;
 
-  if (target != nullptr || use_f16_forward(g, batch, false))
-    return launch_recon_fwd_f16(params, packed, w.bsplit16, w.pose16, out, target, mesh_cluster_vert(mesh), batch, nver, g, im_size,
-                                flags, sm_count(), st);
+  if (target != nullptr || use_f16_forward(g, batch, false)) {
+    const bool fold = clear_keys != nullptr && clear_bytes % 16 == 0;     // the prep kernel clears the keys itself, 16 bytes at a time
+    if (clear_keys != nullptr && !fold) FR_CUDA(cudaMemsetAsync(clear_keys, 0, clear_bytes, st));
+    return launch_recon_fwd_f16(params, packed, w.bsplit16, w.pose16, out, target, cluster_vert, fold ? clear_keys : nullptr,
+                                fold ? clear_bytes : 0, batch, nver, g, im_size, flags, sm_count(), st);
+  }
+  if (clear_keys != nullptr) FR_CUDA(cudaMemsetAsync(clear_keys, 0, clear_bytes, st));
   recon_prep_kernel<<<ceil_div(g.kpad * bpad, 256), 256, 0, st>>>(params, dparam, batch, bpad, ndim_shape, ndim_exp,
                                                                  g.kpad, flags, im_size, w.coefT, w.pose);
   FR_LAUNCHED("recon_prep_kernel");
@@ -180,58 +191,64 @@ int launch_resolve(const unsigned long long* keys, const float* vertex, const fl
   return FR_OK;
 }
 
-// fr_render_depth_forward.  With a mesh table: visibility keys only in the workspace, the cluster rasterizer stages the
-// vertices in shared memory (raster_cluster.cuh).  Without: the generic path (16-byte vertex records in the workspace,
-// per-triangle gathers, raster.cuh).
+// Visibility pass on 16-byte vertex records: one thread per (triangle, face group); with a mesh table the triangles come
+// from it (integer ids, cluster order), else from the reference's float index tensor.
+int launch_keys(const float4* rec, const float* tri, const fr_mesh_table* mesh, unsigned long long* keys, int batch, int nver,
+                int ntri, int height, int width, bool dependent, cudaStream_t st) {
+  const bool table = mesh != nullptr;
+  const int nt = table ? mesh->hdr.ntri_slots : ntri;
+  if (nt == 0) return FR_OK;
+  const uint4* tv = table ? reinterpret_cast<const uint4*>(mesh->dev + mesh->hdr.off_tri_vid) : nullptr;
+  const unsigned gx = (unsigned)ceil_div(nt, kKeysThreads);
+#define FR_LAUNCH_KEYS(FPT, TABLE)                                                                                              \
+  FR_CUDA(launch_pdl(raster_keys_kernel<FPT, TABLE>, dim3(gx, ceil_div(batch, FPT)), dim3(kKeysThreads), 0, st, dependent, rec, tri, tv, \
+                     keys, batch, nver, nt, height, width))
+  if (batch >= 8) {
+    if (table) FR_LAUNCH_KEYS(8, true); else FR_LAUNCH_KEYS(8, false);
+  } else if (batch >= 3) {
+    if (table) FR_LAUNCH_KEYS(4, true); else FR_LAUNCH_KEYS(4, false);
+  } else {
+    if (table) FR_LAUNCH_KEYS(1, true); else FR_LAUNCH_KEYS(1, false);
+  }
+#undef FR_LAUNCH_KEYS
+  FR_LAUNCHED("raster_keys_kernel");
+  return FR_OK;
+}
+
+// fr_render_depth_forward: pack pass (vertex tensor -> 16-byte records, clears the keys), visibility pass, resolve pass.
+// With records_ready the workspace already holds this batch's vertex records and cleared visibility keys (written by the
+// fused call's reconstruction kernels); `vertex` may then be null unless normals or texture are requested.
 int render_depth_forward_impl(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                               float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
                               int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
-                              void* stream, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false}) {
+                              void* stream, bool records_ready, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false}) {
   if (int rc = check_render_dims(batch, nver, ntri, height, width)) return rc;
   if (int rc = check_mesh(mesh, nver, ntri)) return rc;
   if (batch == 0) return FR_OK;
-  FR_REQUIRE(vertex && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
+  FR_REQUIRE((vertex || records_ready) && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
+  FR_REQUIRE(vertex || (texture_image == nullptr && normal == nullptr), "normals / texture need the planar vertex tensor");
   FR_REQUIRE(texture_image == nullptr || texture != nullptr, "texture_image requested without a texture");
   FR_REQUIRE(texture_batch_stride == 0 || texture_batch_stride >= 3ll * nver, "texture_batch_stride must be 0 or >= 3*nver");
-  const size_t need = fr_render_workspace_bytes(batch, nver, height, width, mesh);
+  const size_t need = fr_render_workspace_bytes(batch, nver, height, width);
   if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* keys = static_cast<unsigned long long*>(workspace);
   const int npix = height * width;
+  float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) + key_bytes(batch, height, width));
   const bool pdl = pdl_enabled();   // dependent launches: the kernels call pdl_wait() before touching their predecessor's output
-  bool resolve_dependent = false;
-
-  if (ntri > 0 && mesh != nullptr && mesh->hdr.ntri_slots > 0) {
-    FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
-    FR_CUDA(cudaFuncSetAttribute(rc::raster_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rc::KernelSmem)));
-    const dim3 grid(mesh->hdr.nclusters, ceil_div(batch, rc::kStageFaces));
-    FR_CUDA(launch_pdl(rc::raster_cluster_kernel, grid, dim3(rc::kThreads), sizeof(rc::KernelSmem), st, false, vertex,
-                       static_cast<const unsigned char*>(mesh->dev), keys, batch, nver, height, width));
-    FR_LAUNCHED("raster_cluster_kernel");
-    resolve_dependent = pdl;
-  } else if (ntri > 0 && mesh == nullptr) {
-    float4* rec = reinterpret_cast<float4*>(static_cast<char*>(workspace) + key_bytes(batch, height, width));
-    raster_pack_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
-        vertex, rec, keys, nver, npix, width, height);   // also clears the visibility keys
-    FR_LAUNCHED("raster_pack_kernel");
-    const unsigned gx = (unsigned)ceil_div(ntri, kKeysThreads);
-    const float4* crec = rec;
-    if (batch >= 8)
-      FR_CUDA(launch_pdl(raster_keys_kernel<8>, dim3(gx, ceil_div(batch, 8)), dim3(kKeysThreads), 0, st, pdl, crec, tri, keys, batch, nver,
-                         ntri, height, width));
-    else if (batch >= 3)
-      FR_CUDA(launch_pdl(raster_keys_kernel<4>, dim3(gx, ceil_div(batch, 4)), dim3(kKeysThreads), 0, st, pdl, crec, tri, keys, batch, nver,
-                         ntri, height, width));
-    else
-      FR_CUDA(launch_pdl(raster_keys_kernel<1>, dim3(gx, batch), dim3(kKeysThreads), 0, st, pdl, crec, tri, keys, batch, nver, ntri,
-                         height, width));
-    FR_LAUNCHED("raster_keys_kernel");
-    resolve_dependent = pdl;
-  } else {   // nothing to draw (with no kernel in front, the resolve pass is a normal launch)
+  const bool draws = ntri > 0 && (mesh == nullptr || mesh->hdr.ntri_slots > 0);
+  if (draws) {
+    if (!records_ready) {   // the pack pass also clears the visibility keys
+      raster_pack_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
+          vertex, rec, keys, nver, npix, width, height);
+      FR_LAUNCHED("raster_pack_kernel");
+    }
+    if (int rc = launch_keys(rec, tri, mesh, keys, batch, nver, ntri, height, width, pdl, st)) return rc;
+  } else if (!records_ready) {
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   }
   return launch_resolve(keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver, ntri,
-                        npix, layer, resolve_dependent, st);
+                        npix, layer, pdl && draws, st);
 }
 
 }  // namespace
@@ -288,7 +305,8 @@ int fr_mesh_table_from_blob(const void* blob, size_t bytes, int device, fr_mesh_
   FR_REQUIRE(h.magic == kMeshMagic && h.version == kMeshVersion, "not a mesh table (magic %08x version %u)", h.magic, h.version);
   FR_REQUIRE(h.total_bytes == bytes && h.nclusters >= 0 && h.ntri_slots >= 0 && h.off_vert == sizeof(MeshTableHeader) &&
                  (size_t)h.off_vert + (size_t)h.nclusters * kClusterVerts * 4 <= h.off_tri_begin &&
-                 (size_t)h.off_tri_begin + ((size_t)h.nclusters + 1) * 4 <= h.off_tri && (size_t)h.off_tri + (size_t)h.ntri_slots * 8 <= bytes,
+                 (size_t)h.off_tri_begin + ((size_t)h.nclusters + 1) * 4 <= h.off_tri &&
+                 (size_t)h.off_tri + (size_t)h.ntri_slots * 8 <= h.off_tri_vid && (size_t)h.off_tri_vid + (size_t)h.ntri_slots * 16 <= bytes,
              "mesh table blob is inconsistent");
   const unsigned char* p = static_cast<const unsigned char*>(blob);
   uint32_t hash = 2166136261u;
@@ -318,18 +336,19 @@ int fr_mesh_table_clusters(const fr_mesh_table* m) { return m ? m->hdr.nclusters
 int fr_mesh_table_vertex_slots(const fr_mesh_table* m) { return m ? m->hdr.nvert_slots : 0; }
 
 // ------------------------------------------------------------------------------------------------ packing
-size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp, const fr_mesh_table* mesh) {
+size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp, unsigned layout_flags, const fr_mesh_table* mesh) {
   if (nver <= 0 || ndim_shape < 0 || ndim_exp < 0) return 0;
-  return basis_geom(nver, ndim_shape, ndim_exp, mesh ? mesh->hdr.nclusters : 0).bytes();
+  return basis_geom(nver, ndim_shape, ndim_exp, tile_clusters(mesh, layout_flags)).bytes();
 }
 
 int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, int nver, int ndim_shape, int ndim_exp,
                   unsigned layout_flags, const fr_mesh_table* mesh, float* packed, void* stream) {
   if (int rc = check_model_dims(0, nver, ndim_shape, ndim_exp)) return rc;
   if (int rc = check_mesh(mesh, nver, -1)) return rc;
+  FR_REQUIRE(!(layout_flags & FR_CLUSTER_TILES) || mesh != nullptr, "FR_CLUSTER_TILES needs a mesh table");
   FR_REQUIRE(mu && packed && (pc_shape || ndim_shape == 0) && (pc_exp || ndim_exp == 0), "null model pointer");
   FR_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 16 == 0, "packed basis must be 16-byte aligned");
-  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp, mesh ? mesh->hdr.nclusters : 0);
+  const BasisGeom g = basis_geom(nver, ndim_shape, ndim_exp, tile_clusters(mesh, layout_flags));
   const size_t total = (size_t)g.ntiles * 3 * g.kg * kTileVerts;
   pack_basis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       mu, pc_shape, pc_exp, nver, ndim_shape, ndim_exp, g.kg, g.ntiles, layout_flags, reinterpret_cast<float4*>(packed));
@@ -346,7 +365,8 @@ int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, i
   FR_LAUNCHED("basis_colscale_kernel");
   const size_t pieces = (size_t)g.nclusters * 3 * g.nch16 * 2 * kTileVerts;       // one 128-row tile per cluster (mesh_table.h)
   f16::pack_basis_f16_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(mu, pc_shape, pc_exp, scale, nver, ndim_shape, ndim_exp,
-                                                                              g.nch16, g.nclusters, layout_flags, mesh_cluster_vert(mesh),
+                                                                              g.nch16, g.nclusters, layout_flags,
+                                                                              (layout_flags & FR_CLUSTER_TILES) ? mesh_cluster_vert(mesh) : nullptr,
                                                                               reinterpret_cast<uint4*>(base + g.f16_offset()));
   FR_LAUNCHED("pack_basis_f16_kernel");
   // ... and the same pairs transposed for the backward contraction over the vertices
@@ -371,9 +391,9 @@ int fr_recon_project_forward(const float* params, const float* packed, const fr_
                              int nver, int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                              size_t workspace_bytes, void* stream) {
   FR_REQUIRE(batch == 0 || vertex_proj != nullptr, "null pointer argument");
-  const ReconOut out = {vertex_proj};
-  return recon_project_forward_impl(params, packed, mesh, out, nullptr, batch, nver, ndim_shape, ndim_exp, im_size, flags, workspace,
-                                    workspace_bytes, stream);
+  const ReconOut out = {vertex_proj, nullptr, 0, 0};
+  return recon_project_forward_impl(params, packed, mesh, out, nullptr, nullptr, 0, batch, nver, ndim_shape, ndim_exp, im_size, flags,
+                                    workspace, workspace_bytes, stream);
 }
 
 int fr_recon_project_backward(const float* params, const float* packed, const float* vertex_grad, float* params_grad,
@@ -440,10 +460,10 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ render
-size_t fr_render_workspace_bytes(int batch, int nver, int height, int width, const fr_mesh_table* mesh) {
+size_t fr_render_workspace_bytes(int batch, int nver, int height, int width) {
   if (batch <= 0 || nver <= 0 || height <= 0 || width <= 0) return 0;
-  return key_bytes(batch, height, width) +                                               // visibility keys
-         (mesh ? 0 : align_up(sizeof(float4) * (size_t)batch * nver, kAlign));           // generic path: vertex records
+  return key_bytes(batch, height, width) +                                   // visibility keys
+         align_up(sizeof(float4) * (size_t)batch * nver, kAlign);            // vertex records
 }
 
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
@@ -451,7 +471,7 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
                             int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
                             void* stream) {
   return render_depth_forward_impl(vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver,
-                                   ntri, height, width, mesh, workspace, workspace_bytes, stream);
+                                   ntri, height, width, mesh, workspace, workspace_bytes, stream, false);
 }
 
 int fr_render_depth_backward(const float* depth_grad, const float* tri, const float* tri_ind, float* vertex_grad,
@@ -480,7 +500,7 @@ int fr_rendering_layer_forward(const float* vertex, const float* tri, const floa
   FR_REQUIRE(batch <= 0 || (pncc && normalimg && maskimg && depthimg && texture), "null pointer argument");
   const LayerOut layer = {maskimg, im_gray, raw_depth, true};
   return render_depth_forward_impl(vertex, tri, texture, texture_batch_stride, depthimg, pncc, normalimg, tri_ind, batch, nver, ntri,
-                                   height, width, mesh, workspace, workspace_bytes, stream, layer);
+                                   height, width, mesh, workspace, workspace_bytes, stream, false, layer);
 }
 
 int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg_grad, const float* im_gray, const float* raw_depth,
@@ -502,18 +522,16 @@ int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg
 }
 
 // ------------------------------------------------------------------------------------------------ fused
-// Workspace of fr_recon_render_forward: [reconstruction | visibility keys (+ records without a mesh table) | planar
-// vertex buffer when the call cannot run fused and the caller does not want vertex_proj].
-static bool fused_possible(const fr_mesh_table* mesh, int batch, int nver, int ndim_shape, int ndim_exp) {
-  if (mesh == nullptr || mesh->hdr.ntri_slots == 0) return false;
+// Workspace of fr_recon_render_forward: [reconstruction | visibility keys | vertex records].
+// Does the call run with the rasterizer inside the reconstruction epilogue?  (cluster tiles, tensor-core batch size)
+static bool fused_raster(const fr_mesh_table* mesh, unsigned flags, int batch, int nver, int ndim_shape, int ndim_exp) {
+  if (mesh == nullptr || !(flags & FR_CLUSTER_TILES) || mesh->hdr.ntri_slots == 0) return false;
   return use_f16_forward(basis_geom(nver, ndim_shape, ndim_exp, mesh->hdr.nclusters), batch, true);
 }
 
-size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width,
-                                   const fr_mesh_table* mesh) {
+size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width) {
   if (batch <= 0 || nver <= 0) return 0;
-  const size_t planar = fused_possible(mesh, batch, nver, ndim_shape, ndim_exp) ? 0 : align_up(sizeof(float) * (size_t)batch * 3 * nver, kAlign);
-  return fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp) + fr_render_workspace_bytes(batch, nver, height, width, mesh) + planar;
+  return fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp) + fr_render_workspace_bytes(batch, nver, height, width);
 }
 
 int fr_recon_render_forward(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
@@ -526,41 +544,42 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
   if (batch == 0) return FR_OK;
   FR_REQUIRE(params && packed && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
   const size_t rb = fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp);
-  const size_t vb = fr_render_workspace_bytes(batch, nver, height, width, mesh);
-  const size_t need = fr_pipeline_workspace_bytes(batch, nver, ndim_shape, ndim_exp, height, width, mesh);
-  if (int rc = check_workspace(workspace, workspace_bytes, need)) return rc;
+  const size_t vb = fr_render_workspace_bytes(batch, nver, height, width);
+  if (int rc = check_workspace(workspace, workspace_bytes, rb + vb)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* rws = static_cast<char*>(workspace) + rb;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rws);
+  const size_t kbytes = sizeof(unsigned long long) * (size_t)batch * height * width;
+  const bool timed = stage_events != nullptr && stage_events[0] != nullptr;
   auto record = [&](int i) -> cudaError_t {
     return (stage_events != nullptr && stage_events[i] != nullptr) ? cudaEventRecord(static_cast<cudaEvent_t>(stage_events[i]), st)
                                                                    : cudaSuccess;
   };
-  if (fused_possible(mesh, batch, nver, ndim_shape, ndim_exp)) {
+  if (fused_raster(mesh, flags, batch, nver, ndim_shape, ndim_exp)) {
     // prep kernel (clears the keys) -> tensor-core reconstruction with the cluster rasterizer in its epilogue -> resolve
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(rws);
     const f16::RasterTarget target = {static_cast<const unsigned char*>(mesh->dev), keys, width, height};
-    const ReconOut out = {vertex_proj};
-    if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, batch, nver, ndim_shape, ndim_exp, im_size, flags,
-                                            workspace, rb, stream))
+    const ReconOut out = {vertex_proj, nullptr, 0, 0};
+    if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, keys, kbytes, batch, nver, ndim_shape, ndim_exp, im_size,
+                                            flags, workspace, rb, stream))
       return rc;
     FR_CUDA(record(0));
     const LayerOut layer = {nullptr, nullptr, nullptr, false};
-    const bool dependent = pdl_enabled() && !(stage_events != nullptr && stage_events[0] != nullptr);
     if (int rc = launch_resolve(keys, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height * width,
-                                layer, dependent, st))
+                                layer, pdl_enabled() && !timed, st))
       return rc;
     FR_CUDA(record(1));
     return FR_OK;
   }
-  // small batches / no mesh table: reconstruction into a planar tensor, then the stand-alone rasterizer
-  float* planar = vertex_proj ? vertex_proj : reinterpret_cast<float*>(rws + vb);
-  const ReconOut out = {planar};
-  if (int rc = recon_project_forward_impl(params, packed, mesh, out, nullptr, batch, nver, ndim_shape, ndim_exp, im_size, flags,
-                                          workspace, rb, stream))
+  // The reconstruction kernels write the rasterizer's vertex records straight into the render workspace (same carve-up as
+  // render_depth_forward_impl: keys first, records after) and clear its keys, so the repack pass over vertex_proj disappears;
+  // vertex_proj itself is optional here.
+  const ReconOut out = {vertex_proj, reinterpret_cast<float4*>(rws + key_bytes(batch, height, width)), width, height};
+  if (int rc = recon_project_forward_impl(params, packed, mesh, out, nullptr, keys, kbytes, batch, nver, ndim_shape, ndim_exp, im_size,
+                                          flags, workspace, rb, stream))
     return rc;
   FR_CUDA(record(0));
-  if (int rc = render_depth_forward_impl(planar, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height, width,
-                                         mesh, rws, vb, stream))
+  if (int rc = render_depth_forward_impl(vertex_proj, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height, width,
+                                         mesh, rws, vb, stream, true))
     return rc;
   FR_CUDA(record(1));
   return FR_OK;
@@ -631,10 +650,8 @@ int fr_session_create(const float* mu, const float* pc_shape, const float* pc_ex
     session_free(s);
     return mrc;
   }
-  // the workspace must cover both dispatch classes (small batches run un-fused and need a planar vertex buffer)
-  s->ws_bytes = std::max(fr_pipeline_workspace_bytes(max_batch, nver, ndim_shape, ndim_exp, height, width, s->mesh),
-                         fr_pipeline_workspace_bytes(std::min(max_batch, 8), nver, ndim_shape, ndim_exp, height, width, s->mesh));
-  chk(cudaMalloc(&s->packed, fr_packed_basis_bytes(nver, ndim_shape, ndim_exp, s->mesh)), "cudaMalloc(packed)");
+  s->ws_bytes = fr_pipeline_workspace_bytes(max_batch, nver, ndim_shape, ndim_exp, height, width);
+  chk(cudaMalloc(&s->packed, fr_packed_basis_bytes(nver, ndim_shape, ndim_exp, flags, s->mesh)), "cudaMalloc(packed)");
   chk(cudaMalloc(&s->tri, sizeof(float) * 3 * (size_t)ntri), "cudaMalloc(tri)");
   for (fr_slot& sl : s->slot) {
     chk(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");

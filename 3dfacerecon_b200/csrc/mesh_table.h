@@ -24,7 +24,7 @@ namespace fr {
 constexpr int kClusterVerts = 128;   // == kTileVerts (TMEM lanes of one reconstruction tile)
 constexpr int kClusterTris = 256;    // local triangle ids fit 8 bits
 constexpr uint32_t kMeshMagic = 0x544D5246u;   // "FRMT"
-constexpr uint32_t kMeshVersion = 1u;
+constexpr uint32_t kMeshVersion = 2u;
 constexpr uint32_t kVertOwner = 0x40000000u;   // cluster_vert flag: this cluster writes the vertex to planar outputs
 constexpr uint32_t kVertIdMask = 0x00FFFFFFu;  // nver <= 2^24 (float triangle indices are exact up to there)
 
@@ -33,6 +33,8 @@ constexpr uint32_t kVertIdMask = 0x00FFFFFFu;  // nver <= 2^24 (float triangle i
 //   cluster_vert  int32 [nclusters][128]   vertex id | kVertOwner, -1 = unused slot
 //   tri_begin     int32 [nclusters + 1]    first triangle entry of each cluster
 //   tri_entry     uint2 [ntri_slots]       { l1 | l2 << 8 | l3 << 16 (slots within the cluster), original triangle index }
+//   tri_vid       uint4 [ntri_slots]       { p1, p2, p3 (vertex ids, pre-validated), original triangle index }: the same
+//                                          triangles in the same (cluster) order for kernels that gather by vertex id
 struct MeshTableHeader {
   uint32_t magic, version;
   int32_t nver, ntri;
@@ -42,7 +44,8 @@ struct MeshTableHeader {
   int32_t nvert_slots;         // used cluster_vert slots (vertices counted once per member cluster)
   uint32_t off_vert, off_tri_begin, off_tri, total_bytes;
   uint32_t hash;               // FNV-1a of everything behind the header
-  uint32_t pad[3];
+  uint32_t off_tri_vid;
+  uint32_t pad[2];
 };
 static_assert(sizeof(MeshTableHeader) == 64, "header is 64 bytes");
 
@@ -368,11 +371,13 @@ class MeshTableBuilder {
     h.off_vert = sizeof(MeshTableHeader);
     h.off_tri_begin = h.off_vert + (uint32_t)ncl * kClusterVerts * 4u;
     h.off_tri = (h.off_tri_begin + (uint32_t)(ncl + 1) * 4u + 15u) / 16u * 16u;
-    h.total_bytes = (h.off_tri + (uint32_t)nvalid_ * 8u + 255u) / 256u * 256u;
+    h.off_tri_vid = (h.off_tri + (uint32_t)nvalid_ * 8u + 15u) / 16u * 16u;
+    h.total_bytes = (h.off_tri_vid + (uint32_t)nvalid_ * 16u + 255u) / 256u * 256u;
     std::vector<unsigned char> blob(h.total_bytes, 0);
     int32_t* cv = reinterpret_cast<int32_t*>(blob.data() + h.off_vert);
     int32_t* tb = reinterpret_cast<int32_t*>(blob.data() + h.off_tri_begin);
     uint32_t* te = reinterpret_cast<uint32_t*>(blob.data() + h.off_tri);
+    uint32_t* tq = reinterpret_cast<uint32_t*>(blob.data() + h.off_tri_vid);
     std::fill(cv, cv + (size_t)ncl * kClusterVerts, -1);
     std::vector<int> slot(nver_, -1);
     int nslots = 0, max_tris = 0;
@@ -398,6 +403,11 @@ class MeshTableBuilder {
         const int t = ts[i];
         te[2 * ((size_t)cuts_[c] + i)] = (uint32_t)slot[tv_[3 * t]] | ((uint32_t)slot[tv_[3 * t + 1]] << 8) | ((uint32_t)slot[tv_[3 * t + 2]] << 16);
         te[2 * ((size_t)cuts_[c] + i) + 1] = (uint32_t)orig_[t];
+        uint32_t* q4 = tq + 4 * ((size_t)cuts_[c] + i);
+        q4[0] = (uint32_t)tv_[3 * t];
+        q4[1] = (uint32_t)tv_[3 * t + 1];
+        q4[2] = (uint32_t)tv_[3 * t + 2];
+        q4[3] = (uint32_t)orig_[t];
       }
       max_tris = std::max(max_tris, cuts_[c + 1] - cuts_[c]);
     }

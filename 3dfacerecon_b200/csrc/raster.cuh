@@ -97,17 +97,21 @@ __device__ __forceinline__ void raster_draw(const float4& r1, const float4& r2, 
 // the back) so that Phase B gathers the records and runs the FP64 edge setup + inside tests + atomicMax with every lane
 // busy and without a divergent pixel loop in the single-pixel warps.
 // All record indices are 32-bit: the API guarantees batch * 3 * nver < 2^31.
-template <int FPT>
 #ifndef FR_KEYS_MINB
 #define FR_KEYS_MINB 1
 #endif
 
+// kTable: the triangles come from a mesh table (mesh_table.h) instead of the reference's float index tensor: one 16-byte
+// load of pre-validated integer vertex ids per triangle, in CLUSTER order -- the triangles of a block touch one compact
+// patch of vertices whatever the numbering of the mesh (the three float loads + conversions + range checks of the generic
+// flavour, and its dependence on the generator's triangle order, go away).  tri_vid[s] = {p1, p2, p3, original index}.
+template <int FPT, bool kTable>
 __global__ void __launch_bounds__(kKeysThreads, FR_KEYS_MINB)
-raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri, unsigned long long* __restrict__ keys,
-                   int batch, int nver, int ntri, int height, int width) {
+raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri, const uint4* __restrict__ tri_vid,
+                   unsigned long long* __restrict__ keys, int batch, int nver, int ntri, int height, int width) {
   __shared__ uint2 q_box[kKeysThreads * FPT];           // biased bbox (lo_min, hi_max)
   __shared__ unsigned short q_id[kKeysThreads * FPT];   // (local triangle << 3) | face slot
-  __shared__ int s_idx[3][kKeysThreads];
+  __shared__ int s_idx[4][kKeysThreads];                // three vertex ids + the triangle's index in the reference's order
   __shared__ unsigned q_count;                            // single-pixel survivors | multi-pixel survivors << 16
   static_assert(FPT <= 8, "face slot is packed into 3 bits");
 
@@ -117,16 +121,26 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
   pdl_wait();      // records and cleared keys of the producing kernel (pack pass or reconstruction epilogue) are complete
   __syncthreads();
 
-  const int t = blockIdx.x * kKeysThreads + tid;
+  const int t = blockIdx.x * kKeysThreads + tid;          // ntri = triangles (generic) / table entries (kTable)
   const int b0 = blockIdx.y * FPT;
-  int p1 = 0, p2 = 0, p3 = 0;
+  int p1 = 0, p2 = 0, p3 = 0, torig = t;
   bool valid = t < ntri;
-  if (valid)
-    valid = tri_vertex_index(__ldg(tri + t), nver, &p1) && tri_vertex_index(__ldg(tri + ntri + t), nver, &p2) &&
-            tri_vertex_index(__ldg(tri + 2 * (size_t)ntri + t), nver, &p3);
+  if (valid) {
+    if (kTable) {
+      const uint4 e = __ldg(tri_vid + t);
+      p1 = (int)e.x;
+      p2 = (int)e.y;
+      p3 = (int)e.z;
+      torig = (int)e.w;
+    } else {
+      valid = tri_vertex_index(__ldg(tri + t), nver, &p1) && tri_vertex_index(__ldg(tri + ntri + t), nver, &p2) &&
+              tri_vertex_index(__ldg(tri + 2 * (size_t)ntri + t), nver, &p3);
+    }
+  }
   s_idx[0][tid] = p1;
   s_idx[1][tid] = p2;
   s_idx[2][tid] = p3;
+  s_idx[3][tid] = torig;
 
   const uint32_t limit = (uint32_t)width | ((uint32_t)height << 16);
   uint32_t e1[FPT], e2[FPT], e3[FPT];
@@ -164,7 +178,6 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
   const unsigned counts = q_count;
   const int n_single = (int)(counts & 0xFFFFu), n_multi = (int)(counts >> 16);
   const int npix = height * width;
-  const int tri0 = blockIdx.x * kKeysThreads;
   // ---- phase B: one work list (one-pixel survivors first, then the others), one survivor per thread and trip: the lanes left
   // over when the one-pixel class runs out start on the multi-pixel class instead of idling through a partial trip
   // (measured against two separate loops with two one-pixel survivors per thread: 55.1 -> 53.9 us)
@@ -178,7 +191,7 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
     const unsigned fb = (unsigned)b * (unsigned)nver;
     const float4 r1 = __ldg(rec + (fb + (unsigned)s_idx[0][tl])), r2 = __ldg(rec + (fb + (unsigned)s_idx[1][tl])),
                  r3 = __ldg(rec + (fb + (unsigned)s_idx[2][tl]));
-    raster_draw(r1, r2, r3, bx, tri0 + tl, keys + (size_t)b * npix, width);
+    raster_draw(r1, r2, r3, bx, s_idx[3][tl], keys + (size_t)b * npix, width);
   }
 }
 

@@ -6,10 +6,9 @@
 //
 // Unit of work: one CLUSTER of the mesh table (mesh_table.h: <= 128 vertices, <= 256 triangles with 8-bit local
 // indices) x up to 32 faces.  The projected vertices of the cluster are written ONCE per face into a shared-memory
-// stage -- structure of arrays [face][vertex slot]: x, y, z and the one-word snap code -- either by the tensor-core
-// reconstruction epilogue that has just computed them (recon_f16.cuh, the fused params -> depth-map path: the
-// vertices never travel through global memory) or by one gather from the planar vertex tensor
-// (raster_cluster_kernel below, the stand-alone render_depth op).  A stage is then rasterized in two block-wide phases:
+// stage -- structure of arrays [face][vertex slot]: x, y, z and the one-word snap code -- by the tensor-core
+// reconstruction epilogue that has just computed them (recon_f16.cuh, the FR_CLUSTER_TILES flavour of the fused call: the
+// vertices never travel through global memory).  A stage is then rasterized in two block-wide phases:
 //   cull   every warp walks (32 triangles) x (8 faces) items with lane = triangle: three conflict-free shared loads of
 //          snap codes per face and a handful of packed integer operations decide the reference's bounding-box cull
 //          (:276-282); the survivors' 16-bit ids (local triangle, face) go to ONE block-wide list, one-pixel boxes from
@@ -261,67 +260,6 @@ __device__ __forceinline__ void raster_stage(const Stage<NF>& st, const TriList&
   if (warp == 0 && lane == 0) {                  // visible to the next stage's cull through the caller's stage barrier
     q.count = 0u;
     q.next = 0u;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------- stand-alone op
-// render_depth on a planar vertex tensor [B,3,N] with a mesh table: grid (cluster stride loop, 32-face group).
-// Block = kWarps warps; every thread stages vertex slot (tid % 128) for the faces (tid / 128), (tid / 128) + W/4, ...
-constexpr int kWarps = 16;
-constexpr int kThreads = kWarps * 32;
-constexpr int kStageFaces = 32;
-struct KernelSmem {
-  Stage<kStageFaces> stage;
-  TriList tris;
-  StageQueue queue;
-};
-
-__global__ void __launch_bounds__(kThreads, 2)
-raster_cluster_kernel(const float* __restrict__ vertex, const unsigned char* __restrict__ table, unsigned long long* __restrict__ keys,
-                      int batch, int nver, int height, int width) {
-  extern __shared__ __align__(16) unsigned char rc_smem[];
-  KernelSmem& s = *reinterpret_cast<KernelSmem*>(rc_smem);
-  const TableView tv = table_view(table);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0 = blockIdx.y * kStageFaces;
-  const int nfaces = min(kStageFaces, batch - b0);
-  const int npix = height * width;
-  const int v = tid & (kClusterVerts - 1), fsub = tid >> 7;        // 4 faces in flight per pass of the block
-  if (tid == 0) {
-    s.queue.count = 0u;
-    s.queue.next = 0u;
-  }
-  pdl_trigger();
-  pdl_wait();       // the visibility keys are cleared / the vertex tensor is written by the preceding work
-  for (int c = blockIdx.x; c < tv.nclusters; c += gridDim.x) {
-    const int tb = __ldg(tv.tri_begin + c), ntri_c = __ldg(tv.tri_begin + c + 1) - tb;
-    if (ntri_c == 0) continue;                                      // a cluster of loose vertices: nothing to draw
-    load_tri_list(s.tris, tv.tri_entry + tb, ntri_c, tid, kThreads);
-    const int vid_raw = __ldg(tv.cluster_vert + (size_t)c * kClusterVerts + v);
-    const int vid = vid_raw < 0 ? -1 : (int)((uint32_t)vid_raw & kVertIdMask);
-    constexpr int kPass = kThreads / kClusterVerts;                 // faces per pass
-    constexpr int kUnroll = kStageFaces / kPass;
-    float x[kUnroll], y[kUnroll], z[kUnroll];
-#pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-      const int f = fsub + j * kPass;
-      const bool ok = vid >= 0 && f < nfaces;
-      const float* vb = vertex + (size_t)(b0 + (ok ? f : 0)) * 3 * nver + (ok ? vid : 0);
-      x[j] = ok ? __ldg(vb) : 0.0f;
-      y[j] = ok ? __ldg(vb + nver) : 0.0f;
-      z[j] = ok ? __ldg(vb + 2 * (size_t)nver) : 0.0f;
-    }
-#pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-      const int f = fsub + j * kPass;
-      s.stage.x[f][v] = x[j];
-      s.stage.y[f][v] = y[j];
-      s.stage.z[f][v] = z[j];
-      s.stage.code[f][v] = fr_snap_code(x[j], y[j], width, height);
-    }
-    __syncthreads();
-    raster_stage(s.stage, s.tris, s.queue, ntri_c, nfaces, warp, kWarps, lane, 0, keys + (size_t)b0 * npix, npix, width, height);
-    __syncthreads();
   }
 }
 

@@ -142,11 +142,14 @@ recon_prep_kernel(const float* __restrict__ params, int dparam, int batch, int b
   }
 }
 
-// Where the forward kernels put a projected vertex: `planar` is the reference's vertex_proj [B,3,N] tensor
-// (nets/network.py:171).  (The fused params -> depth-map call needs no such tensor: the tensor-core kernel hands the
-// vertices to its own rasterizer stage in shared memory, recon_f16.cuh.)
+// Where the forward kernels put a projected vertex.  `planar` is the reference's vertex_proj [B,3,N] tensor
+// (nets/network.py:171); `rec` is the rasterizer's 16-byte vertex record array [B][N] {x, y, z, snap code}
+// (raster.cuh): the fused params -> depth-map call has the reconstruction epilogue write the records directly, which
+// saves the rasterizer's repack pass over the vertex tensor.  Either may be null.
 struct ReconOut {
   float* planar;
+  float4* rec;
+  int width, height;   // image size the snap codes refer to (rec != nullptr)
 };
 
 // Projection + y flip of one reconstructed vertex (nets/network.py:163-169).
@@ -167,11 +170,16 @@ __device__ __forceinline__ void store_planar(float* __restrict__ planar, int b, 
   o[(size_t)nver + n] = Y;
   o[2 * (size_t)nver + n] = Z;
 }
+__device__ __forceinline__ void store_vertex(const ReconOut& out, int b, int nver, int n, float X, float Y, float Z) {
+  if (out.planar != nullptr) store_planar(out.planar, b, nver, n, X, Y, Z);
+  if (out.rec != nullptr)
+    out.rec[(size_t)b * nver + n] = make_float4(X, Y, Z, __uint_as_float(fr_snap_code(X, Y, out.width, out.height)));
+}
 __device__ __forceinline__ void project_store(const float* __restrict__ P, float x, float y, float z, float im_size,
                                               unsigned flags, const ReconOut& out, int b, int nver, int n) {
   float X, Y, Z;
   project_vertex(P, x, y, z, im_size, flags, &X, &Y, &Z);
-  store_planar(out.planar, b, nver, n, X, Y, Z);
+  store_vertex(out, b, nver, n, X, Y, Z);
 }
 
 // ---------------------------------------------------------------------------------------------- forward (SIMT)

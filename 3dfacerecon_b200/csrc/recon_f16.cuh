@@ -213,31 +213,28 @@ pack_basis_f16_kernel(const float* __restrict__ mu, const float* __restrict__ pc
 }
 
 // ---------------------------------------------------------------------------------------------- prep
-// One CTA per (padded) face: coefficients with the column scale undone, a per-face power-of-two scale 2^t that brings the
+// One CTA per (padded) face (+ optional key-clearing CTAs behind them): coefficients with the column scale undone, a per-face power-of-two scale 2^t that brings the
 // largest of them into [2^13, 2^14), split into fp16 b0 + b1 and stored per 64-face batch tile in the canonical K-major
 // layout [b0|b1][8-face group][k / 8][face % 8][k % 8] the kernel bulk-copies; pose16 = 2^-t f.R | t3d.
 __global__ void __launch_bounds__(256)
 recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict__ inv_scale, int dparam, int batch, int ks,
                       int ke, int kpad16, unsigned flags, float im_size, unsigned char* __restrict__ bsplit,
-                      float* __restrict__ pose16, unsigned long long* __restrict__ keys, int npix) {
+                      float* __restrict__ pose16, int bpad, unsigned long long* __restrict__ keys, size_t key_vecs) {
   __shared__ float red[8];
   __shared__ float s_pose[kPoseStride];
   __shared__ double s_sc[6];
   pdl_trigger();                                   // the reconstruction kernel may become resident (it waits before reading our output)
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const bool live = b < batch;
-  // fused call: this CTA also clears the visibility keys of its face for the rasterizer stage of the next kernel
-  // (which waits for this grid before its first atomicMax)
-  if (keys != nullptr && live) {
-    unsigned long long* kb = keys + (size_t)b * npix;
-    int i = tid;
-    if ((npix & 1) == 0) {        // 16-byte stores (a face's keys are 16-byte aligned when npix is even)
-      uint4* kv = reinterpret_cast<uint4*>(kb);
-      for (; i < npix / 2; i += 256) kv[i] = make_uint4(0u, 0u, 0u, 0u);
-    } else {
-      for (; i < npix; i += 256) kb[i] = 0ull;
-    }
+  const int tid = threadIdx.x;
+  // fused call: the CTAs behind the (padded) faces only clear the visibility keys for the rasterizer that follows, 16 bytes
+  // per store (the consumer kernels wait for this whole grid before their first atomicMax)
+  if ((int)blockIdx.x >= bpad) {
+    uint4* kv = reinterpret_cast<uint4*>(keys);
+    const size_t stride = (size_t)(gridDim.x - bpad) * 256;
+    for (size_t i = (size_t)((int)blockIdx.x - bpad) * 256 + tid; i < key_vecs; i += stride) kv[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
   }
+  const int b = blockIdx.x;
+  const bool live = b < batch;
   float cmax = 0.0f;
   for (int k = tid; k < kpad16; k += 256) {
     float v = 0.0f;
@@ -518,12 +515,12 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       // vertex of this row, and whether this cluster is the one that writes it to the planar tensor
       int n = tile * kTileVerts + v;
       bool owner = n < nver;
-      if (cluster_vert != nullptr && out.planar != nullptr) {
+      if (cluster_vert != nullptr && (out.planar != nullptr || out.rec != nullptr)) {
         const int32_t raw = __ldg(cluster_vert + (size_t)tile * kTileVerts + v);
         n = (int)((uint32_t)raw & kVertIdMask);
         owner = raw >= 0 && ((uint32_t)raw & kVertOwner) != 0u;
       }
-      const bool store = out.planar != nullptr && owner;
+      const bool store = (out.planar != nullptr || out.rec != nullptr) && owner;
       int ntri_c = 0;
       if (kRaster) {                                              // the cluster's triangle list (the previous tile's last
         const int tb = __ldg(tv.tri_begin + tile);                // barrier has released tris and stage)
@@ -567,7 +564,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
           const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
           float X, Y, Z;
           project_vertex(P, x[j], y[j], z[j], im_size, flags, &X, &Y, &Z);
-          if (store && b0 + jf < batch) store_planar(out.planar, b0 + jf, nver, n, X, Y, Z);
+          if (store && b0 + jf < batch) store_vertex(out, b0 + jf, nver, n, X, Y, Z);
           if (kRaster) {
             rs->stage.x[fl][v] = X;
             rs->stage.y[fl][v] = Y;
@@ -606,20 +603,23 @@ inline bool recon_f16_fits(const BasisGeom& g, bool raster) {
   return (raster ? f16::smem_layout<true>(g.nch16).total : f16::smem_layout<false>(g.nch16).total) <= 227u * 1024u;
 }
 
-// Prep + tensor-core forward.  target == nullptr: the planar flavour (out.planar required); else the raster flavour
-// (fused call: the prep kernel clears the visibility keys, the epilogue rasterizes; out.planar optional).
+// Prep + tensor-core forward.  target == nullptr: the planar flavour (out.planar and / or out.rec); else the raster flavour
+// (the epilogue rasterizes; out optional; needs cluster tiles).  clear_keys / clear_bytes: visibility keys the prep kernel
+// clears on the side (bytes must be a multiple of 16), or nullptr.
 // cluster_vert: device pointer to the mesh table's vertex lists the basis was packed with, or null (consecutive tiles).
 inline int launch_recon_fwd_f16(const float* params, const float* packed, void* bsplit, float* pose16, ReconOut out,
-                                const f16::RasterTarget* target, const int32_t* cluster_vert, int batch, int nver,
-                                const BasisGeom& g, float im_size, unsigned flags, int nsm, cudaStream_t st) {
+                                const f16::RasterTarget* target, const int32_t* cluster_vert, unsigned long long* clear_keys,
+                                size_t clear_bytes, int batch, int nver, const BasisGeom& g, float im_size, unsigned flags, int nsm,
+                                cudaStream_t st) {
   static_assert(f16::kN == kBatchPad, "batch tiles are kBatchPad faces");
   const unsigned char* base = reinterpret_cast<const unsigned char*>(packed);
   const float* inv_scale = reinterpret_cast<const float*>(base + g.scale_offset());
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + g.ks + g.ke;
-  f16::recon_prep_f16_kernel<<<bpad, 256, 0, st>>>(params, inv_scale, dparam, batch, g.ks, g.ke, g.kpad16, flags, im_size,
-                                                  static_cast<unsigned char*>(bsplit), pose16, target ? target->keys : nullptr,
-                                                  target ? target->width * target->height : 0);   // normal launch: waits for everything before
+  const int nclear = clear_keys ? 2 * nsm : 0;
+  f16::recon_prep_f16_kernel<<<bpad + nclear, 256, 0, st>>>(params, inv_scale, dparam, batch, g.ks, g.ke, g.kpad16, flags, im_size,
+                                                           static_cast<unsigned char*>(bsplit), pose16, bpad, clear_keys,
+                                                           clear_bytes / 16);   // normal launch: waits for everything before
   FR_LAUNCHED("recon_prep_f16_kernel");
   const int nbt = ceil_div(batch, f16::kN);
   int ctas = nsm / nbt;

@@ -66,6 +66,8 @@ class MeshTable:
         out["cluster_vert"] = b[off_v:off_v + ncl * 128 * 4].view(np.int32).reshape(ncl, 128)
         out["tri_begin"] = b[off_b:off_b + (ncl + 1) * 4].view(np.int32)
         out["tri_entry"] = b[off_t:off_t + nslots * 8].view(np.uint32).reshape(nslots, 2)
+        off_q = int(h[13])
+        out["tri_vid"] = b[off_q:off_q + nslots * 16].view(np.uint32).reshape(nslots, 4)
         return out
 
     def close(self):

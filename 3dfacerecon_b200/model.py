@@ -34,7 +34,7 @@ class DeviceModel:
     """Packed basis + triangles + textures of one 3DMM on one GPU."""
 
     def __init__(self, model: dict, device="cuda:0", convention: str = "network", validate_tri: bool = True,
-                 tri_base: int | None = None, cache_dir: str | None = None):
+                 tri_base: int | None = None, cache_dir: str | None = None, cluster_tiles: bool = False):
         if convention not in _CONVENTIONS:
             raise ValueError("convention must be one of %s" % sorted(_CONVENTIONS))
         self.device = torch.device(device)
@@ -42,6 +42,10 @@ class DeviceModel:
             raise ValueError("DeviceModel needs a CUDA device: there is no CPU path")
         self.convention = convention
         self.pack_flags, self.run_flags = _CONVENTIONS[convention]
+        if cluster_tiles:       # FR_CLUSTER_TILES (include/facerecon_b200.h): the fused call rasterizes inside the reconstruction epilogue
+            self.pack_flags |= _lib.FR_CLUSTER_TILES
+            self.run_flags |= _lib.FR_CLUSTER_TILES
+        self.cluster_tiles = bool(cluster_tiles)
         mu = np.ascontiguousarray(np.asarray(model["mu"], np.float32).reshape(-1))
         pc_shape = np.ascontiguousarray(model["pc_shape"], np.float32)
         pc_exp = np.ascontiguousarray(model["pc_exp"], np.float32)
@@ -80,7 +84,7 @@ class DeviceModel:
             # reading the 500 MB packed image back from disk).
             self.mesh = self._mesh_table(tri, mu, cache_dir)
             _mesh.register(self.tri, self.mesh)
-            nbytes = lib().fr_packed_basis_bytes(self.nver, self.ndim_shape, self.ndim_exp, self.mesh.handle)
+            nbytes = lib().fr_packed_basis_bytes(self.nver, self.ndim_shape, self.ndim_exp, self.pack_flags, self.mesh.handle)
             self.packed = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
             d_mu = torch.from_numpy(mu).to(self.device)
             d_ps = torch.from_numpy(pc_shape).to(self.device)

@@ -106,7 +106,7 @@ class _RenderingLayer(torch.autograd.Function):
         pncc, normalimg, maskimg, depthimg, raw, tri_ind = new(3), new(3), new(1), new(1), new(1), new(1)
         mesh_h = _mesh_handle(tri, N, ver, mesh)
         with torch.cuda.device(dev):
-            ws = _workspace(dev, lib().fr_render_workspace_bytes(B, N, height, width, mesh_h))
+            ws = _workspace(dev, lib().fr_render_workspace_bytes(B, N, height, width))
             check(lib().fr_rendering_layer_forward(ver.data_ptr(), tri.data_ptr(), tex_ptr, tex_stride,
                                                    None if gray is None else gray.data_ptr(), pncc.data_ptr(), normalimg.data_ptr(),
                                                    maskimg.data_ptr(), depthimg.data_ptr(), raw.data_ptr(), tri_ind.data_ptr(), B, N, T,

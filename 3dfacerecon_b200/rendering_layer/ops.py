@@ -97,7 +97,7 @@ class _RenderDepth(torch.autograd.Function):
         normal = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
         tri_ind = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            nbytes = lib().fr_render_workspace_bytes(B, N, H, W, mesh_h)
+            nbytes = lib().fr_render_workspace_bytes(B, N, H, W)
             ws = _workspace(dev, nbytes)
             check(lib().fr_render_depth_forward(ver.data_ptr(), tri.data_ptr(), tex_ptr, tex_stride, depth.data_ptr(),
                                                 texture_image.data_ptr(), normal.data_ptr(), tri_ind.data_ptr(), B, N, T,

@@ -222,8 +222,8 @@ def run_ours(args):
     tri_ind = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
     rbytes = lib.fr_recon_workspace_bytes(B, nver, ks, ke)
     mesh = dm.mesh.handle
-    ws = torch.empty(max(lib.fr_pipeline_workspace_bytes(B, nver, ks, ke, H, W, mesh),
-                         rbytes + lib.fr_render_workspace_bytes(B, nver, H, W, mesh)), dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(lib.fr_pipeline_workspace_bytes(B, nver, ks, ke, H, W),
+                         rbytes + lib.fr_render_workspace_bytes(B, nver, H, W)), dtype=torch.uint8, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
@@ -381,7 +381,7 @@ def run_ours(args):
             p3 = torch.from_numpy(synth.sample_params_constrained(B3, seed=3)).to(dev)
             d3 = torch.empty((B3, H, W, 1), dtype=torch.float32, device=dev)
             t3 = torch.empty((B3, H, W, 1), dtype=torch.float32, device=dev)
-            ws3 = torch.empty(lib.fr_pipeline_workspace_bytes(B3, nver, ks, ke, H, W, mesh), dtype=torch.uint8, device=dev)
+            ws3 = torch.empty(lib.fr_pipeline_workspace_bytes(B3, nver, ks, ke, H, W), dtype=torch.uint8, device=dev)
 
             def fwd3():
                 check(lib.fr_recon_render_forward(p3.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), mesh, None, d3.data_ptr(),

@@ -52,6 +52,11 @@ extern "C" {
 #define FR_MEAN_INTERLEAVED 0x10u /* mu[3*n+c]      rendering_layer/sample_test.py:101 */
 #define FR_BASIS_PLANAR 0x0u      /* pc[c*N+n,k]    nets/network.py:154,156 (default) */
 #define FR_BASIS_INTERLEAVED 0x20u/* pc[3*n+c,k]    prepare_data/Project2D.m:8-9 */
+/* Pack-time AND run-time flag: the row tiles of the tensor-core forward operands follow the clusters of the mesh table
+ * (instead of 128 consecutive vertices), and fr_recon_render_forward rasterizes each cluster inside the reconstruction
+ * epilogue from shared memory.  A basis packed with this flag must always be used with it and with the same mesh table.
+ * Same results either way; measured slower on B200 than the default pipeline, kept as an option. */
+#define FR_CLUSTER_TILES 0x40u
 
 /* number of pose parameters in front of the shape/expression coefficients (utils/parser_3dmm.py:49) */
 #define FR_NDIM_POSE 7
@@ -91,7 +96,7 @@ int fr_mesh_table_vertex_slots(const fr_mesh_table* mesh);   /* vertices counted
  * vertices).  mu [3N], pc_shape [3N,ndim_shape], pc_exp [3N,ndim_exp] are device pointers in the reference's layouts
  * (nets/network.py:41-43).  One-off, at model load.  Every later call that takes this packed basis must be given the
  * same `mesh` (or NULL if it was packed with NULL). */
-size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp, const fr_mesh_table* mesh);
+size_t fr_packed_basis_bytes(int nver, int ndim_shape, int ndim_exp, unsigned layout_flags, const fr_mesh_table* mesh);
 int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, int nver, int ndim_shape, int ndim_exp,
                   unsigned layout_flags, const fr_mesh_table* mesh, float* packed, void* stream);
 
@@ -120,7 +125,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
  * Triangles whose indices fall outside [0,nver) are skipped (the reference reads out of bounds).
  * mesh: the mesh table of `tri` (cluster rasterizer) or NULL (generic per-triangle path); same outputs either way.
  * At most 65535 faces per call. */
-size_t fr_render_workspace_bytes(int batch, int nver, int height, int width, const fr_mesh_table* mesh);
+size_t fr_render_workspace_bytes(int batch, int nver, int height, int width);
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                             float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
                             int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
@@ -158,8 +163,7 @@ int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg
  * the other through a planar vertex buffer in the workspace.
  * stage_events: NULL, or two cudaEvent_t (either may be NULL) recorded on `stream` after the reconstruction(+raster)
  * kernels and after the last kernel -- lets a benchmark split the device time of one real call. */
-size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width,
-                                   const fr_mesh_table* mesh);
+size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width);
 int fr_recon_render_forward(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
                             float* vertex_proj, float* depth, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
                             int ndim_exp, int height, int width, float im_size, unsigned flags, void* workspace,

@@ -23,8 +23,8 @@ def _model_from_golden(g):
             "mu_tex": g["mu_tex"], "ndim_shape": g["pc_shape"].shape[1], "ndim_exp": g["pc_exp"].shape[1], "ndim_pose": 7}
 
 
-def _gpu_vertices(model, params, im_size, convention="network"):
-    dm = fr("model").DeviceModel(model, DEV, convention)
+def _gpu_vertices(model, params, im_size, convention="network", cluster_tiles=False):
+    dm = fr("model").DeviceModel(model, DEV, convention, cluster_tiles=cluster_tiles)
     out = fr("nets.network").recon_project(torch.from_numpy(np.asarray(params, np.float32)).to(DEV), dm, im_size)
     torch.cuda.synchronize()
     return dm, out.cpu().numpy()
@@ -48,10 +48,13 @@ def bfm():
     return fr("synth").make_synthetic_model(seed=0, jitter=0.2)          # true dims: 53 215 / 105 840 / 199 / 29
 
 
-@pytest.mark.parametrize("B,full", [(1, False), (3, True), (8, False), (16, True), (20, False), (64, False), (70, True)])
-def test_bfm_size_forward(bfm, B, full):
+@pytest.mark.parametrize("B,full,tiles", [(1, False, False), (3, True, False), (8, False, False), (16, True, False), (20, False, False),
+                                          (64, False, False), (70, True, False), (3, False, True), (20, True, True), (70, False, True)])
+def test_bfm_size_forward(bfm, B, full, tiles):
+    """All forward kernels (FFMA for <= 8 faces, tcgen05 above) with consecutive row tiles and with the mesh table's clusters
+    as row tiles (FR_CLUSTER_TILES: border vertices are computed by several clusters, written by their owner)."""
     p = fr("synth").sample_params_constrained(B, seed=2 + B, full_range=full)
-    _, got = _gpu_vertices(bfm, p, 200)
+    _, got = _gpu_vertices(bfm, p, 200, cluster_tiles=tiles)
     want = recon.vertices_transform(p, bfm, 200)                           # float64 ground truth
     assert got.shape == want.shape == (B, 3, 53215)
     err = np.abs(got - want).max(axis=(1, 2)) / np.abs(want).max(axis=(1, 2))
@@ -146,17 +149,18 @@ def test_session_host_buffers_match_tensor_path(bfm):
     sess.close()
 
 
-@pytest.mark.parametrize("B", [3, 20])
-def test_fused_call_matches_separate_calls(bfm, B):
-    """fr_recon_render_forward (un-fused SIMT path at B=3; at B=20 the tcgen05 kernel with the cluster rasterizer in its
-    epilogue) == fr_recon_project_forward + fr_render_depth_forward bit for bit, with and without the vertex tensor."""
+@pytest.mark.parametrize("B,tiles", [(3, False), (20, False), (3, True), (20, True), (70, True)])
+def test_fused_call_matches_separate_calls(bfm, B, tiles):
+    """fr_recon_render_forward == fr_recon_project_forward + fr_render_depth_forward bit for bit, with and without the vertex
+    tensor: FFMA path (B = 3) and tcgen05 path writing the rasterizer's records (default), and the FR_CLUSTER_TILES
+    flavour whose tcgen05 epilogue rasterizes each cluster from shared memory (B = 20, 70)."""
     lib, check = fr("_lib").lib(), fr("_lib").check
     p = fr("synth").sample_params_constrained(B, seed=60 + B)
-    dm, vp = _gpu_vertices(bfm, p, 200)
+    dm, vp = _gpu_vertices(bfm, p, 200, cluster_tiles=tiles)
     image = torch.empty((B, 200, 200, 3), device=DEV)
     want = fr("rendering_layer.ops").render_depth(torch.from_numpy(vp).to(DEV), dm.tri, dm.vertex_code.unsqueeze(0).expand(B, -1, -1), image)
     pt = torch.from_numpy(p).to(DEV)
-    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, dm.ndim_shape, dm.ndim_exp, 200, 200, dm.mesh.handle), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, dm.ndim_shape, dm.ndim_exp, 200, 200), dtype=torch.uint8, device=DEV)
     sp = torch.cuda.current_stream().cuda_stream
     for with_vertex in (True, False):
         ws.fill_(0xAB)                                                    # stale workspace contents must not matter
@@ -176,23 +180,24 @@ def test_fused_call_matches_separate_calls(bfm, B):
             assert bool(torch.isnan(vertex).all())                         # untouched
 
 
+@pytest.mark.parametrize("tiles", [False, True])
 @pytest.mark.parametrize("B,H,W", [(70, 33, 31), (9, 48, 64), (130, 20, 20)])
-def test_fused_call_small_model_odd_shapes(small_model, B, H, W):
+def test_fused_call_small_model_odd_shapes(small_model, B, H, W, tiles):
     """The fused call on a small model (K = 18: one 16-k chunk pair, one M tile), several 64-face batch tiles, non-square images
     and an odd pixel count (keys cleared by memset instead of the reconstruction epilogue): bit-identical to the two calls."""
     lib, check = fr("_lib").lib(), fr("_lib").check
     ks, ke = small_model["ndim_shape"], small_model["ndim_exp"]
     p = fr("synth").sample_params_constrained(B, ks, ke, max(H, W), seed=7 + B)
-    dm = fr("model").DeviceModel(small_model, DEV)
+    dm = fr("model").DeviceModel(small_model, DEV, cluster_tiles=tiles)
     pt = torch.from_numpy(p).to(DEV)
     sp = torch.cuda.current_stream().cuda_stream
-    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, H, W, dm.mesh.handle), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, H, W), dtype=torch.uint8, device=DEV)
     rb = lib.fr_recon_workspace_bytes(B, dm.nver, ks, ke)
     vp = torch.empty((B, 3, dm.nver), device=DEV)
     want_d, want_t = torch.empty((B, H, W, 1), device=DEV), torch.empty((B, H, W, 1), device=DEV)
     check(lib.fr_recon_project_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.mesh.handle, vp.data_ptr(), B, dm.nver, ks, ke,
                                        float(max(H, W)), dm.run_flags, ws.data_ptr(), rb, sp))
-    ws2 = torch.empty(lib.fr_render_workspace_bytes(B, dm.nver, H, W, None), dtype=torch.uint8, device=DEV)
+    ws2 = torch.empty(lib.fr_render_workspace_bytes(B, dm.nver, H, W), dtype=torch.uint8, device=DEV)
     check(lib.fr_render_depth_forward(vp.data_ptr(), dm.tri.data_ptr(), None, 0, want_d.data_ptr(), None, None, want_t.data_ptr(), B,
                                       dm.nver, dm.ntri, H, W, None, ws2.data_ptr(), ws2.numel(), sp))      # generic rasterizer
     ws.fill_(0x5C)
@@ -229,18 +234,19 @@ def test_small_model_backward_all_paths(small_model, B):
         assert (np.abs(got[:, sl] - want[:, sl]) <= GRAD_TOL * scale).all(), sl
 
 
-def test_fused_call_is_cuda_graph_capturable(small_model):
+@pytest.mark.parametrize("tiles", [False, True])
+def test_fused_call_is_cuda_graph_capturable(small_model, tiles):
     """include/facerecon_b200.h promises stream-ordered, capturable calls (the reference launches on the legacy default
     stream and mallocs per call): capture the fused call -- prep kernel, programmatic dependent launches, rasterizer -- in a
     CUDA graph, replay it on new parameters, compare with the eager call."""
     lib, check = fr("_lib").lib(), fr("_lib").check
     ks, ke = small_model["ndim_shape"], small_model["ndim_exp"]
     B, S = 20, 48
-    dm = fr("model").DeviceModel(small_model, DEV)
+    dm = fr("model").DeviceModel(small_model, DEV, cluster_tiles=tiles)
     pa = torch.from_numpy(fr("synth").sample_params_constrained(B, ks, ke, S, seed=1)).to(DEV)
     pb = torch.from_numpy(fr("synth").sample_params_constrained(B, ks, ke, S, seed=2)).to(DEV)
     params = pa.clone()
-    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, S, S, dm.mesh.handle), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, ks, ke, S, S), dtype=torch.uint8, device=DEV)
     depth, tri_ind = torch.empty((B, S, S, 1), device=DEV), torch.empty((B, S, S, 1), device=DEV)
 
     def call(stream):

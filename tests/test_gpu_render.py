@@ -14,7 +14,7 @@ DEV = "cuda:0"
 NAMES = ("depth", "texture_image", "normal", "tri_ind")
 
 
-MESH_MODES = ["now", None]       # cluster rasterizer with a mesh table built on the spot / generic per-triangle kernels
+MESH_MODES = ["now", None]       # triangles from a mesh table built on the spot (integer ids, cluster order) / from the float index tensor
 
 
 def _gpu_render(vertex, tri, texture, H, W, expand_texture=False, mesh="now"):
@@ -155,11 +155,11 @@ def test_signed_zero_depths_and_zero_params():
             _assert_same(_gpu_render(v, tri, np.zeros_like(v), 8, 8, mesh=mesh), want, "signed zero")
     lib, check = fr("_lib").lib(), fr("_lib").check
     model = fr("synth").make_synthetic_model(grid=(23, 31), ndim_shape=12, ndim_exp=5, seed=3, jitter=0.2)
-    dm = fr("model").DeviceModel(model, DEV)
-    for B in (3, 20):                                                       # un-fused small batch / fused tensor-core path
+    for tiles, B in ((False, 3), (False, 20), (True, 20)):                 # FFMA path / tcgen05 + records / tcgen05 + cluster rasterizer
+        dm = fr("model").DeviceModel(model, DEV, cluster_tiles=tiles)
         S = 32
         params = torch.zeros((B, dm.ndim), device=DEV)
-        ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, dm.ndim_shape, dm.ndim_exp, S, S, dm.mesh.handle), dtype=torch.uint8, device=DEV)
+        ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, dm.ndim_shape, dm.ndim_exp, S, S), dtype=torch.uint8, device=DEV)
         d, t = torch.empty((B, S, S, 1), device=DEV), torch.empty((B, S, S, 1), device=DEV)
         check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), dm.mesh.handle, None, d.data_ptr(),
                                           t.data_ptr(), B, dm.nver, dm.ntri, dm.ndim_shape, dm.ndim_exp, S, S, float(S), dm.run_flags,
@@ -176,7 +176,7 @@ def test_full_batch_properties():
     B = 64
     m, vp = _bfm_vertices(B, seed=2)
     got = _gpu_render(vp, m["tri"], m["vertex"], 200, 200, expand_texture=True)
-    _assert_same(_gpu_render(vp, m["tri"], m["vertex"], 200, 200, expand_texture=True, mesh=None), got, "cluster vs generic")
+    _assert_same(_gpu_render(vp, m["tri"], m["vertex"], 200, 200, expand_texture=True, mesh=None), got, "table order vs reference order")
     depth, teximg, normal, tri_ind = got
     covered = tri_ind[..., 0] >= 0
     assert (depth[..., 0][~covered].view(np.uint32) == 0xD6B5E621).all()
@@ -275,7 +275,7 @@ def test_full_size_properties_batch_256():
     sp = torch.cuda.current_stream().cuda_stream
 
     def fused(params, nb):
-        ws = torch.empty(lib.fr_pipeline_workspace_bytes(nb, dm.nver, dm.ndim_shape, dm.ndim_exp, S, S, dm.mesh.handle), dtype=torch.uint8, device=DEV)
+        ws = torch.empty(lib.fr_pipeline_workspace_bytes(nb, dm.nver, dm.ndim_shape, dm.ndim_exp, S, S), dtype=torch.uint8, device=DEV)
         vp = torch.empty((nb, 3, dm.nver), device=DEV)
         d, t = torch.empty((nb, S, S, 1), device=DEV), torch.empty((nb, S, S, 1), device=DEV)
         check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), dm.mesh.handle, vp.data_ptr(),

@@ -41,6 +41,11 @@ def _check_table(tri, nver, table):
         got = ids[cluster_of, lk]
         assert (got == tri[k, orig].astype(np.int64)).all(), k
     assert (local >> 24 == 0).all()
+    # the vertex-id flavour of the same list
+    tq = p["tri_vid"]
+    assert (tq[:, 3].astype(np.int64) == orig).all()
+    for k in range(3):
+        assert (tq[:, k].astype(np.int64) == tri[k, orig].astype(np.int64)).all(), k
     return p
 
 

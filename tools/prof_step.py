@@ -27,7 +27,7 @@ params = torch.from_numpy(synth.sample_params_constrained(B, seed=2)).to(dev)
 nver, ntri, ks, ke = dm.nver, dm.ntri, dm.ndim_shape, dm.ndim_exp
 mesh = dm.mesh.handle
 rb = lib.fr_recon_workspace_bytes(B, nver, ks, ke)
-ws = torch.empty(max(lib.fr_pipeline_workspace_bytes(B, nver, ks, ke, H, W, mesh), rb + lib.fr_render_workspace_bytes(B, nver, H, W, mesh)),
+ws = torch.empty(max(lib.fr_pipeline_workspace_bytes(B, nver, ks, ke, H, W), rb + lib.fr_render_workspace_bytes(B, nver, H, W)),
                  dtype=torch.uint8, device=dev)
 vertex = torch.empty((B, 3, nver), device=dev)
 depth, tri_ind = torch.empty((B, H, W, 1), device=dev), torch.empty((B, H, W, 1), device=dev)
