@@ -23,7 +23,7 @@ FR_BASIS_PLANAR, FR_BASIS_INTERLEAVED = 0x0, 0x20
 FR_CLUSTER_TILES = 0x40
 FR_PARAMS_RAW = 0x100
 FR_NDIM_POSE = 7
-FR_SESSION_SLOTS = 2
+FR_SESSION_SLOTS = 3
 
 _vp, _sz, _i, _f, _u, _ll = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, ctypes.c_uint, ctypes.c_longlong
 

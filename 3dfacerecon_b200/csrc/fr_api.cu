@@ -116,6 +116,17 @@ int check_mesh(const fr_mesh_table* mesh, int nver, int ntri) {
 const int32_t* mesh_cluster_vert(const fr_mesh_table* mesh) {
   return mesh ? reinterpret_cast<const int32_t*>(mesh->dev + mesh->hdr.off_vert) : nullptr;
 }
+const int32_t* mesh_rank_vert(const fr_mesh_table* mesh) {
+  return mesh ? reinterpret_cast<const int32_t*>(mesh->dev + mesh->hdr.off_rank_vert) : nullptr;
+}
+const int32_t* mesh_vert_rank(const fr_mesh_table* mesh) {
+  return mesh ? reinterpret_cast<const int32_t*>(mesh->dev + mesh->hdr.off_vert_rank) : nullptr;
+}
+// The vertex behind every row of the tensor-core forward operand tiles: cluster lists (FR_CLUSTER_TILES), rank order (any
+// other basis packed with a mesh table), null = consecutive vertex ids (packed without a table).
+const int32_t* mesh_row_vert(const fr_mesh_table* mesh, unsigned flags) {
+  return (flags & FR_CLUSTER_TILES) ? mesh_cluster_vert(mesh) : mesh_rank_vert(mesh);
+}
 
 // Tensor-core path for this batch?  (FR_RECON_PATH = simt | f16 overrides the dispatch, for A/B comparisons.)
 bool use_f16_forward(const BasisGeom& g, int batch, bool raster) {
@@ -144,7 +155,7 @@ int recon_project_forward_impl(const float* params, const float* packed, const f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
-  const int32_t* cluster_vert = (flags & FR_CLUSTER_TILES) ? mesh_cluster_vert(mesh) : nullptr;
+  const int32_t* cluster_vert = mesh_row_vert(mesh, flags);
 
   if (target != nullptr || use_f16_forward(g, batch, false)) {
     const bool fold = clear_keys != nullptr && clear_bytes % 16 == 0;     // the prep kernel clears the keys itself, 16 bytes at a time
@@ -221,7 +232,8 @@ int launch_keys(const float4* rec, const float* tri, const fr_mesh_table* mesh, 
 int render_depth_forward_impl(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                               float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
                               int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
-                              void* stream, bool records_ready, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false}) {
+                              void* stream, bool records_ready, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false},
+                              cudaEvent_t after_keys = nullptr) {
   if (int rc = check_render_dims(batch, nver, ntri, height, width)) return rc;
   if (int rc = check_mesh(mesh, nver, ntri)) return rc;
   if (batch == 0) return FR_OK;
@@ -240,15 +252,16 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
   if (draws) {
     if (!records_ready) {   // the pack pass also clears the visibility keys
       raster_pack_kernel<<<dim3(ceil_div(nver, kRasterThreads * kSnapPerThread), batch), kRasterThreads, 0, st>>>(
-          vertex, rec, keys, nver, npix, width, height);
+          vertex, rec, keys, mesh_vert_rank(mesh), nver, npix, width, height);
       FR_LAUNCHED("raster_pack_kernel");
     }
     if (int rc = launch_keys(rec, tri, mesh, keys, batch, nver, ntri, height, width, pdl, st)) return rc;
+    if (after_keys != nullptr) FR_CUDA(cudaEventRecord(after_keys, st));
   } else if (!records_ready) {
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   }
   return launch_resolve(keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver, ntri,
-                        npix, layer, pdl && draws, st);
+                        npix, layer, pdl && draws && after_keys == nullptr, st);
 }
 
 }  // namespace
@@ -306,7 +319,9 @@ int fr_mesh_table_from_blob(const void* blob, size_t bytes, int device, fr_mesh_
   FR_REQUIRE(h.total_bytes == bytes && h.nclusters >= 0 && h.ntri_slots >= 0 && h.off_vert == sizeof(MeshTableHeader) &&
                  (size_t)h.off_vert + (size_t)h.nclusters * kClusterVerts * 4 <= h.off_tri_begin &&
                  (size_t)h.off_tri_begin + ((size_t)h.nclusters + 1) * 4 <= h.off_tri &&
-                 (size_t)h.off_tri + (size_t)h.ntri_slots * 8 <= h.off_tri_vid && (size_t)h.off_tri_vid + (size_t)h.ntri_slots * 16 <= bytes,
+                 (size_t)h.off_tri + (size_t)h.ntri_slots * 8 <= h.off_tri_vid &&
+                 (size_t)h.off_tri_vid + (size_t)h.ntri_slots * 16 <= h.off_rank_vert && h.off_rank_vert <= h.off_vert_rank &&
+                 (size_t)h.off_vert_rank + (size_t)h.nver * 4 <= bytes,
              "mesh table blob is inconsistent");
   const unsigned char* p = static_cast<const unsigned char*>(blob);
   uint32_t hash = 2166136261u;
@@ -366,7 +381,7 @@ int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, i
   const size_t pieces = (size_t)g.nclusters * 3 * g.nch16 * 2 * kTileVerts;       // one 128-row tile per cluster (mesh_table.h)
   f16::pack_basis_f16_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(mu, pc_shape, pc_exp, scale, nver, ndim_shape, ndim_exp,
                                                                               g.nch16, g.nclusters, layout_flags,
-                                                                              (layout_flags & FR_CLUSTER_TILES) ? mesh_cluster_vert(mesh) : nullptr,
+                                                                              mesh_row_vert(mesh, layout_flags),
                                                                               reinterpret_cast<uint4*>(base + g.f16_offset()));
   FR_LAUNCHED("pack_basis_f16_kernel");
   // ... and the same pairs transposed for the backward contraction over the vertices
@@ -391,7 +406,7 @@ int fr_recon_project_forward(const float* params, const float* packed, const fr_
                              int nver, int ndim_shape, int ndim_exp, float im_size, unsigned flags, void* workspace,
                              size_t workspace_bytes, void* stream) {
   FR_REQUIRE(batch == 0 || vertex_proj != nullptr, "null pointer argument");
-  const ReconOut out = {vertex_proj, nullptr, 0, 0};
+  const ReconOut out = {vertex_proj, nullptr, 0, 0, nullptr};
   return recon_project_forward_impl(params, packed, mesh, out, nullptr, nullptr, 0, batch, nver, ndim_shape, ndim_exp, im_size, flags,
                                     workspace, workspace_bytes, stream);
 }
@@ -550,7 +565,7 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
   char* rws = static_cast<char*>(workspace) + rb;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(rws);
   const size_t kbytes = sizeof(unsigned long long) * (size_t)batch * height * width;
-  const bool timed = stage_events != nullptr && stage_events[0] != nullptr;
+  const bool timed = stage_events != nullptr && (stage_events[0] != nullptr || stage_events[1] != nullptr);
   auto record = [&](int i) -> cudaError_t {
     return (stage_events != nullptr && stage_events[i] != nullptr) ? cudaEventRecord(static_cast<cudaEvent_t>(stage_events[i]), st)
                                                                    : cudaSuccess;
@@ -558,30 +573,33 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
   if (fused_raster(mesh, flags, batch, nver, ndim_shape, ndim_exp)) {
     // prep kernel (clears the keys) -> tensor-core reconstruction with the cluster rasterizer in its epilogue -> resolve
     const f16::RasterTarget target = {static_cast<const unsigned char*>(mesh->dev), keys, width, height};
-    const ReconOut out = {vertex_proj, nullptr, 0, 0};
+    const ReconOut out = {vertex_proj, nullptr, 0, 0, nullptr};
     if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, keys, kbytes, batch, nver, ndim_shape, ndim_exp, im_size,
                                             flags, workspace, rb, stream))
       return rc;
     FR_CUDA(record(0));
+    FR_CUDA(record(1));
     const LayerOut layer = {nullptr, nullptr, nullptr, false};
     if (int rc = launch_resolve(keys, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height * width,
                                 layer, pdl_enabled() && !timed, st))
       return rc;
-    FR_CUDA(record(1));
+    FR_CUDA(record(2));
     return FR_OK;
   }
   // The reconstruction kernels write the rasterizer's vertex records straight into the render workspace (same carve-up as
   // render_depth_forward_impl: keys first, records after) and clear its keys, so the repack pass over vertex_proj disappears;
   // vertex_proj itself is optional here.
-  const ReconOut out = {vertex_proj, reinterpret_cast<float4*>(rws + key_bytes(batch, height, width)), width, height};
+  const ReconOut out = {vertex_proj, reinterpret_cast<float4*>(rws + key_bytes(batch, height, width)), width, height,
+                        mesh_vert_rank(mesh)};
   if (int rc = recon_project_forward_impl(params, packed, mesh, out, nullptr, keys, kbytes, batch, nver, ndim_shape, ndim_exp, im_size,
                                           flags, workspace, rb, stream))
     return rc;
   FR_CUDA(record(0));
+  const cudaEvent_t after_keys = (stage_events != nullptr) ? static_cast<cudaEvent_t>(stage_events[1]) : nullptr;
   if (int rc = render_depth_forward_impl(vertex_proj, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height, width,
-                                         mesh, rws, vb, stream, true))
+                                         mesh, rws, vb, stream, true, LayerOut{nullptr, nullptr, nullptr, false}, after_keys))
     return rc;
-  FR_CUDA(record(1));
+  FR_CUDA(record(2));
   return FR_OK;
 }
 

@@ -33,8 +33,14 @@ constexpr uint32_t kVertIdMask = 0x00FFFFFFu;  // nver <= 2^24 (float triangle i
 //   cluster_vert  int32 [nclusters][128]   vertex id | kVertOwner, -1 = unused slot
 //   tri_begin     int32 [nclusters + 1]    first triangle entry of each cluster
 //   tri_entry     uint2 [ntri_slots]       { l1 | l2 << 8 | l3 << 16 (slots within the cluster), original triangle index }
-//   tri_vid       uint4 [ntri_slots]       { p1, p2, p3 (vertex ids, pre-validated), original triangle index }: the same
-//                                          triangles in the same (cluster) order for kernels that gather by vertex id
+//   tri_vid       uint4 [ntri_slots]       { r1, r2, r3 (vertex RANKS, pre-validated), original triangle index }: the same
+//                                          triangles in the same (cluster) order for kernels that gather vertex records
+//   rank_vert     int32 [ceil(nver/128)*128]  vertex id | kVertOwner of every rank, -1 behind the last one
+//   vert_rank     int32 [nver]             rank of every vertex
+// RANK = the position of a vertex in cluster order (clusters in table order, within a cluster its owned vertices in slot
+// order).  Kernels that keep per-vertex data in global memory (the 16-byte vertex records of raster.cuh, the row order of
+// the packed basis) use ranks instead of the mesh's own numbering: the vertices a block of triangles touches are then
+// neighbours in memory whatever the numbering of the mesh file -- locality comes from this table, not from the generator.
 struct MeshTableHeader {
   uint32_t magic, version;
   int32_t nver, ntri;
@@ -44,8 +50,7 @@ struct MeshTableHeader {
   int32_t nvert_slots;         // used cluster_vert slots (vertices counted once per member cluster)
   uint32_t off_vert, off_tri_begin, off_tri, total_bytes;
   uint32_t hash;               // FNV-1a of everything behind the header
-  uint32_t off_tri_vid;
-  uint32_t pad[2];
+  uint32_t off_tri_vid, off_rank_vert, off_vert_rank;
 };
 static_assert(sizeof(MeshTableHeader) == 64, "header is 64 bytes");
 
@@ -55,6 +60,7 @@ static_assert(sizeof(MeshTableHeader) == 64, "header is 64 bytes");
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 namespace fr {
@@ -201,6 +207,38 @@ class MeshTableBuilder {
   }
   bool fits(int lo, int hi) { return hi - lo <= kClusterTris && count_unique(lo, hi) <= kClusterVerts; }
 
+  // Z-order (Morton) key of a point within the bounding box of a vertex set, over the two axes of largest extent.
+  struct ZOrder {
+    float lo[2], scale[2];
+    int axis[2];
+    ZOrder(const float* coord, const std::vector<int>& verts) {
+      float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+      for (int n : verts)
+        for (int c = 0; c < 3; ++c) {
+          mn[c] = std::min(mn[c], coord[(size_t)3 * n + c]);
+          mx[c] = std::max(mx[c], coord[(size_t)3 * n + c]);
+        }
+      int order[3] = {0, 1, 2};
+      std::sort(order, order + 3, [&](int a, int b) { return mx[a] - mn[a] > mx[b] - mn[b]; });
+      for (int k = 0; k < 2; ++k) {
+        axis[k] = order[k];
+        lo[k] = verts.empty() ? 0.0f : mn[order[k]];
+        const float ext = verts.empty() ? 0.0f : mx[order[k]] - mn[order[k]];
+        scale[k] = ext > 0.0f ? 255.0f / ext : 0.0f;
+      }
+    }
+    uint32_t key(const float* p) const {
+      uint32_t q[2];
+      for (int k = 0; k < 2; ++k) {
+        const float f = (p[axis[k]] - lo[k]) * scale[k];
+        q[k] = (uint32_t)std::min(255.0f, std::max(0.0f, f));
+      }
+      uint32_t m = 0;
+      for (int b = 0; b < 8; ++b) m |= ((q[0] >> b) & 1u) << (2 * b) | ((q[1] >> b) & 1u) << (2 * b + 1);
+      return m;
+    }
+  };
+
   struct AxisLess {
     const float* cen;
     int axis;
@@ -337,15 +375,25 @@ class MeshTableBuilder {
 
   std::vector<unsigned char> serialise() {
     const int ncl_tri = (int)cuts_.size() - 1;
-    // cluster vertex lists (sorted by vertex id: coalesced planar stores when the mesh order is local)
+    // cluster vertex lists: in vertex-id order when the mesh numbering is already local (the cluster's ids span a narrow
+    // range: planar tensors in the mesh's numbering are then written / read in runs), else in Z order of the vertex
+    // positions within the cluster -- neighbouring slots / ranks are neighbouring vertices whatever the numbering
     std::vector<std::vector<int>> cverts(ncl_tri);
     std::vector<char> owned(nver_, 0);
+    std::vector<std::pair<uint32_t, int>> keyed;
     for (int c = 0; c < ncl_tri; ++c) {
       std::vector<int>& v = cverts[c];
       for (int i = cuts_[c]; i < cuts_[c + 1]; ++i)
         for (int k = 0; k < 3; ++k) v.push_back(tv_[3 * perm_[i] + k]);
       std::sort(v.begin(), v.end());
       v.erase(std::unique(v.begin(), v.end()), v.end());
+      if (!v.empty() && (long long)(v.back() - v.front()) > 64ll * (long long)v.size()) {
+        const ZOrder z(coord_.data(), v);
+        keyed.clear();
+        for (int n : v) keyed.emplace_back(z.key(&coord_[(size_t)3 * n]), n);
+        std::sort(keyed.begin(), keyed.end());
+        for (size_t i = 0; i < v.size(); ++i) v[i] = keyed[i].second;
+      }
     }
     // vertices no triangle references still have to be reconstructed (planar vertex_proj): they fill free slots
     std::vector<char> referenced(nver_, 0);
@@ -372,7 +420,10 @@ class MeshTableBuilder {
     h.off_tri_begin = h.off_vert + (uint32_t)ncl * kClusterVerts * 4u;
     h.off_tri = (h.off_tri_begin + (uint32_t)(ncl + 1) * 4u + 15u) / 16u * 16u;
     h.off_tri_vid = (h.off_tri + (uint32_t)nvalid_ * 8u + 15u) / 16u * 16u;
-    h.total_bytes = (h.off_tri_vid + (uint32_t)nvalid_ * 16u + 255u) / 256u * 256u;
+    const uint32_t nrank = (uint32_t)((nver_ + kClusterVerts - 1) / kClusterVerts * kClusterVerts);
+    h.off_rank_vert = h.off_tri_vid + (uint32_t)nvalid_ * 16u;
+    h.off_vert_rank = h.off_rank_vert + nrank * 4u;
+    h.total_bytes = (h.off_vert_rank + (uint32_t)nver_ * 4u + 255u) / 256u * 256u;
     std::vector<unsigned char> blob(h.total_bytes, 0);
     int32_t* cv = reinterpret_cast<int32_t*>(blob.data() + h.off_vert);
     int32_t* tb = reinterpret_cast<int32_t*>(blob.data() + h.off_tri_begin);
@@ -395,15 +446,25 @@ class MeshTableBuilder {
       }
       nslots += s;
       tb[c] = cuts_[c];
-      // triangles of a cluster in original index order (the order is irrelevant for the result: visibility is resolved
-      // by (depth, index) keys; it keeps neighbouring lanes on neighbouring vertices)
+      // triangles of a cluster in the order of their slots (lowest slot first; the order is irrelevant for the result:
+      // visibility is resolved by (depth, index) keys; it keeps neighbouring lanes on neighbouring vertices)
       std::vector<int> ts(perm_.begin() + cuts_[c], perm_.begin() + cuts_[c + 1]);
-      std::sort(ts.begin(), ts.end(), [&](int a, int b) { return orig_[a] < orig_[b]; });
+      {
+        keyed.clear();
+        for (int t : ts) {
+          const int a = slot[tv_[3 * t]], b = slot[tv_[3 * t + 1]], d = slot[tv_[3 * t + 2]];
+          keyed.emplace_back((uint32_t)std::min(a, std::min(b, d)) * 1024u + (uint32_t)(a + b + d), t);
+        }
+        std::sort(keyed.begin(), keyed.end(), [&](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) {
+          return a.first < b.first || (a.first == b.first && orig_[a.second] < orig_[b.second]);
+        });
+        for (size_t i = 0; i < ts.size(); ++i) ts[i] = keyed[i].second;
+      }
       for (size_t i = 0; i < ts.size(); ++i) {
         const int t = ts[i];
         te[2 * ((size_t)cuts_[c] + i)] = (uint32_t)slot[tv_[3 * t]] | ((uint32_t)slot[tv_[3 * t + 1]] << 8) | ((uint32_t)slot[tv_[3 * t + 2]] << 16);
         te[2 * ((size_t)cuts_[c] + i) + 1] = (uint32_t)orig_[t];
-        uint32_t* q4 = tq + 4 * ((size_t)cuts_[c] + i);
+        uint32_t* q4 = tq + 4 * ((size_t)cuts_[c] + i);      // vertex ids for now, ranks once they are known (below)
         q4[0] = (uint32_t)tv_[3 * t];
         q4[1] = (uint32_t)tv_[3 * t + 1];
         q4[2] = (uint32_t)tv_[3 * t + 2];
@@ -419,6 +480,19 @@ class MeshTableBuilder {
       tb[c] = nvalid_;
     }
     tb[ncl] = nvalid_;
+    // ranks: owned vertices in cluster / slot order
+    int32_t* rank_vert = reinterpret_cast<int32_t*>(blob.data() + h.off_rank_vert);
+    int32_t* vert_rank = reinterpret_cast<int32_t*>(blob.data() + h.off_vert_rank);
+    std::fill(rank_vert, rank_vert + nrank, -1);
+    int next = 0;
+    for (size_t i = 0; i < (size_t)ncl * kClusterVerts; ++i)
+      if (cv[i] >= 0 && ((uint32_t)cv[i] & kVertOwner)) {
+        const int v = (int)((uint32_t)cv[i] & kVertIdMask);
+        vert_rank[v] = next;
+        rank_vert[next++] = v | (int32_t)kVertOwner;
+      }
+    for (size_t i = 0; i < (size_t)nvalid_; ++i)
+      for (int k = 0; k < 3; ++k) tq[4 * i + k] = (uint32_t)vert_rank[tq[4 * i + k]];
     h.max_cluster_tris = max_tris;
     h.nvert_slots = nslots;
     uint32_t hash = 2166136261u;

@@ -42,7 +42,7 @@ __device__ __forceinline__ bool tri_vertex_index(float f, int nver, int* out) {
 constexpr int kSnapPerThread = 4;
 __global__ void __launch_bounds__(kRasterThreads)
 raster_pack_kernel(const float* __restrict__ vertex, float4* __restrict__ rec, unsigned long long* __restrict__ keys,
-                   int nver, int npix, int width, int height) {
+                   const int32_t* __restrict__ vert_rank, int nver, int npix, int width, int height) {
   pdl_trigger();
   const int b = blockIdx.y;
   const int base = blockIdx.x * (kRasterThreads * kSnapPerThread) + threadIdx.x;
@@ -65,8 +65,9 @@ raster_pack_kernel(const float* __restrict__ vertex, float4* __restrict__ rec, u
 #pragma unroll
   for (int j = 0; j < kSnapPerThread; ++j) {
     const int n = base + j * kRasterThreads;
-    if (n < nver)
-      rec[(size_t)b * nver + n] = make_float4(x[j], y[j], z[j], __uint_as_float(fr_snap_code(x[j], y[j], width, height)));
+    if (n < nver)   // records are stored by vertex rank (mesh_table.h) when a mesh table is in play
+      rec[(size_t)b * nver + (vert_rank != nullptr ? __ldg(vert_rank + n) : n)] =
+          make_float4(x[j], y[j], z[j], __uint_as_float(fr_snap_code(x[j], y[j], width, height)));
   }
 }
 

@@ -150,6 +150,7 @@ struct ReconOut {
   float* planar;
   float4* rec;
   int width, height;   // image size the snap codes refer to (rec != nullptr)
+  const int32_t* vert_rank;   // records are stored by vertex RANK (mesh_table.h) when a mesh table is in play, else by vertex id
 };
 
 // Projection + y flip of one reconstructed vertex (nets/network.py:163-169).
@@ -170,10 +171,12 @@ __device__ __forceinline__ void store_planar(float* __restrict__ planar, int b, 
   o[(size_t)nver + n] = Y;
   o[2 * (size_t)nver + n] = Z;
 }
+__device__ __forceinline__ void store_record(const ReconOut& out, int b, int nver, int slot, float X, float Y, float Z) {
+  out.rec[(size_t)b * nver + slot] = make_float4(X, Y, Z, __uint_as_float(fr_snap_code(X, Y, out.width, out.height)));
+}
 __device__ __forceinline__ void store_vertex(const ReconOut& out, int b, int nver, int n, float X, float Y, float Z) {
   if (out.planar != nullptr) store_planar(out.planar, b, nver, n, X, Y, Z);
-  if (out.rec != nullptr)
-    out.rec[(size_t)b * nver + n] = make_float4(X, Y, Z, __uint_as_float(fr_snap_code(X, Y, out.width, out.height)));
+  if (out.rec != nullptr) store_record(out, b, nver, out.vert_rank != nullptr ? __ldg(out.vert_rank + n) : n, X, Y, Z);
 }
 __device__ __forceinline__ void project_store(const float* __restrict__ P, float x, float y, float z, float im_size,
                                               unsigned flags, const ReconOut& out, int b, int nver, int n) {

@@ -368,7 +368,8 @@ struct RasterTarget {
   int width, height;
 };
 
-// tiles: fp16 operand tiles in cluster order; cluster_vert: [nclusters][128] vertex ids (null = consecutive tiles).
+// tiles: fp16 operand tiles; cluster_vert: the vertex (id | owner flag, -1 = none) behind every row of every tile -- the mesh
+// table's cluster lists (FR_CLUSTER_TILES) or its rank order (one tile = 128 consecutive ranks); null = consecutive vertex ids.
 template <bool kRaster>
 __global__ void __launch_bounds__(Cfg<kRaster>::kThreads, 1)
 recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned char* __restrict__ bsplit,
@@ -564,7 +565,11 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
           const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
           float X, Y, Z;
           project_vertex(P, x[j], y[j], z[j], im_size, flags, &X, &Y, &Z);
-          if (store && b0 + jf < batch) store_vertex(out, b0 + jf, nver, n, X, Y, Z);
+          if (store && b0 + jf < batch) {
+            if (out.planar != nullptr) store_planar(out.planar, b0 + jf, nver, n, X, Y, Z);
+            // records go by rank: with a row map in rank order that is the row itself (cluster tiles never write records)
+            if (out.rec != nullptr) store_record(out, b0 + jf, nver, cluster_vert != nullptr ? tile * kTileVerts + v : n, X, Y, Z);
+          }
           if (kRaster) {
             rs->stage.x[fl][v] = X;
             rs->stage.y[fl][v] = Y;

@@ -66,8 +66,11 @@ class MeshTable:
         out["cluster_vert"] = b[off_v:off_v + ncl * 128 * 4].view(np.int32).reshape(ncl, 128)
         out["tri_begin"] = b[off_b:off_b + (ncl + 1) * 4].view(np.int32)
         out["tri_entry"] = b[off_t:off_t + nslots * 8].view(np.uint32).reshape(nslots, 2)
-        off_q = int(h[13])
+        off_q, off_rv, off_vr = int(h[13]), int(h[14]), int(h[15])
         out["tri_vid"] = b[off_q:off_q + nslots * 16].view(np.uint32).reshape(nslots, 4)
+        nrank = (out["nver"] + 127) // 128 * 128
+        out["rank_vert"] = b[off_rv:off_rv + nrank * 4].view(np.int32)
+        out["vert_rank"] = b[off_vr:off_vr + out["nver"] * 4].view(np.int32)
         return out
 
     def close(self):

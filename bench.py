@@ -4,22 +4,29 @@
     python bench.py [--gpus N --steps K --warmup W]            # this repo's CUDA path
     python bench.py --impl reference [...]                      # the reference's CPU path on the host cores
 
-Workload (BASELINE.json configs[1]): 64 synthetic 235-d parameter vectors per GPU -> BFM-sized reconstruction
-(53 215 vertices, 199+29 components), pose projection, 200x200 z-buffer depth render (depth + tri_ind), forward only.
-At N > 1 every rank runs the same per-GPU batch on its own parameter shard (weak scaling, no data-path collective:
-faces are independent, the basis is replicated -- SURVEY.md 8e).
+Workload of the headline (BASELINE.json configs[1]): 64 synthetic 235-d parameter vectors per GPU -> BFM-sized
+reconstruction (53 215 vertices, 199+29 components), pose projection, 200x200 z-buffer depth render (depth + tri_ind),
+forward only.  At N > 1 every rank runs the same per-GPU batch on its own parameter shard (weak scaling, no data-path
+collective: faces are independent, the basis is replicated -- SURVEY.md 8e).
 
 One step = one pass of the hot path over one batch.  Prints ONE JSON line (rank 0):
-  value      faces/s with inputs resident in HBM, device-timed with CUDA events (max over ranks), L2 flushed
-             between timed iterations
-  e2e        the same metric through the host-buffer C-ABI session (fr_session_forward): params copied in from
-             pinned host memory and the depth maps copied back inside the timed region
-  roofline   dominant kernel group: algorithmic bytes / measured device time vs the measured HBM copy bandwidth
-  cpu_baseline  the reference CPU op (oracle/_ref, or the oracle port) + numpy recon timed on the host cores
+  value      faces/s with inputs resident in HBM, device-timed with CUDA events (max over ranks), L2 flushed between
+             timed iterations
+  e2e        the same metric through the host-buffer C-ABI session: params copied in from pinned host memory and the depth
+             maps copied back inside the timed region; next to it a D2H-only loop over the same pinned buffers (the host
+             link's ceiling for this result size)
+  roofline   dominant kernel (the visibility pass): algorithmic bytes of its part / its device time, measured live with
+             CUDA events the library records between its kernels, vs the measured HBM copy bandwidth; the whole step under
+             three byte conventions beside it
+  config3    BASELINE configs[2]: 4096 faces sharded by batch over the N ranks (shard_batch), the same fused call
+  cpu_baseline  one P-thread float32 GEMM for the whole batch + the reference CPU op (oracle/_ref) on P processes
+  extras     (N = 1) configs[0] (batch 1, sample_test conventions, HBM GB/s), configs[3] (batch 256 forward + backward),
+             the same step on a mesh with shuffled vertex / triangle numbering, and the FR_CLUSTER_TILES flavour
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import importlib
 import json
 import os
@@ -38,60 +45,106 @@ H = W = 200
 IM_SIZE = 200.0
 METRIC = "faces_per_sec_recon_plus_200x200_depth_render"
 UNIT = "faces/s"
+CONFIG3_FACES = 4096
+WORKLOAD = ("BASELINE configs[1]: batch-64 synthetic 235-d params -> 3DMM recon + pose projection + 200x200 depth render "
+            "(depth + tri_ind), forward only, per GPU")
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own path on the host cores (numpy recon as nets/network.py:153-169 + the reference CPU op)
+# CPU arm: the reference's own path on the host cores -- numpy float32 recon as nets/network.py:153-169 (ONE GEMM over the
+# whole batch with all BLAS threads) + the reference CPU op on P processes (it is non-reentrant: static scratch,
+# render_depth_op.cc:125-131 => processes, not threads; they read the vertices from a shared buffer)
 # ----------------------------------------------------------------------------------------------------------------------
 _CPU = {}
 
 
-def _cpu_worker_init(model, use_ref):
+def _cpu_worker_init(model_small, use_ref, shared, shape):
     try:
         from threadpoolctl import threadpool_limits
         _CPU["limit"] = threadpool_limits(1)
     except Exception:
         pass
+    import numpy as np
     import oracle  # noqa: F401  (test/bench infrastructure: the CPU checker doubles as the CPU baseline)
-    _CPU["model"] = model
+    _CPU["model"] = model_small
     _CPU["use_ref"] = use_ref
+    _CPU["vp"] = np.frombuffer(shared, dtype=np.float32).reshape(shape)
 
 
-def _cpu_worker_step(params_shard):
-    """recon + projection (float32 numpy, as TF would) + reference CPU render for a shard of faces; returns a checksum."""
+def _cpu_worker_render(span):
+    """Reference CPU render of faces [lo, hi) of the shared vertex buffer; returns a checksum."""
     import numpy as np
     import oracle
-    from oracle import recon
-    m = _CPU["model"]
-    if len(params_shard) == 0:
+    lo, hi = span
+    if hi <= lo:
         return 0.0
-    vp = recon.vertices_transform(params_shard, m, IM_SIZE, dtype=np.float32).astype(np.float32)
+    m = _CPU["model"]
+    vp = np.ascontiguousarray(_CPU["vp"][lo:hi])
     B = vp.shape[0]
     if _CPU["use_ref"]:
-        tex = np.broadcast_to(m["vertex"], (B,) + m["vertex"].shape)
-        depth = oracle.ref_render_depth(vp, m["tri"], np.ascontiguousarray(tex), (B, H, W, 3))[0]
+        tex = np.ascontiguousarray(np.broadcast_to(m["vertex"], (B,) + m["vertex"].shape))
+        depth = oracle.ref_render_depth(vp, m["tri"], tex, (B, H, W, 3))[0]
     else:
         depth = oracle.oracle_render_depth_forward(vp, m["tri"], m["vertex"], H, W)[0]
     return float(depth[depth > -1e13].sum())
 
 
 class CpuArm:
-    """Process pool (the reference op is non-reentrant: static scratch, render_depth_op.cc:125-131 => processes)."""
-
-    def __init__(self, model, cores=None):
+    def __init__(self, model, batch, cores=None):
         import multiprocessing as mp
         import oracle
+        self.model = model
+        self.batch = batch
         self.use_ref = oracle.ref_available()
         self.cores = cores or max(1, len(os.sched_getaffinity(0)))
+        nver = model["mu"].size // 3
+        self.shape = (batch, 3, nver)
         ctx = mp.get_context("fork")
-        self.pool = ctx.Pool(self.cores, initializer=_cpu_worker_init, initargs=(model, self.use_ref))
+        self.shared = ctx.RawArray(ctypes.c_float, batch * 3 * nver)
+        small = {"tri": model["tri"], "vertex": model["vertex"]}
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_worker_init, initargs=(small, self.use_ref, self.shared, self.shape))
+        import numpy as np
+        self.nver = nver
+        self.ks = int(model["pc_shape"].shape[1])
+        self.basis = np.ascontiguousarray(np.concatenate([model["pc_shape"], model["pc_exp"]], axis=1), np.float32)   # network.py:351 does the same concat
+        self.mu = np.ascontiguousarray(np.asarray(model["mu"], np.float32).reshape(3 * nver, 1))
+
+    def recon(self, params):
+        """nets/network.py:153-169 in float32 numpy, laid out for speed: ONE [3N,228] x [228,B] GEMM on all BLAS threads (the
+        reference issues two, :153,155), mean added, then the batched (f.R) v + t and the y flip.  Same values as the checker
+        oracle.recon.vertices_transform(dtype=float32) up to float32 summation order (verified once in self_check)."""
+        import numpy as np
+        from oracle import recon
+        p = np.asarray(params, np.float32)
+        coef_t = np.ascontiguousarray(p[:, 7:].T)                                 # [228, B]
+        v = self.basis @ coef_t                                                   # [3N, B]
+        v += self.mu
+        vb = np.ascontiguousarray(v.T).reshape(len(p), 3, self.nver)              # [B, 3, N] planar (network.py:154)
+        rot = recon.rotation_matrix_batch(p[:, 0:3])                              # float64 sin/cos -> float32, network.py:292-297
+        m = p[:, 6, None, None] * rot                                             # network.py:165
+        vp = np.matmul(m, vb)
+        vp += p[:, 3:6, None]
+        vp[:, 1, :] = np.float32(IM_SIZE) - vp[:, 1, :] - np.float32(1)           # network.py:168
+        return vp
+
+    def self_check(self, params):
+        import numpy as np
+        from oracle import recon
+        want = recon.vertices_transform(params[:2], self.model, IM_SIZE, dtype=np.float64)
+        got = self.recon(params[:2])
+        err = float(np.abs(got - want).max() / np.abs(want).max())
+        assert err < 1e-5, err
+        return err
 
     def step(self, params):
         import numpy as np
-        shards = [s for s in np.array_split(params, self.cores) if len(s)]
-        return sum(self.pool.map(_cpu_worker_step, shards, chunksize=1))
+        vp = self.recon(params)
+        np.frombuffer(self.shared, dtype=np.float32).reshape(self.shape)[:len(params)] = vp
+        bounds = np.linspace(0, len(params), self.cores + 1).astype(int)
+        return sum(self.pool.map(_cpu_worker_render, list(zip(bounds[:-1], bounds[1:])), chunksize=1))
 
     def time_steps(self, params, steps, warmup):
+        self.self_check(params)
         for _ in range(warmup):
             self.step(params)
         t0 = time.perf_counter()
@@ -106,6 +159,12 @@ class CpuArm:
     @property
     def kind(self):
         return "reference" if self.use_ref else "port"
+
+    def describe(self, steps):
+        return ("%d steps of the same %d-face batch: numpy float32 recon+projection (network.py:153-169) as one %d-thread GEMM + "
+                "%s, faces split over %d processes" % (steps, self.batch, self.cores,
+                                                      "the reference CPU op (oracle/_ref, render_depth_op.cc compiled in place)"
+                                                      if self.use_ref else "the oracle C port", self.cores))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -175,21 +234,58 @@ def _peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def _traffic(kernel_group):
+def _traffic(kernel):
     """dram bytes per launch from the committed ncu --set full capture (profiles/roofline_traffic.json), or None."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
-        return json.load(open(path)).get(kernel_group)
+        return json.load(open(path)).get(kernel)
     except Exception:
         return None
 
 
 def algorithmic_bytes(B, nver, ntri, K):
-    """compulsory HBM bytes per launch of B faces, split into the two kernel groups."""
+    """compulsory HBM bytes per launch of B faces, split into the recon part (basis + mean + params read,
+    vertex_proj written) and the render part (tri + vertex_proj read, depth + tri_ind written)."""
     n3 = 3 * nver
-    recon = 4 * (n3 * K + n3 + B * (7 + K) + B * n3)                 # basis + mean + params read, vertex_proj written
-    render = 4 * (3 * ntri + B * n3 + 2 * B * H * W)                 # tri + vertex_proj read, depth + tri_ind written
+    recon = 4 * (n3 * K + n3 + B * (7 + K) + B * n3)
+    render = 4 * (3 * ntri + B * n3 + 2 * B * H * W)
     return recon, render
+
+
+def fused_compulsory_bytes(B, nver, ntri, K):
+    """What the fused call cannot avoid: basis + mean + params + tri read, depth + tri_ind written (no vertex tensor)."""
+    n3 = 3 * nver
+    return 4 * (n3 * K + n3 + B * (7 + K) + 3 * ntri + 2 * B * H * W)
+
+
+def backward_bytes(B, nver, ntri, K):
+    """SURVEY.md 8(d) bytes_bwd(B)."""
+    n3 = 3 * nver
+    return 4 * (n3 * K + 3 * ntri + B * (2 * H * W + 2 * n3 + n3 + 2 * (7 + K)))
+
+
+def _numa_bind(local_rank):
+    """Best effort: pin this process (and so its pinned allocations' first touch) to the CPUs of the GPU's NUMA node."""
+    info = {"gpu_numa_node": None, "bound": False}
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout.strip().lower()
+        bus = out[4:] if out.startswith("0000") and len(out) > 12 else out          # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        info["gpu_numa_node"] = node
+        if node >= 0:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"] = True
+                info["cpus"] = len(cpus)
+    except Exception as exc:     # virtualised hosts often expose no topology: report it, carry on
+        info["error"] = type(exc).__name__
+    return info
 
 
 def run_ours(args):
@@ -198,6 +294,7 @@ def run_ours(args):
     pkg = importlib.import_module(PKG)
     synth = importlib.import_module(PKG + ".synth")
     dist = importlib.import_module(PKG + ".distributed")
+    sharding = importlib.import_module(PKG + ".sharding")
     rank, local_rank, world = dist.init_from_env()
     if world != args.gpus and rank == 0:
         print("note: WORLD_SIZE=%d but --gpus %d; using WORLD_SIZE" % (world, args.gpus), file=sys.stderr)
@@ -205,7 +302,8 @@ def run_ours(args):
     model = synth.make_synthetic_model(seed=0, jitter=0.2)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = CpuArm(model)                                            # fork the pool before CUDA is initialised
+        cpu = CpuArm(model, B)                                         # fork the pool before CUDA is initialised / the affinity changes
+    numa = _numa_bind(local_rank)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -216,61 +314,47 @@ def run_ours(args):
     K = ks + ke
     params_all = synth.sample_params_constrained(B * world, seed=2)
     params_host = params_all[rank * B:(rank + 1) * B]
-    params = torch.from_numpy(params_host).to(dev)
-    vertex = torch.empty((B, 3, nver), dtype=torch.float32, device=dev)
-    depth = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
-    tri_ind = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
-    rbytes = lib.fr_recon_workspace_bytes(B, nver, ks, ke)
-    mesh = dm.mesh.handle
-    ws = torch.empty(max(lib.fr_pipeline_workspace_bytes(B, nver, ks, ke, H, W),
-                         rbytes + lib.fr_render_workspace_bytes(B, nver, H, W)), dtype=torch.uint8, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
-    def step_full(vertex_ptr=None, events=None):
-        """The north-star call: params -> depth + tri_ind.  The intermediate vertex tensor is an optional output of the fused
-        call (the reconstruction epilogue hands the vertices to its rasterizer stage in shared memory); the timed loop does
-        not ask for it."""
-        check(lib.fr_recon_render_forward(params.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), mesh, vertex_ptr,
-                                          depth.data_ptr(), tri_ind.data_ptr(), B, nver, ntri, ks, ke, H, W, IM_SIZE,
-                                          dm.run_flags, ws.data_ptr(), ws.numel(), sp, events))
+    class Fused:
+        """Buffers + the fused call for one (model, batch)."""
+
+        def __init__(self, dmodel, params_np):
+            self.dm = dmodel
+            self.B = int(params_np.shape[0])
+            self.params = torch.from_numpy(np.ascontiguousarray(params_np, np.float32)).to(dev)
+            self.depth = torch.empty((self.B, H, W, 1), dtype=torch.float32, device=dev)
+            self.tri_ind = torch.empty((self.B, H, W, 1), dtype=torch.float32, device=dev)
+            self.rb = lib.fr_recon_workspace_bytes(self.B, dmodel.nver, ks, ke)
+            self.ws = torch.empty(lib.fr_pipeline_workspace_bytes(self.B, dmodel.nver, ks, ke, H, W), dtype=torch.uint8, device=dev)
+
+        def __call__(self, vertex_ptr=None, events=None):
+            d = self.dm
+            check(lib.fr_recon_render_forward(self.params.data_ptr(), d.packed.data_ptr(), d.tri.data_ptr(), d.mesh.handle, vertex_ptr,
+                                              self.depth.data_ptr(), self.tri_ind.data_ptr(), self.B, d.nver, d.ntri, ks, ke, H, W,
+                                              IM_SIZE, d.run_flags, self.ws.data_ptr(), self.ws.numel(), sp, events))
+
+    main = Fused(dm, params_host)
+    vertex = torch.empty((B, 3, nver), dtype=torch.float32, device=dev)
 
     def step_recon():
-        check(lib.fr_recon_project_forward(params.data_ptr(), dm.packed.data_ptr(), mesh, vertex.data_ptr(), B, nver, ks, ke, IM_SIZE,
-                                           dm.run_flags, ws.data_ptr(), rbytes, sp))
+        check(lib.fr_recon_project_forward(main.params.data_ptr(), dm.packed.data_ptr(), dm.mesh.handle, vertex.data_ptr(), B, nver,
+                                           ks, ke, IM_SIZE, dm.run_flags, main.ws.data_ptr(), main.rb, sp))
 
     def step_render():
-        check(lib.fr_render_depth_forward(vertex.data_ptr(), dm.tri.data_ptr(), None, 0, depth.data_ptr(), None, None,
-                                          tri_ind.data_ptr(), B, nver, ntri, H, W, mesh, ws.data_ptr() + rbytes, ws.numel() - rbytes, sp))
+        check(lib.fr_render_depth_forward(vertex.data_ptr(), dm.tri.data_ptr(), None, 0, main.depth.data_ptr(), None, None,
+                                          main.tri_ind.data_ptr(), B, nver, ntri, H, W, dm.mesh.handle, main.ws.data_ptr() + main.rb,
+                                          main.ws.numel() - main.rb, sp))
 
-    def timed_parts(steps, warmup):
-        """The fused step with an event recorded by the library between its reconstruction(+rasterizer) kernels and the resolve
-        pass (stage_events argument): device time of the two parts of the same real step, L2 flushed before every step."""
-        import ctypes
-        for _ in range(warmup):
-            flush.zero_()
-            step_full()
-        torch.cuda.synchronize(dev)
-        mids = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for (a, b), m in zip(evs, mids):
-            m.record(stream)                                           # creates the underlying cudaEvent
-            flush.zero_()
-            a.record(stream)
-            step_full(None, (ctypes.c_void_p * 2)(m.cuda_event, None))
-            b.record(stream)
-        torch.cuda.synchronize(dev)
-        recon = sum(a.elapsed_time(m) for (a, _), m in zip(evs, mids)) / steps
-        render = sum(m.elapsed_time(b) for (_, b), m in zip(evs, mids)) / steps
-        return recon, render
-
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, barrier=True):
         """Per-step CUDA-event timing on the launching stream, L2 flushed (outside the events) before every step."""
         for _ in range(warmup):
             flush.zero_()
             fn()
-        dist.barrier()
+        if barrier:
+            dist.barrier()
         torch.cuda.synchronize(dev)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in evs:
@@ -279,74 +363,137 @@ def run_ours(args):
             fn()
             b.record(stream)
         torch.cuda.synchronize(dev)
-        dist.barrier()
+        if barrier:
+            dist.barrier()
         return sum(a.elapsed_time(b) for a, b in evs) / steps          # ms per step
+
+    def timed_parts(call, steps, warmup):
+        """The fused step with events recorded by the library between its kernels (stage_events): device time of the
+        reconstruction kernels, the visibility kernel and the resolve kernel of the same real step, L2 flushed before each."""
+        for _ in range(warmup):
+            flush.zero_()
+            call()
+        torch.cuda.synchronize(dev)
+        rows = []
+        for _ in range(steps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            for e in ev[1:]:
+                e.record(stream)                                       # creates the underlying cudaEvent
+            flush.zero_()
+            ev[0].record(stream)
+            call(None, (ctypes.c_void_p * 3)(ev[1].cuda_event, ev[2].cuda_event, ev[3].cuda_event))
+            rows.append(ev)
+        torch.cuda.synchronize(dev)
+        return [sum(r[i].elapsed_time(r[i + 1]) for r in rows) / steps for i in range(3)]
 
     sampler = _clock_sampler_start(local_rank) if rank == 0 else (None, None)
     time.sleep(0.3 if rank == 0 else 0.0)                             # let nvidia-smi come up
     t_begin = time.time()
     launches0 = lib.fr_launch_count()
-    ms_full = timed(step_full, args.steps, args.warmup)
-    launches = (lib.fr_launch_count() - launches0)
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
-    ms_full_vertex = timed(lambda: step_full(vertex.data_ptr()), args.steps, args.warmup)   # same call, vertex_proj materialised too
-    ms_part_recon, ms_part_render = timed_parts(args.steps, args.warmup)
+    ms_full = timed(main, args.steps, args.warmup)
+    launches_timed = (lib.fr_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    ms_full_vertex = timed(lambda: main(vertex.data_ptr()), args.steps, args.warmup)   # same call, vertex_proj materialised too
+    ms_parts = timed_parts(main, args.steps, args.warmup)
     ms_recon = timed(step_recon, args.steps, args.warmup)
     ms_render = timed(step_render, args.steps, args.warmup)
+
+    # BASELINE configs[2]: 4096 faces sharded by batch over the ranks, the same fused call on each shard
+    c3_start, c3_count = sharding.shard_batch(CONFIG3_FACES, world, rank)
+    c3 = None
+    if not args.no_config3:
+        p3 = synth.sample_params_constrained(CONFIG3_FACES, seed=3)[c3_start:c3_start + c3_count]
+        shard = Fused(dm, p3)
+        ms_c3 = timed(shard, max(3, min(args.steps, 10)), 3)
+        c3 = {"ms": dist.reduce_scalar(ms_c3, "max"), "faces": int(dist.reduce_scalar(c3_count, "sum"))}
+        del shard
+
     # the timed loops last only milliseconds: keep the same step running so the 50 ms clock sampler sees it under load
     t_soak = time.time()
     while time.time() - t_soak < SOAK_SECONDS:
         for _ in range(20):
-            step_full()
+            main()
         torch.cuda.synchronize(dev)
     t_end = time.time()
     clocks = _clock_sampler_stop(*sampler, t_begin, t_end) if rank == 0 else None
-    ms_full_max = dist.reduce_scalar(ms_full, "max")
-    ms_recon_max = dist.reduce_scalar(ms_recon, "max")
-    ms_render_max = dist.reduce_scalar(ms_render, "max")
-    ms_full_vertex_max = dist.reduce_scalar(ms_full_vertex, "max")
-    ms_part_recon_max = dist.reduce_scalar(ms_part_recon, "max")
-    ms_part_render_max = dist.reduce_scalar(ms_part_render, "max")
-    faces_total = dist.reduce_scalar(B, "sum")
-    launches_total = int(dist.reduce_scalar(launches_timed, "sum"))
+    red = lambda v, op="max": dist.reduce_scalar(v, op)
+    ms_full_max, ms_full_vertex_max = red(ms_full), red(ms_full_vertex)
+    ms_parts_max = [red(v) for v in ms_parts]
+    ms_recon_max, ms_render_max = red(ms_recon), red(ms_render)
+    faces_total = red(B, "sum")
+    launches_total = int(red(launches_timed, "sum"))
 
-    # parity gate that travels with every measurement: a few faces of this very output against the CPU oracle
+    # parity gate that travels with every measurement: faces of this very output against the CPU oracle
     parity = None
     if rank == 0 and not args.no_parity:
         import oracle
         from oracle import recon as orecon
+        nchk = min(8, B)
+        main()
         torch.cuda.synchronize(dev)
-        depth_timed = depth.clone()
-        step_full(vertex.data_ptr())                                      # same call, this time materialising vertex_proj
+        depth_timed = main.depth.clone()
+        main(vertex.data_ptr())                                           # same call, this time materialising vertex_proj
         torch.cuda.synchronize(dev)
-        assert depth_timed.cpu().numpy().tobytes() == depth.cpu().numpy().tobytes()
-        vp = vertex[:2].cpu().numpy()
-        want_vp = orecon.vertices_transform(params_host[:2], model, IM_SIZE)
+        assert depth_timed.cpu().numpy().tobytes() == main.depth.cpu().numpy().tobytes()
+        sel = np.linspace(0, B - 1, nchk).astype(int)
+        vp = vertex[torch.from_numpy(sel).to(dev)].cpu().numpy()
+        want_vp = orecon.vertices_transform(params_host[sel], model, IM_SIZE)
         want = oracle.oracle_render_depth_forward(vp, model["tri"], model["vertex"], H, W)
-        parity = {"faces_checked": 2,
+        got_t = main.tri_ind.cpu().numpy()[sel]
+        got_d = main.depth.cpu().numpy()[sel]
+        parity = {"faces_checked": int(nchk),
                   "vertex_rel_err": float(np.abs(vp - want_vp).max() / np.abs(want_vp).max()),
-                  "tri_ind_bit_exact": bool(tri_ind[:2].cpu().numpy().tobytes() == want[3].tobytes()),
-                  "depth_bit_exact": bool(depth[:2].cpu().numpy().tobytes() == want[0].tobytes())}
+                  "tri_ind_bit_exact": bool(got_t.tobytes() == want[3].tobytes()),
+                  "depth_bit_exact": bool(got_d.tobytes() == want[0].tobytes())}
 
-    # other BASELINE configs, reported as extras (not the headline): config 4 = batch-256 forward + backward of the whole
-    # path (d depth -> d params through render_depth's backward and the recon backward), config 1 = batch-1 forward latency
+    peak, peak_src = _peak_hbm()
+
+    def roof(nbytes, ms):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"algorithmic_bytes": int(nbytes), "ms": ms, "achieved": gbs, "frac": gbs / peak}
+
+    # other BASELINE configs and flavours, reported as extras (not the headline)
     extras = None
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:
         net = importlib.import_module(PKG + ".nets.network")
         ops = importlib.import_module(PKG + ".rendering_layer.ops")
+        extras = {}
 
-        def time_torch(fn, reps):
+        def time_torch(fn, reps, flush_l2=False):
             for _ in range(3):
                 fn()
             torch.cuda.synchronize(dev)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
+            tot = 0.0
             for _ in range(reps):
+                if flush_l2:
+                    flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
                 fn()
-            b.record(stream)
-            torch.cuda.synchronize(dev)
-            return a.elapsed_time(b) / reps
+                b.record(stream)
+                torch.cuda.synchronize(dev)
+                tot += a.elapsed_time(b)
+            return tot / reps
 
+        # configs[0]: rendering_layer/sample_test.py -- one face, sample_test conventions (interleaved mean, Rz.Ry.Rx, y' = S - y),
+        # pose exactly [0,0,0,S/2,S/2,0,1e-3] (sample_test.py:23-38), all four render outputs, L2 flushed
+        dm_b = pkg.DeviceModel(model, dev, convention="sample_test")
+        p1 = torch.from_numpy(synth.sample_params_sample_test(seed=1).astype(np.float32)).to(dev)
+        img1 = torch.empty((1, H, W, 3), device=dev)
+
+        def fwd1():
+            with torch.no_grad():
+                vp1 = net.recon_project(p1, dm_b, IM_SIZE)
+                ops.render_depth(vp1, dm_b.tri, dm_b.vertex_code.unsqueeze(0), img1)
+
+        ms_1 = time_torch(fwd1, 20, flush_l2=True)
+        rb1, nb1 = algorithmic_bytes(1, nver, ntri, K)
+        extras["config1_b1_sample_test"] = dict(roof(rb1 + nb1 + 4 * (3 * nver + 6 * H * W), ms_1),
+                                                api="recon_project + render_depth (all four outputs), torch API, sample_test convention, "
+                                                    "L2 flushed before every call; bytes = SURVEY 8(d) bytes_fwd(1) + texture read + "
+                                                    "texture_image / normal written")
+        del dm_b
+
+        # configs[3]: batch-256 forward + backward of the whole path (d depth -> d params), torch API, all four render outputs
         B4 = 256
         p4 = torch.from_numpy(synth.sample_params_constrained(B4, seed=4)).to(dev).requires_grad_(True)
         img4 = torch.empty((B4, H, W, 3), device=dev)
@@ -355,52 +502,55 @@ def run_ours(args):
 
         def fwd_bwd():
             p4.grad = None
-            vp = net.recon_project(p4, dm, IM_SIZE)
-            d, _, _, ti = ops.render_depth(vp, dm.tri, tex4, img4)
-            (d * (gd4 * (ti >= 0))).sum().backward()
+            vp4 = net.recon_project(p4, dm, IM_SIZE)
+            d4, _, _, ti4 = ops.render_depth(vp4, dm.tri, tex4, img4)
+            (d4 * (gd4 * (ti4 >= 0))).sum().backward()
 
         def fwd_only4():
             with torch.no_grad():
-                vp = net.recon_project(p4, dm, IM_SIZE)
-                ops.render_depth(vp, dm.tri, tex4, img4)
+                vp4 = net.recon_project(p4, dm, IM_SIZE)
+                ops.render_depth(vp4, dm.tri, tex4, img4)
 
-        ms_fb = time_torch(fwd_bwd, 10)
-        ms_f4 = time_torch(fwd_only4, 10)
-        p1 = torch.from_numpy(synth.sample_params_constrained(1, seed=1)).to(dev)
-        img1 = torch.empty((1, H, W, 3), device=dev)
-
-        def fwd1():
-            with torch.no_grad():
-                vp = net.recon_project(p1, dm, IM_SIZE)
-                ops.render_depth(vp, dm.tri, dm.vertex_code.unsqueeze(0), img1)
-
-        ms_1 = time_torch(fwd1, 20)
-        # config 3's per-GPU share at 8 GPUs (512 faces) and the whole 4096-face batch on this one GPU, fused call, depth + tri_ind
-        big = {}
-        for B3 in (512, 4096):
-            p3 = torch.from_numpy(synth.sample_params_constrained(B3, seed=3)).to(dev)
-            d3 = torch.empty((B3, H, W, 1), dtype=torch.float32, device=dev)
-            t3 = torch.empty((B3, H, W, 1), dtype=torch.float32, device=dev)
-            ws3 = torch.empty(lib.fr_pipeline_workspace_bytes(B3, nver, ks, ke, H, W), dtype=torch.uint8, device=dev)
-
-            def fwd3():
-                check(lib.fr_recon_render_forward(p3.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), mesh, None, d3.data_ptr(),
-                                                  t3.data_ptr(), B3, nver, ntri, ks, ke, H, W, IM_SIZE, dm.run_flags, ws3.data_ptr(),
-                                                  ws3.numel(), sp, None))
-            ms3 = time_torch(fwd3, 5)
-            big["config3_b%d_fwd" % B3] = {"ms": ms3, "faces_per_s": B3 / (ms3 * 1e-3), "api": "fr_recon_render_forward, one call"}
-            del p3, d3, t3, ws3
-        extras = {"config4_b256_fwd_bwd": {"ms": ms_fb, "faces_per_s": B4 / (ms_fb * 1e-3), "fwd_only_ms": ms_f4,
-                                           "api": "recon_project + render_depth (all four outputs) + autograd backward, torch API, L2 warm"},
-                  "config1_b1_fwd": {"ms": ms_1, "api": "recon_project + render_depth (all four outputs), torch API, L2 warm"}}
-        extras.update(big)
+        ms_fb = time_torch(fwd_bwd, 10, flush_l2=True)
+        ms_f4 = time_torch(fwd_only4, 10, flush_l2=True)
+        rb4, nb4 = algorithmic_bytes(B4, nver, ntri, K)
+        b4 = rb4 + nb4 + backward_bytes(B4, nver, ntri, K)
+        extras["config4_b256_fwd_bwd"] = dict(roof(b4, ms_fb), faces_per_s=B4 / (ms_fb * 1e-3), fwd_only_ms=ms_f4,
+                                              with_extra_outputs=roof(b4 + B4 * 4 * (6 * H * W + 3 * nver), ms_fb),
+                                              api="recon_project + render_depth (all four outputs) + autograd backward, torch API, "
+                                                  "L2 flushed; bytes = SURVEY 8(d) bytes_fwd(256) + bytes_bwd(256)")
         del p4, img4, gd4
 
+        # the headline step on the same surface with randomly renumbered vertices and shuffled triangles
+        model_p = synth.make_synthetic_model(seed=0, jitter=0.2, permute=True)
+        dm_p = pkg.DeviceModel(model_p, dev)
+        fp = Fused(dm_p, params_host)
+        ms_perm = timed(fp, 10, 3, barrier=False)
+        extras["shuffled_mesh_b64"] = {"ms": ms_perm, "slowdown_vs_grid_order": ms_perm / ms_full_max,
+                                       "note": "same fused call; vertex / triangle numbering of the mesh randomly permuted -- the "
+                                               "mesh table's rank order supplies the locality"}
+        del fp, dm_p, model_p
+
+        # FR_CLUSTER_TILES flavour: cluster rasterizer inside the reconstruction epilogue
+        dm_c = pkg.DeviceModel(model, dev, cluster_tiles=True)
+        fc = Fused(dm_c, params_host)
+        ms_tiles = timed(fc, 10, 3, barrier=False)
+        torch.cuda.synchronize(dev)
+        main()
+        torch.cuda.synchronize(dev)
+        same = bool(torch.equal(fc.depth, main.depth) and torch.equal(fc.tri_ind, main.tri_ind))
+        extras["cluster_tiles_b64"] = {"ms": ms_tiles, "vs_default": ms_tiles / ms_full_max, "bit_identical_to_default": same,
+                                       "clusters": dm_c.mesh.nclusters, "vertex_slots": dm_c.mesh.vertex_slots}
+        del fc, dm_c
+
     # end to end through the host-buffer C-ABI session: every step copies its params in from pinned host memory and its
-    # depth maps back to pinned host memory inside the timed region.  The session's two slots are alternated
-    # (fr_session_submit / fr_session_wait) so the copy-out of step i overlaps the kernels of step i+1; the synchronous
-    # single-call latency (fr_session_forward) is reported next to it.
-    del ws, flush
+    # depth maps back to pinned host memory inside the timed region.  The session's slots are used round-robin
+    # (fr_session_submit / fr_session_wait) so the copy-out of step i overlaps the kernels of the following steps; the
+    # synchronous single-call latency (fr_session_forward) and a D2H-only loop over the same buffers are reported next to it.
+    main()
+    torch.cuda.synchronize(dev)
+    depth_ref = main.depth.cpu().numpy().tobytes() if rank == 0 else None
+    del main, vertex, flush
     sess = pkg.Session(model, H, W, max_batch=B, device=local_rank)
     nslots = pkg._lib.FR_SESSION_SLOTS
     pin_params = [torch.from_numpy(params_host.copy()).pin_memory() for _ in range(nslots)]
@@ -419,6 +569,19 @@ def run_ours(args):
         for _ in range(steps):
             sess.forward(pp[0], IM_SIZE, depth=pd[0], want_tri_ind=False)   # returns when depth is on the host
 
+    dsrc = torch.zeros((B, H, W, 1), dtype=torch.float32, device=dev)
+    copy_streams = [torch.cuda.Stream(dev) for _ in range(nslots)]
+
+    def d2h_only(steps):
+        """The result copy alone: the same bytes, the same pinned buffers, one stream per slot."""
+        for i in range(steps):
+            slot = i % nslots
+            copy_streams[slot].synchronize()
+            with torch.cuda.stream(copy_streams[slot]):
+                pin_depth[slot].copy_(dsrc, non_blocking=True)
+        for s in copy_streams:
+            s.synchronize()
+
     def wall(fn, steps):
         fn(max(3, args.warmup))
         dist.barrier()
@@ -431,69 +594,64 @@ def run_ours(args):
 
     e2e_sync_ms_max = wall(e2e_sync, args.steps)
     e2e_ms_max = wall(e2e_pipelined, args.steps)
-    want_depth = depth.cpu().numpy().tobytes()
-    e2e_ok = all(t.numpy().tobytes() == want_depth for t in pin_depth)
+    e2e_ok = all(t.numpy().tobytes() == depth_ref for t in pin_depth) if rank == 0 else None
+    d2h_ms_max = wall(d2h_only, args.steps)
     sess.close()
 
     cpu_baseline = None
     if cpu is not None:
         cpu_steps = 3
         sec = cpu.time_steps(params_host, cpu_steps, 1)
-        cpu_baseline = {"value": B / sec, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
-                        "sample": "%d steps of the same %d-face batch: numpy float32 recon+projection (network.py:153-169) + "
-                                  "%s, faces split over %d processes" %
-                                  (cpu_steps, B, "reference CPU op oracle/_ref" if cpu.use_ref else "oracle C port", cpu.cores)}
+        cpu_baseline = {"value": B / sec, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe(cpu_steps)}
         cpu.close()
 
     if rank == 0:
-        peak, peak_src = _peak_hbm()
         rb, nb = algorithmic_bytes(B, nver, ntri, K)
-        # dominant part of the timed (fused) step: reconstruction (prep + tcgen05 kernel) vs rasterizer (keys + resolve)
-        parts = {"recon_raster_part_of_step (recon_prep_f16 + recon_fwd_f16<raster> kernels)": (rb + nb - 8 * B * H * W, ms_part_recon_max),
-                 "render_resolve_part_of_step (raster_resolve kernel)": (8 * B * H * W, ms_part_render_max)}
-        dom = max(parts, key=lambda k: parts[k][1])
-        dbytes, dms = parts[dom]
-        achieved = dbytes / (dms * 1e-3) / 1e9
-        other = [k for k in parts if k != dom][0]
+        out_bytes = 8 * B * H * W
+        ms_rec, ms_keys, ms_res = ms_parts_max
+        d2h_bytes = int(pin_depth[0].numel() * 4)
         line = {
             "metric": METRIC, "value": faces_total / (ms_full_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full_max, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: batch-64 synthetic 235-d params -> 3DMM recon + pose projection + "
-                                   "200x200 depth render (depth + tri_ind), forward only, per GPU",
+            "config": {"workload": WORKLOAD,
                        "arithmetic": "f32 results; reconstruction on tcgen05 with fp16 hi/lo operand pairs (22 significant bits) and "
                                      "fp32 accumulation, rasterizer cull in packed integers and inside tests in separately rounded f64 "
                                      "(bit-exact with the reference)",
                        "batch_per_gpu": B, "nver": nver, "ntri": ntri, "ndim_shape": ks, "ndim_exp": ke, "image": [H, W],
                        "l2": "flushed before every timed step (512 MiB write, outside the events)",
-                       "call": "fr_recon_render_forward, depth + tri_ind out; the optional vertex_proj output is not requested in "
-                               "the timed loop (the parity check re-runs the call with it); groups_ms times the two separate "
-                               "entry points, which do materialise and re-read it",
+                       "call": "fr_recon_render_forward with the model's mesh table, depth + tri_ind out; the optional vertex_proj "
+                               "output is not requested in the timed loop (the parity check re-runs the call with it)",
                        "parallelism": "batch-sharded x%d, basis replicated, no collective" % world},
             "e2e": {"value": faces_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
-                    "h2d_bytes_per_step": int(pin_params[0].numel() * 4), "d2h_bytes_per_step": int(pin_depth[0].numel() * 4),
-                    "api": "fr_session_submit/fr_session_wait alternating over %d slots (host buffers, pinned; the copy-out "
-                           "of step i overlaps the kernels of step i+1)" % nslots,
+                    "h2d_bytes_per_step": int(pin_params[0].numel() * 4), "d2h_bytes_per_step": d2h_bytes,
+                    "api": "fr_session_submit/fr_session_wait round-robin over %d slots (host buffers, pinned; the copy-out of "
+                           "step i overlaps the kernels of the following steps)" % nslots,
                     "sync_call_ms": e2e_sync_ms_max, "sync_call_value": faces_total / (e2e_sync_ms_max * 1e-3),
-                    "matches_device_path": e2e_ok},
+                    "d2h_only_ms": d2h_ms_max, "d2h_only_gbs_per_gpu": d2h_bytes / (d2h_ms_max * 1e-3) / 1e9,
+                    "pcie_frac": d2h_ms_max / e2e_ms_max,
+                    "note": "d2h_only = the result copy alone (same bytes, same pinned buffers, max over ranks); pcie_frac = its share of "
+                            "the end-to-end step: near 1 means the host link, not the library, bounds e2e",
+                    "numa": numa, "matches_device_path": e2e_ok},
             "gpu_launches": launches_total,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": _traffic("render_part" if dom.startswith("render") else "recon_part"),
-                         "peak_source": peak_src, "algorithmic_bytes": dbytes, "ms": dms,
-                         "how": "device time between CUDA events of the same real step (the library records one between the "
-                                "two parts), algorithmic bytes per SURVEY.md 8(d)",
-                         "limiter": "the render part is bound by instruction issue and dependent gathers (profiles/r01_summary.md), "
-                                    "the recon part by HBM" if dom.startswith("render") else "HBM (basis stream + vertex records)",
-                         "other_part": {"kernel": other, "algorithmic_bytes": parts[other][0], "ms": parts[other][1],
-                                        "achieved": parts[other][0] / (parts[other][1] * 1e-3) / 1e9,
-                                        "frac": parts[other][0] / (parts[other][1] * 1e-3) / 1e9 / peak,
-                                        "traffic": _traffic("recon_part" if dom.startswith("render") else "render_part")},
-                         "whole_step": {"algorithmic_bytes": rb + nb, "ms": ms_full_max,
-                                        "achieved": (rb + nb) / (ms_full_max * 1e-3) / 1e9,
-                                        "frac": (rb + nb) / (ms_full_max * 1e-3) / 1e9 / peak},
-                         "fused_call_with_vertex_proj_output_ms": ms_full_vertex_max,
-                         "separate_entry_points_ms": {"fr_recon_project_forward": ms_recon_max,
-                                                      "fr_render_depth_forward": ms_render_max}},
+            "roofline": dict(roof(nb - out_bytes, ms_keys), bound="hbm", kernel="fr::raster_keys_kernel<8, true> (visibility pass)",
+                             peak=peak, unit="GB/s", traffic=_traffic("raster_keys_kernel"), peak_source=peak_src,
+                             how="device time between the CUDA events the library records before and after this kernel inside one "
+                                 "real fused call (stage_events, kernels serialised), L2 flushed before the call; bytes = SURVEY 8(d) "
+                                 "render part minus the resolve pass's outputs (tri + vertex data read)",
+                             limiter="instruction issue, not HBM: ~34 M warp instructions for 6.8 M (triangle, face) pairs "
+                                     "(exact integer cull + separately rounded FP64 inside tests), DESIGN.md 4.2",
+                             recon_kernels=roof(rb, ms_rec), resolve_kernel=roof(2 * out_bytes, ms_res),
+                             render_part=roof(nb, ms_keys + ms_res),
+                             whole_step={"survey_8d_bytes": roof(rb + nb, ms_full_max),
+                                         "with_vertex_proj_materialised": roof(rb + nb, ms_full_vertex_max),
+                                         "fused_compulsory_bytes": roof(fused_compulsory_bytes(B, nver, ntri, K), ms_full_max)},
+                             separate_entry_points_ms={"fr_recon_project_forward": ms_recon_max,
+                                                       "fr_render_depth_forward": ms_render_max}),
+            "config3": None if c3 is None else {
+                "workload": "BASELINE configs[2]: %d faces sharded by batch (shard_batch) over %d GPU(s), fused call per shard" % (c3["faces"], world),
+                "ms": c3["ms"], "value": c3["faces"] / (c3["ms"] * 1e-3), "unit": UNIT, "scaling": "strong",
+                "roofline_whole_step": roof(sum(algorithmic_bytes(-(-CONFIG3_FACES // world), nver, ntri, K)), c3["ms"])},
             "cpu_baseline": cpu_baseline, "clocks": clocks, "parity": parity, "extras": extras,
         }
         print(json.dumps(line))
@@ -510,18 +668,15 @@ def run_reference(args):
     B = args.batch
     model = synth.make_synthetic_model(seed=0, jitter=0.2)
     params = synth.sample_params_constrained(B, seed=2)
-    cpu = CpuArm(model)
-    steps, warmup = min(args.steps, 10), min(args.warmup, 2)
-    sec = cpu.time_steps(params, steps, max(1, warmup))
+    cpu = CpuArm(model, B)
+    sec = cpu.time_steps(params, args.steps, args.warmup)
     value = B / sec
-    sample = ("each step = the full %d-face batch: numpy float32 recon+projection + %s, faces split over %d processes"
-              % (B, "reference CPU op (oracle/_ref, render_depth_op.cc compiled in place)" if cpu.use_ref else "oracle C port", cpu.cores))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": max(1, warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: batch-64 synthetic 235-d params -> 3DMM recon + pose projection + "
-                                   "200x200 depth render, forward only, host CPU", "batch_per_gpu": B, "image": [H, W]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
+            "config": {"workload": WORKLOAD.replace("per GPU", "host CPU"), "batch_per_gpu": B, "image": [H, W]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
+                             "sample": "each step = the full %d-face batch: " % B + cpu.describe(args.steps).split(": ", 1)[1]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     cpu.close()
@@ -538,11 +693,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        args.warmup = max(args.warmup, 1)
         run_reference(args)
     else:
+        args.warmup = max(args.warmup, 3)
         run_ours(args)
 
 

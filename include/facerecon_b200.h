@@ -155,14 +155,15 @@ int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg
                                 int height, int width, void* stream);
 
 /* ---- fused: params -> depth map (the north-star path in one call) -------------------------------
- * Same results as fr_recon_project_forward followed by fr_render_depth_forward (depth + tri_ind only).  With a mesh
- * table and more than 8 faces it runs as three kernels: parameter prep (which also clears the visibility keys), the
- * tensor-core reconstruction whose epilogue projects each cluster's vertices into shared memory and rasterizes the
- * cluster's triangles from there, and the resolve pass -- the vertices never reach global memory.  vertex_proj
- * [batch,3,nver] is optional (NULL = do not materialise it).  Small batches / mesh == NULL run the two stages one after
- * the other through a planar vertex buffer in the workspace.
- * stage_events: NULL, or two cudaEvent_t (either may be NULL) recorded on `stream` after the reconstruction(+raster)
- * kernels and after the last kernel -- lets a benchmark split the device time of one real call. */
+ * Same results as fr_recon_project_forward followed by fr_render_depth_forward (depth + tri_ind only), in four kernels:
+ * parameter prep (which also clears the visibility keys), the tensor-core reconstruction whose epilogue writes the
+ * rasterizer's 16-byte vertex records (by vertex rank when a mesh table is given), the visibility pass and the resolve
+ * pass -- the repack pass over the vertex tensor disappears.  vertex_proj [batch,3,nver] is optional (NULL = do not
+ * materialise it).  With FR_CLUSTER_TILES (and more than 8 faces) the reconstruction epilogue instead rasterizes each cluster
+ * of the mesh table from shared memory: no records, three kernels.
+ * stage_events: NULL, or three cudaEvent_t (any may be NULL) recorded on `stream` after the reconstruction kernels, after
+ * the visibility kernel and after the resolve kernel -- lets a benchmark split the device time of one real call (the
+ * kernels then launch fully serialised instead of programmatically dependent). */
 size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim_exp, int height, int width);
 int fr_recon_render_forward(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
                             float* vertex_proj, float* depth, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
@@ -186,7 +187,7 @@ int fr_session_forward(fr_session* s, const float* params, int batch, float im_s
  * without waiting; fr_session_wait blocks until that batch's outputs are in the host buffers.  Alternating the slots
  * overlaps the device->host copy of one batch with the kernels of the next (pinned host buffers required for the
  * overlap; the host buffers of a slot must stay untouched until its wait).  fr_session_forward == submit + wait on slot 0. */
-#define FR_SESSION_SLOTS 2
+#define FR_SESSION_SLOTS 3
 int fr_session_submit(fr_session* s, int slot, const float* params, int batch, float im_size, float* depth, float* tri_ind,
                       float* vertex_proj);
 int fr_session_wait(fr_session* s, int slot);

@@ -42,10 +42,20 @@ def _check_table(tri, nver, table):
         assert (got == tri[k, orig].astype(np.int64)).all(), k
     assert (local >> 24 == 0).all()
     # the vertex-id flavour of the same list
+    # ranks: a permutation of the vertices in cluster order; the rank flavour of the triangle list
+    rv, vr = p["rank_vert"], p["vert_rank"]
+    assert (rv[:nver] >= 0).all() and (rv[nver:] == -1).all() and ((rv[:nver] & 0x40000000) != 0).all()
+    assert (np.sort(rv[:nver] & 0x00FFFFFF) == np.arange(nver)).all()
+    assert (vr[rv[:nver] & 0x00FFFFFF] == np.arange(nver)).all()
+    first_owner = np.full(nver, -1)
+    for c in range(ncl):
+        row = ids[c][owner[c]]
+        first_owner[row] = c
+    assert (np.diff(first_owner[rv[:nver] & 0x00FFFFFF]) >= 0).all()       # ranks follow the cluster order
     tq = p["tri_vid"]
     assert (tq[:, 3].astype(np.int64) == orig).all()
     for k in range(3):
-        assert (tq[:, k].astype(np.int64) == tri[k, orig].astype(np.int64)).all(), k
+        assert (tq[:, k].astype(np.int64) == vr[tri[k, orig].astype(np.int64)]).all(), k
     return p
 
 

@@ -1,7 +1,7 @@
 """Developer tool: runs the fused params -> depth-map call and the two stand-alone entry points a few times at batch B on the
 BFM-sized synthetic model -- a short command line for `ncu` captures (bench.py does much more).  Prints CUDA-event times.
 
-    python tools/prof_step.py [B] [reps] [permute]
+    python tools/prof_step.py [B] [reps] [grid|permute] [tiles]
 """
 import importlib
 import os
@@ -17,12 +17,13 @@ synth = importlib.import_module("3dfacerecon_b200.synth")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 permute = len(sys.argv) > 3 and sys.argv[3] == "permute"
+tiles = len(sys.argv) > 4 and sys.argv[4] == "tiles"          # FR_CLUSTER_TILES flavour (rasterizer inside the reconstruction epilogue)
 H = W = 200
 dev = torch.device("cuda:0")
 lib, check = pkg._lib.lib(), pkg._lib.check
 model = synth.make_synthetic_model(seed=0, jitter=0.2, permute=permute)
-dm = pkg.DeviceModel(model, dev, cache_dir=os.path.join(ROOT, "gpurun_out", "cache"))
-print("clusters", dm.mesh.nclusters, "vertex slots", dm.mesh.vertex_slots)
+dm = pkg.DeviceModel(model, dev, cluster_tiles=tiles)
+print("B", B, "permute", permute, "cluster_tiles", tiles, "clusters", dm.mesh.nclusters, "vertex slots", dm.mesh.vertex_slots)
 params = torch.from_numpy(synth.sample_params_constrained(B, seed=2)).to(dev)
 nver, ntri, ks, ke = dm.nver, dm.ntri, dm.ndim_shape, dm.ndim_exp
 mesh = dm.mesh.handle
