@@ -476,7 +476,9 @@ def run_ours(args):
 
         # configs[0]: rendering_layer/sample_test.py -- one face, sample_test conventions (interleaved mean, Rz.Ry.Rx, y' = S - y),
         # pose exactly [0,0,0,S/2,S/2,0,1e-3] (sample_test.py:23-38), all four render outputs, L2 flushed
-        dm_b = pkg.DeviceModel(model, dev, convention="sample_test")
+        model_b = dict(model)                     # the same surface with the mean stored interleaved, as sample_test.py:101 reads it
+        model_b["mu"] = np.ascontiguousarray(model["mu"].reshape(3, nver).T).reshape(3 * nver, 1)
+        dm_b = pkg.DeviceModel(model_b, dev, convention="sample_test")
         p1 = torch.from_numpy(synth.sample_params_sample_test(seed=1).astype(np.float32)).to(dev)
         img1 = torch.empty((1, H, W, 3), device=dev)
 
@@ -491,7 +493,7 @@ def run_ours(args):
                                                 api="recon_project + render_depth (all four outputs), torch API, sample_test convention, "
                                                     "L2 flushed before every call; bytes = SURVEY 8(d) bytes_fwd(1) + texture read + "
                                                     "texture_image / normal written")
-        del dm_b
+        del dm_b, model_b
 
         # configs[3]: batch-256 forward + backward of the whole path (d depth -> d params), torch API, all four render outputs
         B4 = 256
