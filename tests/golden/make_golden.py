@@ -14,6 +14,10 @@ Nothing under /root/reference is copied: its code is executed where it lies.
 * ``recon_B_*.npz``    -- outputs of ``rendering_layer/sample_test.py``'s own ``get_random_params`` /
                           ``rotation_matrix`` functions and of the numpy statements of its ``main()``
                           (:93-113), executed verbatim from the reference file.
+* ``layer_cases.npz``  -- outputs of the reference's own ``FaceRecNet.rendering_layer`` source (nets/network.py:172-201),
+                          executed against ``FakeTF`` with ``render_depth`` bound to the compiled reference op.
+* ``constraints.npz``  -- outputs of the reference's own ``FaceRecNet.set_constraints`` source (:204-218).
+* ``geometry_loss.npz``-- value of the geometry-loss statements of ``FaceRecNet.get_loss`` (:346-355), executed verbatim.
 """
 from __future__ import annotations
 
@@ -99,6 +103,55 @@ class FakeTF:
     def shape(x, name=None):
         return np.asarray(np.shape(x))
 
+    # ---- the further ops rendering_layer / set_constraints / the geometry loss use (float32 elementwise numpy)
+    @staticmethod
+    def to_float(x, name=None):
+        return _t(np.asarray(x, np.float32))
+
+    @staticmethod
+    def clip_by_value(x, lo, hi, name=None):
+        return _t(np.minimum(np.maximum(np.asarray(x), np.float32(lo)), np.float32(hi)))
+
+    @staticmethod
+    def where(cond, a, b, name=None):
+        return _t(np.where(np.asarray(cond), np.asarray(a), np.asarray(b)))
+
+    @staticmethod
+    def reduce_sum(x, axis=None, name=None):
+        x = np.asarray(x)
+        assert x.dtype == np.float32 and axis == -1 and x.shape[-1] == 3
+        return _t((x[..., 0] + x[..., 1]) + x[..., 2])        # Eigen reduces a 3-long inner axis in order
+
+    @staticmethod
+    def square(x, name=None):
+        x = np.asarray(x)
+        return _t(x * x)
+
+    @staticmethod
+    def zeros_like(x, name=None):
+        return _t(np.zeros_like(np.asarray(x)))
+
+    @staticmethod
+    def sqrt(x, name=None):
+        return _t(np.sqrt(np.asarray(x)))
+
+    @staticmethod
+    def maximum(x, y, name=None):
+        return _t(np.maximum(np.asarray(x), np.float32(y)))
+
+    class nn:
+        @staticmethod
+        def sigmoid(x, name=None):
+            x = np.asarray(x, np.float32)
+            return _t(np.float32(1) / (np.float32(1) + np.exp(-x)))
+
+    class losses:
+        @staticmethod
+        def mean_squared_error(labels, predictions, scope=None):
+            d = np.asarray(predictions, np.float32) - np.asarray(labels, np.float32)
+            return np.float32(np.sum((d * d).astype(np.float64)) / d.size)     # TF: float32 sum of squares / count; summed in
+                                                                               # float64 here so the golden is order-free
+
 
 def _extract_methods(path, class_name, names):
     tree = ast.parse(open(path).read(), path)
@@ -163,6 +216,61 @@ def reference_sample_test(model, im_size, seed):
     angles = np.random.uniform(-1.5, 1.5, (5, 3))
     rots = np.stack([ns["rotation_matrix"](list(a)) for a in angles])
     return params, ns["vertex_proj"], angles, rots
+
+
+def _ref_class(names, extra_ns=None):
+    """FaceRecNet methods `names`, extracted from the reference file and compiled against FakeTF."""
+    from math import cos, sin
+    path = os.path.join(REF, "nets", "network.py")
+    methods = _extract_methods(path, "FaceRecNet", names)
+    cls = ast.ClassDef(name="RefNet", bases=[], keywords=[], body=methods, decorator_list=[])
+    if hasattr(ast, "TypeVar"):
+        cls.type_params = []
+    mod = ast.fix_missing_locations(ast.Module(body=[cls], type_ignores=[]))
+    ns = {"np": np, "tf": FakeTF, "cos": cos, "sin": sin}
+    ns.update(extra_ns or {})
+    exec(compile(mod, path, "exec"), ns)
+    return ns["RefNet"]()
+
+
+def reference_rendering_layer(vertex_proj, tri, colors, im_gray):
+    """Run the reference's FaceRecNet.rendering_layer (network.py:172-201); its render_depth is the compiled reference op."""
+    def render_depth(ver, tri, texture, image):
+        return tuple(_t(a) for a in oracle.ref_render_depth(np.asarray(ver), np.asarray(tri), np.asarray(texture), np.shape(image)))
+    g = _ref_class(["rendering_layer"], {"render_depth": render_depth})
+    g.batch_size = vertex_proj.shape[0]
+    g.im_gray = _t(im_gray.astype(np.float32))
+    return [np.asarray(a, np.float32) for a in g.rendering_layer(vertex_proj.astype(np.float32), tri, colors)]
+
+
+def reference_set_constraints(raw, im_size, ks, ke):
+    """Run the reference's FaceRecNet.set_constraints (network.py:204-218) on raw [B,1,1,d]."""
+    g = _ref_class(["set_constraints"])
+    g.im_size, g.ndim_pose, g.ndim_shape, g.ndim_exp, g.ndim = im_size, 7, ks, ke, 7 + ks + ke
+    return np.asarray(g.set_constraints(_t(raw.astype(np.float32))), np.float32)
+
+
+def reference_geometry_loss(model, pred, label):
+    """Execute the geometry-loss statements of FaceRecNet.get_loss (network.py:346-355) verbatim."""
+    path = os.path.join(REF, "nets", "network.py")
+    get_loss = _extract_methods(path, "FaceRecNet", ["get_loss"])[0]
+    wanted = ("geometry_pred", "geometry_label", "geometry_basis", "loss_geometry")
+    stmts = []
+    for node in ast.walk(get_loss):
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name) and node.targets[0].id in wanted:
+            stmts.append(node)
+    stmts.sort(key=lambda n: n.lineno)
+    assert [n.targets[0].id for n in stmts] == list(wanted), [n.targets[0].id for n in stmts]
+
+    class Self:
+        pass
+    me = Self()
+    me.pred_params, me.params_label = _t(pred.astype(np.float32)[:, None, None, :]), _t(label.astype(np.float32)[:, None, None, :])
+    me.pc_shape, me.pc_exp = _t(model["pc_shape"].astype(np.float32)), _t(model["pc_exp"].astype(np.float32))
+    me.ndim_pose, me.ndim_shape, me.ndim_exp = 7, model["ndim_shape"], model["ndim_exp"]
+    ns = {"np": np, "tf": FakeTF, "self": me}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=stmts, type_ignores=[])), path, "exec"), ns)
+    return np.float32(ns["loss_geometry"])
 
 
 def small_model(grid, ks, ke, seed, jitter):
@@ -248,6 +356,33 @@ def main():
             blob[name + "/" + k] = a
         out["render_" + name] = int((tri_ind >= 0).sum())
     np.savez_compressed(os.path.join(HERE, "render_cases.npz"), **blob)
+
+    # ---------------- (f) rows: rendering_layer post-processing, set_constraints, geometry loss -- reference source executed
+    from oracle import recon
+    m = small_model((23, 31), 12, 5, 3, 0.2)                         # == tests/conftest.py small_model
+    B, S = 5, 64
+    p = synth.sample_params_constrained(B, 12, 5, S, seed=11)
+    vp = recon.vertices_transform(p, m, S, dtype=np.float32).astype(np.float32)
+    zs = vp[:, 2, :]
+    vp[:, 2, :] = ((zs - zs.mean()) / (zs.std() + 1e-9) * 0.6 + 0.5).astype(np.float32)   # depths straddle 1e-6 and 1: all clip regimes
+    gray = rng.uniform(0, 1, (B, S, S, 1)).astype(np.float32)
+    pncc, normalimg, maskimg, depthimg = reference_rendering_layer(vp, m["tri"], m["vertex"], gray)
+    np.savez_compressed(os.path.join(HERE, "layer_cases.npz"), vertex_proj=vp, tri=m["tri"], colors=m["vertex"], im_gray=gray,
+                        pncc=pncc, normalimg=normalimg, maskimg=maskimg, depthimg=depthimg)
+    out["layer"] = (int((depthimg > 1e-6).sum()), int((normalimg != 0).any(-1).sum()))
+
+    raw = rng.normal(scale=1.5, size=(7, 1, 1, 235)).astype(np.float32)
+    raw[0, 0, 0, :8] = [0.0, 40.0, -40.0, 100.0, -100.0, 3.0, -3.0, 0.5]      # saturated / extreme sigmoid arguments
+    np.savez_compressed(os.path.join(HERE, "constraints.npz"), raw=raw, im_size=200,
+                        constrained=reference_set_constraints(raw, 200, 199, 29))
+    out["constraints"] = raw.shape
+
+    mg = small_model((9, 11), 199, 29, 14, 0.2)
+    pred = synth.sample_params_constrained(6, seed=70)
+    label = synth.sample_params_constrained(6, seed=71)
+    np.savez_compressed(os.path.join(HERE, "geometry_loss.npz"), pred=pred, label=label, loss=reference_geometry_loss(mg, pred, label),
+                        grid=np.array((9, 11)), **model_arrays(mg))
+    out["geometry_loss"] = float(reference_geometry_loss(mg, pred, label))
     for k, v_ in out.items():
         print(k, v_)
 

@@ -344,6 +344,34 @@ def test_geometry_loss_gram_form(bfm):
     assert np.abs(got_grad[:, 7:] - want_grad).max() <= 1e-5 * np.abs(want_grad).max()
 
 
+def test_set_constraints_pinned_to_reference_source():
+    """SURVEY 8f-2 pinned: tests/golden/constraints.npz holds the output of the reference's own FaceRecNet.set_constraints
+    source (nets/network.py:204-218, executed by make_golden.py).  The torch mirror must reproduce it, and the prep kernels'
+    fused constraints (FR_PARAMS_RAW) must give the vertices of the reference-constrained parameters."""
+    g = np.load(os.path.join(GOLDEN, "constraints.npz"))
+    raw, want = g["raw"], g["constrained"]
+    model = fr("synth").make_synthetic_model(grid=(9, 11), seed=14, jitter=0.2)           # true K = 199 + 29
+    net = fr("nets.network").FaceRecNet(mesh_data=model, batch_size=raw.shape[0], im_size=int(g["im_size"]), device=DEV)
+    got = net.set_constraints(torch.from_numpy(raw).to(DEV)).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    assert (got[..., 5] == 0).all() and (want[..., 5] == 0).all()                          # network.py:213
+    vp_ref = net.vertices_transform(torch.from_numpy(want).to(DEV)).cpu().numpy()          # vertices of the reference-constrained params
+    vp_fused = net.vertices_transform_raw(torch.from_numpy(raw).to(DEV)).cpu().numpy()     # constraints inside the prep kernel
+    assert np.abs(vp_fused - vp_ref).max() <= 2e-6 * np.abs(vp_ref).max()
+
+
+def test_geometry_loss_pinned_to_reference_source():
+    """SURVEY 8f-3 pinned: tests/golden/geometry_loss.npz holds the value of the geometry-loss statements of the reference's
+    FaceRecNet.get_loss (nets/network.py:346-355, executed verbatim by make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, "geometry_loss.npz"))
+    model = _model_from_golden(g)
+    net = fr("nets.network").FaceRecNet(mesh_data=model, batch_size=g["pred"].shape[0], im_size=200, device=DEV)
+    loss = net.geometry_loss(torch.from_numpy(g["pred"]).to(DEV)[:, None, None, :], torch.from_numpy(g["label"]).to(DEV)[:, None, None, :])
+    want = float(g["loss"])
+    assert abs(float(loss) - want) <= 1e-5 * want, (float(loss), want)
+
+
 def test_facerecnet_mirror(bfm):
     """The FaceRecNet geometry slice end to end: default pred_params -> depth_rendering_layer (network.py:300-308)."""
     net = fr("nets.network").FaceRecNet(mesh_data=bfm, batch_size=2, im_size=200, device=DEV)

@@ -258,6 +258,32 @@ def test_rendering_layer_fused_matches_unfused(small_model):
     assert np.abs(grads[0] - grads[1]).max() <= 1e-6 * np.abs(grads[1]).max()
 
 
+def test_rendering_layer_pinned_to_reference_source(small_model):
+    """SURVEY 8f-1 pinned: tests/golden/layer_cases.npz holds the four outputs of the reference's own
+    FaceRecNet.rendering_layer source (nets/network.py:172-201) executed by make_golden.py with render_depth bound to the
+    compiled reference op.  The fused layer (post-processing inside the resolve kernel) and the un-fused torch mirror must
+    reproduce them: bit for bit where only selections / one multiply are involved, 2e-6 for the normalised normals."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "layer_cases.npz"))
+    B, S = g["im_gray"].shape[0], g["im_gray"].shape[1]
+    assert np.array_equal(g["tri"], small_model["tri"])                 # the golden was made on this very model
+    net = fr("nets.network").FaceRecNet(im_gray=torch.from_numpy(g["im_gray"]).to(DEV), mesh_data=small_model, batch_size=B, im_size=S,
+                                        device=DEV)
+    vp = torch.from_numpy(g["vertex_proj"]).to(DEV)
+    colors = torch.from_numpy(g["colors"]).to(DEV)
+    assert (g["depthimg"] > 1e-6).mean() > 0.02 and (g["depthimg"] == np.float32(1e-6)).any() and (g["maskimg"] > 0).any()
+    for layer in (net.rendering_layer, net.rendering_layer_unfused):
+        got = [t.cpu().numpy() for t in layer(vp, net.tri, colors)]
+        for a, name in zip(got, ("pncc", "normalimg", "maskimg", "depthimg")):
+            w = g[name]
+            assert a.shape == w.shape, name
+            if name == "normalimg":
+                assert np.abs(a - w).max() <= 2e-6, (layer.__name__, name)
+            else:
+                assert a.tobytes() == w.tobytes(), (layer.__name__, name)
+
+
 def test_full_size_properties_batch_256():
     """BASELINE config sizes (53 215 vertices, 105 840 triangles, 200 x 200), 256 faces -- too many for the CPU oracle in a
     test, so size-independent properties instead: (a) the 256-face call equals four 64-face calls byte for byte,
