@@ -384,3 +384,32 @@ def test_facerecnet_mirror(bfm):
     nrm = (net.normal_batch ** 2).sum(-1)
     cov = net.coarse_depth_map[..., 0] > 1e-6
     assert torch.allclose(nrm[cov], torch.ones_like(nrm[cov]), atol=1e-3)
+
+
+def test_device_model_tri_base_and_mesh_cache(small_model, tmp_path):
+    """The drop-in flow read_3dmm_model(path) -> FaceRecNet(mesh_data=...) with the BFM files' 1-based ``tri``: detected and
+    shifted with a warning (tri_base=None), stated explicitly (tri_base=1), or rejected when out of range; and the mesh
+    table's on-disk cache (cache_dir) gives the same table and the same results as a fresh build."""
+    model_mod = fr("model")
+    one_based = dict(small_model)
+    one_based["tri"] = small_model["tri"] + 1.0
+    assert one_based["tri"].max() == small_model["mu"].size // 3            # the last vertex is referenced
+    with pytest.warns(UserWarning, match="1-based"):
+        dm_auto = model_mod.DeviceModel(one_based, DEV)
+    dm_explicit = model_mod.DeviceModel(one_based, DEV, tri_base=1)
+    dm_zero = model_mod.DeviceModel(small_model, DEV, cache_dir=str(tmp_path))
+    assert dm_auto.tri_base == 1 and torch.equal(dm_auto.tri, dm_zero.tri) and torch.equal(dm_explicit.tri, dm_zero.tri)
+    with pytest.raises(ValueError, match="tri_base"):
+        model_mod.DeviceModel(one_based, DEV, tri_base=0)                   # index nver is out of range when taken as 0-based
+    files = list(tmp_path.iterdir())
+    assert len(files) == 1 and files[0].name.startswith("mesh_")
+    dm_cached = model_mod.DeviceModel(small_model, DEV, cache_dir=str(tmp_path))
+    assert dm_cached.mesh.blob().tobytes() == dm_zero.mesh.blob().tobytes()
+    files[0].write_bytes(files[0].read_bytes()[:-7])                        # a damaged cache entry is rebuilt, not trusted
+    dm_rebuilt = model_mod.DeviceModel(small_model, DEV, cache_dir=str(tmp_path))
+    assert dm_rebuilt.mesh.blob().tobytes() == dm_zero.mesh.blob().tobytes()
+    ks, ke = small_model["ndim_shape"], small_model["ndim_exp"]
+    p = torch.from_numpy(fr("synth").sample_params_constrained(12, ks, ke, 64, seed=5)).to(DEV)
+    want = fr("nets.network").recon_project(p, dm_zero, 64)
+    for dm in (dm_auto, dm_cached, dm_rebuilt):
+        assert torch.equal(fr("nets.network").recon_project(p, dm, 64), want)

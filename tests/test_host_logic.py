@@ -200,3 +200,33 @@ def test_backward_operand_arithmetic_budget():
     want = dv @ P
     err = np.abs(got - want).max(axis=1) / np.abs(want).max(axis=1)
     assert err.max() < 5e-6, err                                          # gradients are judged at 1e-4
+
+
+def test_read_3dmm_model_from_mat_files(tmp_path):
+    """utils/parser_3dmm.py:6-61 on real .mat files (written here with scipy.io.savemat in the BFM layout): same dict keys,
+    mu = mu_shape + mu_exp (:32), ndim_pose = 7 (:49), and the MATLAB 1-based ``tri`` is returned unshifted like the
+    reference does -- tri_is_one_based flags it for DeviceModel(tri_base=None)."""
+    sio = pytest.importorskip("scipy.io")
+    parser = fr("utils.parser_3dmm")
+    rng = np.random.default_rng(0)
+    n, t, ks, ke = 40, 60, 199, 29
+    shape = {"mu_shape": rng.normal(size=(3 * n, 1)).astype(np.float32), "w": rng.normal(size=(3 * n, ks)).astype(np.float32),
+             "tri": rng.integers(1, n + 1, (3, t)).astype(np.float64), "tex": rng.uniform(0, 255, (3, n)).astype(np.float32),
+             "w_tex": rng.normal(size=(3 * n, 5)).astype(np.float32), "alpha_tex": rng.normal(size=(5, 1)).astype(np.float32)}
+    shape["tri"][0, 0], shape["tri"][1, 0] = 1, n                     # both ends of the 1-based range occur
+    exp = {"mu_exp": rng.normal(size=(3 * n, 1)).astype(np.float32), "w_exp": rng.normal(size=(3 * n, ke)).astype(np.float32)}
+    code = {"vertex_code": rng.uniform(0, 1, (3, n)).astype(np.float32)}
+    sio.savemat(str(tmp_path / "Model_Shape.mat"), shape)
+    sio.savemat(str(tmp_path / "Model_Expression.mat"), exp)
+    sio.savemat(str(tmp_path / "vertex_code.mat"), code)
+    m = parser.read_3dmm_model(str(tmp_path))
+    assert sorted(m) == sorted(["vertex", "tri", "mu", "mu_tex", "pc_tex", "param_tex", "pc_shape", "pc_exp", "ndim_shape", "ndim_exp",
+                                "ndim_pose"])
+    assert np.array_equal(m["mu"], shape["mu_shape"] + exp["mu_exp"])
+    assert np.array_equal(m["pc_shape"], shape["w"]) and np.array_equal(m["pc_exp"], exp["w_exp"])
+    assert np.array_equal(m["vertex"], code["vertex_code"]) and np.array_equal(m["mu_tex"], shape["tex"])
+    assert (m["ndim_shape"], m["ndim_exp"], m["ndim_pose"]) == (ks, ke, 7)
+    assert np.array_equal(m["tri"], shape["tri"])                     # unshifted, as the reference returns it
+    assert parser.tri_is_one_based(m["tri"], n) and not parser.tri_is_one_based(m["tri"] - 1, n)
+    with pytest.raises(FileNotFoundError):
+        parser.read_3dmm_model(str(tmp_path / "missing"))
