@@ -109,20 +109,19 @@ class CpuArm:
         self.basis = np.ascontiguousarray(np.concatenate([model["pc_shape"], model["pc_exp"]], axis=1), np.float32)   # network.py:351 does the same concat
         self.mu = np.ascontiguousarray(np.asarray(model["mu"], np.float32).reshape(3 * nver, 1))
 
-    def recon(self, params):
+    def recon(self, params, out=None):
         """nets/network.py:153-169 in float32 numpy, laid out for speed: ONE [3N,228] x [228,B] GEMM on all BLAS threads (the
         reference issues two, :153,155), mean added, then the batched (f.R) v + t and the y flip.  Same values as the checker
         oracle.recon.vertices_transform(dtype=float32) up to float32 summation order (verified once in self_check)."""
         import numpy as np
         from oracle import recon
         p = np.asarray(params, np.float32)
-        coef_t = np.ascontiguousarray(p[:, 7:].T)                                 # [228, B]
-        v = self.basis @ coef_t                                                   # [3N, B]
-        v += self.mu
-        vb = np.ascontiguousarray(v.T).reshape(len(p), 3, self.nver)              # [B, 3, N] planar (network.py:154)
+        v = p[:, 7:] @ self.basis.T                                               # [B, 3N]: one GEMM (BLAS reads the basis transposed in place)
+        v += self.mu.T
+        vb = v.reshape(len(p), 3, self.nver)                                      # [B, 3, N] planar (network.py:154)
         rot = recon.rotation_matrix_batch(p[:, 0:3])                              # float64 sin/cos -> float32, network.py:292-297
         m = p[:, 6, None, None] * rot                                             # network.py:165
-        vp = np.matmul(m, vb)
+        vp = np.matmul(m, vb, out=out)
         vp += p[:, 3:6, None]
         vp[:, 1, :] = np.float32(IM_SIZE) - vp[:, 1, :] - np.float32(1)           # network.py:168
         return vp
@@ -138,8 +137,7 @@ class CpuArm:
 
     def step(self, params):
         import numpy as np
-        vp = self.recon(params)
-        np.frombuffer(self.shared, dtype=np.float32).reshape(self.shape)[:len(params)] = vp
+        self.recon(params, out=np.frombuffer(self.shared, dtype=np.float32).reshape(self.shape)[:len(params)])
         bounds = np.linspace(0, len(params), self.cores + 1).astype(int)
         return sum(self.pool.map(_cpu_worker_render, list(zip(bounds[:-1], bounds[1:])), chunksize=1))
 
