@@ -11,6 +11,7 @@
 #include "mesh_table.h"
 #include "raster.cuh"
 #include "raster_cluster.cuh"
+#include "raster_tile.cuh"
 #include "recon.cuh"
 #include "recon_f16.cuh"
 #include "recon_bwd_f16.cuh"
@@ -187,6 +188,12 @@ int check_render_dims(int batch, int nver, int ntri, int height, int width) {
   return FR_OK;
 }
 
+// Smallest batch that goes to the tile rasterizer (FR_TILE_KEYS = 0 disables it, n > 0 sets the threshold).
+int tile_keys_min_batch() {
+  static const int v = env_int("FR_TILE_KEYS", 8);
+  return v <= 0 ? (1 << 30) : v;
+}
+
 // Resolve pass: keys -> depth / tri_ind (+ normals, texture, rendering-layer post-processing).
 int launch_resolve(const unsigned long long* keys, const float* vertex, const float* tri, const float* texture,
                    long long texture_batch_stride, float* depth, float* texture_image, float* normal, float* tri_ind, int batch,
@@ -209,6 +216,20 @@ int launch_keys(const float4* rec, const float* tri, const fr_mesh_table* mesh, 
   const bool table = mesh != nullptr;
   const int nt = table ? mesh->hdr.ntri_slots : ntri;
   if (nt == 0) return FR_OK;
+  // With a mesh table and enough faces to fill a tile: the shared-memory tile rasterizer (raster_tile.cuh), one block per
+  // (cluster, 16 faces).  FR_TILE_KEYS=0 keeps the gather kernel below (A/B switch).
+  if (table && batch >= tile_keys_min_batch() && height <= rt::kMaxExtent && width <= rt::kMaxExtent) {
+#ifndef FR_TILE_NF
+#define FR_TILE_NF 16
+#endif
+    constexpr int NF = FR_TILE_NF;
+    const size_t smem = sizeof(rt::TileSmem<NF>);
+    FR_CUDA(cudaFuncSetAttribute(rt::raster_tile_keys_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FR_CUDA(launch_pdl(rt::raster_tile_keys_kernel<NF>, dim3(mesh->hdr.nclusters, ceil_div(batch, NF)), dim3(rt::kTileThreads), smem, st,
+                       dependent, rec, static_cast<const unsigned char*>(mesh->dev), keys, batch, nver, height, width));
+    FR_LAUNCHED("raster_tile_keys_kernel");
+    return FR_OK;
+  }
   const uint4* tv = table ? reinterpret_cast<const uint4*>(mesh->dev + mesh->hdr.off_tri_vid) : nullptr;
   const unsigned gx = (unsigned)ceil_div(nt, kKeysThreads);
 #define FR_LAUNCH_KEYS(FPT, TABLE)                                                                                              \
@@ -321,7 +342,7 @@ int fr_mesh_table_from_blob(const void* blob, size_t bytes, int device, fr_mesh_
                  (size_t)h.off_tri_begin + ((size_t)h.nclusters + 1) * 4 <= h.off_tri &&
                  (size_t)h.off_tri + (size_t)h.ntri_slots * 8 <= h.off_tri_vid &&
                  (size_t)h.off_tri_vid + (size_t)h.ntri_slots * 16 <= h.off_rank_vert && h.off_rank_vert <= h.off_vert_rank &&
-                 (size_t)h.off_vert_rank + (size_t)h.nver * 4 <= bytes,
+                 h.nver > 0 && (size_t)mesh_off_cluster_rank(h) + (size_t)h.nclusters * kClusterVerts * 4 <= bytes,
              "mesh table blob is inconsistent");
   const unsigned char* p = static_cast<const unsigned char*>(blob);
   uint32_t hash = 2166136261u;

@@ -73,19 +73,21 @@ FR_HD bool fr_tri_bbox(float x1, float y1, float x2, float y2, float x3, float y
   return true;
 }
 
-// IEEE x / 3.0f without the division sequence: q0 = x*c, q = fma(fma(-3,q0,x), c, q0) with c = RN(1/3) is the correctly
-// rounded quotient for every finite float (exhaustively verified over all 2^32 bit patterns, tools/div3_check.cu: the only
-// mismatches are +-inf, where the residual becomes NaN, and -0.0, which comes out as +0.0); zeros and huge / non-finite
-// inputs take the plain division.
+// IEEE x / 3.0f without the division sequence (and without its slow-path call): q0 = x*c, q = fma(fma(-3,q0,x), c, q0) with
+// c = RN(1/3) is the correctly rounded quotient for EVERY finite non-zero float, denormals included (exhaustively verified
+// over all 2^32 bit patterns, on the host with a correctly rounded fmaf and on the device by tools/div3_check.cu); +-0,
+// +-inf and NaN are their own quotients: x + x reproduces them (sign of zero kept, NaN quieted like the division does).
 FR_HD float fr_div3(float x) {
 #if defined(__CUDA_ARCH__)
-  if (fabsf(x) < 1.0e30f && x != 0.0f) {                     // (-0.0 must stay -0.0: the residual trick turns it into +0.0)
+  if ((__float_as_uint(x) & 0x7FFFFFFFu) - 1u < 0x7F7FFFFFu) {      // finite and non-zero
     const float c = 0.3333333432674407958984375f;
     const float q0 = __fmul_rn(x, c);
     return __fmaf_rn(__fmaf_rn(-3.0f, q0, x), c, q0);
   }
-#endif
+  return __fadd_rn(x, x);
+#else
   return FR_FDIV(x, 3.0f);
+#endif
 }
 
 // Flat depth of a triangle (:217): float adds left to right, IEEE float divide by 3.0f.
@@ -312,6 +314,131 @@ FR_HD bool fr_code_keep(uint32_t e1, uint32_t e2, uint32_t e3, uint32_t limit, u
   *lo_min = lo;
   *hi_max = hi;
   return (nonempty & inside_lo & inside_hi & G) == G;
+}
+
+// ---- cull on the raw packed min / max of the codes (tile rasterizer, raster_tile.cuh) ---------------
+// mn / mx = per-field minimum / maximum of the three snap codes (one VIMNMX3.U16x2 each).  With e = 2 ceil_b + s
+// (s = 1 when the coordinate is an integer): floor_b(max) + 1 = ((mx + 1) & ~1) / 2 and ceil_b(min) = mn / 2, so the
+// integer box is non-empty on an axis iff ((mx + 1) & ~1) - mn >= 1.  Needs code fields < 2^15 (extent <= 16000): the
+// field differences then stay below 2^15 and adding 0x7FFF turns ">= 1" into bit 15 of every field.
+// The image-range half of the reference's cull (:282) is NOT part of this test (see fr_box_in_image).
+FR_HD uint32_t fr_code_even_up(uint32_t mx) { return (mx + 0x00010001u) & 0xFFFEFFFEu; }   // per field 2 (floor_b(max) + 1)
+FR_HD bool fr_code_nonempty(uint32_t mn, uint32_t mx) {
+  return (((fr_code_even_up(mx) - mn) + 0x7FFF7FFFu) & 0x80008000u) == 0x80008000u;
+}
+// The box is exactly one pixel: floor_b(max) == ceil_b(min) on both axes (implies non-empty).
+FR_HD bool fr_code_single(uint32_t mn, uint32_t mx) { return (((fr_code_even_up(mx) - 0x00020002u) ^ mn) & 0xFFFEFFFEu) == 0u; }
+// Biased box corners (same values as fr_code_box): lo = x_min+1 | y_min+1 << 16, hi = x_max+1 | y_max+1 << 16.
+FR_HD uint32_t fr_code_lo(uint32_t mn) { return (mn >> 1) & 0x7FFF7FFFu; }
+FR_HD uint32_t fr_code_hi(uint32_t mx) { return ((fr_code_even_up(mx) >> 1) & 0x7FFF7FFFu) - 0x00010001u; }
+// x_min >= 0, y_min >= 0, x_max <= W-1, y_max <= H-1 on the biased corners; limit = W | H << 16.
+FR_HD bool fr_box_in_image(uint32_t lo, uint32_t hi, uint32_t limit) {
+  const uint32_t G = 0x80008000u;
+  return ((((lo | G) - 0x00010001u) & ((limit | G) - hi)) & G) == G;
+}
+
+// ---- certified fast inside test ------------------------------------------------------------------
+// PointInTri (:76-121) decides  u >= 0, v >= 0, u + v < 1  on u = (dot11 dot02 - dot01 dot12) inv, v = ..., ten rounded
+// double operations per pixel plus a division per triangle.  In exact arithmetic (Lagrange's identity)
+//     u den = c10 cu,   v den = c01 cv,   den = c10^2      c10 = v1 x v0,  cu = v1 x v2,  cv = v0 x v2  (2-D cross products)
+// so with s = sign(c10), C = |c10|:  u = s cu / C,  v = -s cv / C,  1 - u - v = (C - s cu + s cv) / C.
+// The fast test evaluates the three numerators  cu' = s cu,  cv' = -s cv,  cw' = C - cu' - cv'  in FLOAT (a dozen
+// operations per pixel, no conversion to double, no division) and only answers when the reference's rounded double
+// computation provably gives the same answer; everything else is "undecided" and takes the literal fr_point_in_tri.
+//
+// Let Lb >= every |component| of v0, v1, v2: the integer box is w x h pixels and all three vertices lie within one pixel
+// of it, so Lb = max(w, h) + 1 works; 2^e >= Lb^2 below.
+//  (1) The reference.  Its numerators / denominator carry an absolute error below E = 64 eps Lb^4 (eps = 2^-53: two rounded
+//      dot products of magnitude <= 2 Lb^2 with error <= 5 eps Lb^2 each, their rounded products, the rounded difference).
+//      If C > 2^-20 Lb^2 then den_ref > 0.99 C^2 > 0, and
+//        cu' >  2^-24 Lb^2  =>  num_u,ref >= C cu' - E > 0  =>  u_ref > 0        cu' < -2^-24 Lb^2  =>  u_ref < 0   (same for v)
+//        cw' >  2^-24 Lb^2  =>  u_ref + v_ref < 1 - 2 eps  (the rounded sum is < 1, hence also u_ref, v_ref <= 1)
+//        cw' < -2^-24 Lb^2  =>  u_ref + v_ref >= 1
+//      (the last two need C cw' > 3 E + 12.2 eps C Lb^2, and 3 E / C < 3 2^-27 Lb^2).
+//  (2) The float evaluation.  Every float difference (v0, v1, v2 components) has relative error <= 2^-24; a cross product
+//      a b - c d (one rounded product, one fused or rounded multiply-subtract) then has absolute error < 7.1 2^-24 Lb^2
+//      < 2^-21 Lb^2, and cw' (two more subtractions) < 34 2^-24 Lb^2 < 2^-18.9 Lb^2.
+//  So  |cu'_float| > 2^-17 2^e,  |cv'_float| > ...,  |cw'_float| > 2^-17 2^e  and  C_float > 2^-16 2^e  certify (1) with room to
+//  spare (thresholds are powers of two and compared on the float's bit pattern).  For sub-pixel triangles this leaves
+//  pixel centres within ~3e-5 px of an edge, slivers of area < 3e-5 px^2 and degenerate triangles (den == 0 paints the
+//  box, :105-109) to the literal path.  Coordinates are finite and inside (-1, 16000) here (the cull guarantees it), so
+//  nothing overflows; float underflow only makes a numerator 0 = undecided.
+struct FrTriFast {
+  float ax, ay;         // pt1
+  float v0x, v0y;       // pt3 - pt1  (the reference's v0)
+  float v1x, v1y;       // pt2 - pt1
+  float cabs;           // |c10|
+  uint32_t sigma;       // sign bit of c10
+  int32_t tol;          // bit pattern of the decision threshold 2^(e-17)
+  bool ok;              // C > 2^(e-16)
+};
+
+FR_HD uint32_t fr_fbits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c;
+  c.f = f;
+  return c.u;
+#endif
+}
+FR_HD float fr_fxor(float f, uint32_t mask) {      // flips bits of the pattern (sign changes)
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(__float_as_uint(f) ^ mask);
+#else
+  union { float f; uint32_t u; } c;
+  c.f = f;
+  c.u ^= mask;
+  return c.f;
+#endif
+}
+
+// Threshold pattern for a box of box_extent = max(w, h) pixels: 2^(e-17) with 2^e >= (box_extent + 1)^2.
+FR_HD int32_t fr_fast_tol(int box_extent) {
+  const uint32_t n = (uint32_t)box_extent + 1u, n2m1 = n * n - 1u;   // e = bit length of Lb^2 - 1
+#if defined(__CUDA_ARCH__)
+  const int e = 32 - __clz((int)n2m1);
+#else
+  const int e = n2m1 ? 32 - __builtin_clz(n2m1) : 0;
+#endif
+  return (int32_t)((uint32_t)(127 - 17 + e) << 23);
+}
+
+FR_HD void fr_fast_setup(float x1, float y1, float x2, float y2, float x3, float y3, int32_t tol, FrTriFast* f) {
+  f->ax = x1;
+  f->ay = y1;
+  f->v0x = x3 - x1;
+  f->v0y = y3 - y1;
+  f->v1x = x2 - x1;
+  f->v1y = y2 - y1;
+  const float c10 = f->v1x * f->v0y - f->v1y * f->v0x;      // (rounded or fused: both covered by the margins)
+  const uint32_t bits = fr_fbits(c10);
+  f->sigma = bits & 0x80000000u;
+  f->cabs = fr_fxor(c10, f->sigma);
+  f->tol = tol;
+  f->ok = (int32_t)(bits & 0x7FFFFFFFu) > tol + (1 << 23);
+}
+
+// 1 = inside, 0 = outside, -1 = undecided (run fr_point_in_tri).
+FR_HD int fr_fast_classify(const FrTriFast* f, int px, int py) {
+  const float v2x = (float)px - f->ax, v2y = (float)py - f->ay;
+  const float cu = f->v1x * v2y - f->v1y * v2x;
+  const float cv = f->v0x * v2y - f->v0y * v2x;
+  const float cup = fr_fxor(cu, f->sigma), cvp = fr_fxor(cv, f->sigma ^ 0x80000000u);
+  const float cwp = (f->cabs - cup) - cvp;
+  const int32_t hu = (int32_t)fr_fbits(cup), hv = (int32_t)fr_fbits(cvp), hw = (int32_t)fr_fbits(cwp);
+#if defined(__CUDA_ARCH__)
+  const int32_t mn = __vimin3_s32(hu, hv, hw);
+  const uint32_t mx = __vimax3_u32((uint32_t)hu, (uint32_t)hv, (uint32_t)hw);
+#else
+  const int32_t mn = hu < hv ? (hu < hw ? hu : hw) : (hv < hw ? hv : hw);
+  const uint32_t a = (uint32_t)hu, b = (uint32_t)hv, c = (uint32_t)hw;
+  const uint32_t mx = a > b ? (a > c ? a : c) : (b > c ? b : c);
+#endif
+  if (!f->ok) return -1;
+  if (mn > f->tol) return 1;                                   // all three numerators positive and above the threshold
+  if (mx > (0x80000000u | (uint32_t)f->tol)) return 0;         // one of them negative and below minus the threshold
+  return -1;
 }
 
 FR_HD void fr_snap_bbox(uint32_t lo_min, uint32_t hi_max, FrBBox* bb) {

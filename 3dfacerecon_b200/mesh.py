@@ -71,6 +71,8 @@ class MeshTable:
         nrank = (out["nver"] + 127) // 128 * 128
         out["rank_vert"] = b[off_rv:off_rv + nrank * 4].view(np.int32)
         out["vert_rank"] = b[off_vr:off_vr + out["nver"] * 4].view(np.int32)
+        off_cr = (off_vr + out["nver"] * 4 + 15) // 16 * 16
+        out["cluster_rank"] = b[off_cr:off_cr + ncl * 128 * 4].view(np.int32).reshape(ncl, 128)
         return out
 
     def close(self):

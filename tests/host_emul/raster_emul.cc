@@ -206,3 +206,76 @@ extern "C" long long fr_emul_check_snap_code(int width, int height, unsigned str
   }
   return bad;
 }
+
+// Tile rasterizer arithmetic (raster_tile.cuh): the raw-min/max cull must agree with fr_code_keep / fr_code_box, and the
+// certified fast inside test may only answer what the literal PointInTri answers.  Random sub-pixel triangles plus the
+// adversarial families: vertices on integer / half-integer coordinates, pixel centres exactly on edges and vertices,
+// slivers, degenerate and near-degenerate triangles, tiny and huge coordinates, large boxes.
+// Returns a negative code on a mismatch, else the number of pixel tests the fast test decided (out[0] = all tests).
+static uint64_t emul_rng(uint64_t* s) {
+  *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17;
+  return *s;
+}
+static float emul_unit(uint64_t* s) { return (float)(emul_rng(s) >> 40) * (1.0f / 16777216.0f); }
+
+extern "C" long long fr_emul_check_tile_arith(int width, int height, int ntrials, unsigned seed, long long* out) {
+  uint64_t st = 0x9E3779B97F4A7C15ull ^ ((uint64_t)seed << 1 | 1ull);
+  const uint32_t limit = (uint32_t)width | ((uint32_t)height << 16);
+  long long decided = 0, total = 0;
+  for (int it = 0; it < ntrials; ++it) {
+    float x[3], y[3];
+    const int family = (int)(emul_rng(&st) % 10);
+    const float cx = emul_unit(&st) * (float)(width + 4) - 2.0f, cy = emul_unit(&st) * (float)(height + 4) - 2.0f;
+    const float scale = (family == 9) ? 40.0f : ((family == 8) ? 6.0f : 1.5f);
+    for (int k = 0; k < 3; ++k) {
+      x[k] = cx + (emul_unit(&st) - 0.5f) * scale;
+      y[k] = cy + (emul_unit(&st) - 0.5f) * scale;
+    }
+    switch (family) {
+      case 0: for (int k = 0; k < 3; ++k) { x[k] = floorf(x[k]); y[k] = floorf(y[k]); } break;            // integer vertices
+      case 1: for (int k = 0; k < 3; ++k) { x[k] = floorf(x[k] * 2.0f) * 0.5f; y[k] = floorf(y[k] * 2.0f) * 0.5f; } break;
+      case 2: x[2] = x[0] + (x[1] - x[0]) * 0.5f; y[2] = y[0] + (y[1] - y[0]) * 0.5f; break;                // (nearly) collinear
+      case 3: x[1] = x[0]; y[1] = y[0]; break;                                                             // two equal vertices
+      case 4: x[0] = floorf(x[0]); y[0] = floorf(y[0]); break;                                             // pt1 on a pixel centre
+      case 5: y[0] = floorf(cy); y[1] = y[0]; break;                                                       // an edge through a pixel row
+      case 6: x[2] = x[0] + (x[1] - x[0]) * 0.5f + 1e-6f; y[2] = y[0] + (y[1] - y[0]) * 0.5f; break;        // sliver
+      default: break;
+    }
+    const uint32_t e1 = fr_snap_code(x[0], y[0], width, height), e2 = fr_snap_code(x[1], y[1], width, height),
+                   e3 = fr_snap_code(x[2], y[2], width, height);
+    uint32_t lo, hi;
+    const bool keep = fr_code_keep(e1, e2, e3, limit, &lo, &hi);
+    const uint32_t mn = fr_min3_u16x2(e1, e2, e3), mx = fr_max3_u16x2(e1, e2, e3);
+    uint32_t lo_ref, hi_ref;
+    fr_code_box(e1, e2, e3, &lo_ref, &hi_ref);
+    const bool nonempty_ref = (lo_ref & 0xFFFFu) <= (hi_ref & 0xFFFFu) && (lo_ref >> 16) <= (hi_ref >> 16);
+    if (fr_code_nonempty(mn, mx) != nonempty_ref) return -1;
+    if (nonempty_ref) {
+      if (fr_code_lo(mn) != lo_ref || fr_code_hi(mx) != hi_ref) return -2;
+      if (fr_code_single(mn, mx) != (lo_ref == hi_ref)) return -3;
+      if ((fr_code_nonempty(mn, mx) && fr_box_in_image(fr_code_lo(mn), fr_code_hi(mx), limit)) != keep) return -4;
+    } else if (keep) {
+      return -5;
+    }
+    if (!keep) continue;
+    FrBBox bb;
+    fr_snap_bbox(lo, hi, &bb);
+    FrTriEdge e;
+    fr_tri_edge_setup(x[0], y[0], x[1], y[1], x[2], y[2], &e);
+    const int ext = (bb.x_max - bb.x_min > bb.y_max - bb.y_min ? bb.x_max - bb.x_min : bb.y_max - bb.y_min) + 1;
+    FrTriFast ff;
+    fr_fast_setup(x[0], y[0], x[1], y[1], x[2], y[2], fr_fast_tol(ext), &ff);
+    for (int py = bb.y_min; py <= bb.y_max; ++py)
+      for (int px = bb.x_min; px <= bb.x_max; ++px) {
+        const int fast = fr_fast_classify(&ff, px, py);
+        const bool exact = fr_point_in_tri(&e, px, py);
+        ++total;
+        if (fast >= 0) {
+          ++decided;
+          if ((fast == 1) != exact) return -10 - family;
+        }
+      }
+  }
+  if (out) out[0] = total;
+  return decided;
+}

@@ -52,6 +52,8 @@ def _check_table(tri, nver, table):
         row = ids[c][owner[c]]
         first_owner[row] = c
     assert (np.diff(first_owner[rv[:nver] & 0x00FFFFFF]) >= 0).all()       # ranks follow the cluster order
+    cr = p["cluster_rank"]                                                   # where the tile rasterizer finds a slot's record
+    assert cr.shape == cv.shape and (cr[~used] == -1).all() and (cr[used] == vr[ids[used]]).all()
     tq = p["tri_vid"]
     assert (tq[:, 3].astype(np.int64) == orig).all()
     for k in range(3):

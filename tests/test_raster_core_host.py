@@ -145,3 +145,18 @@ def test_clustered_emulation_matches_oracle(emul, render_golden):
         d, t = run(v, tri, 8, 8, None)
         assert d.tobytes() == want[0].tobytes() and t.tobytes() == want[3].tobytes()
         assert (np.signbit(want[0][want[3] >= 0]) == (tri[0, 0] == 0)).all()
+
+
+def test_tile_cull_and_certified_fast_inside_test(emul):
+    """The tile rasterizer's arithmetic (raster_core.h, used by raster_tile.cuh): the cull on the raw packed min / max of the
+    snap codes equals fr_code_keep / fr_code_box, and the float fast inside test never contradicts the literal PointInTri
+    -- over random and adversarial triangles (integer vertices, pixel centres on edges, slivers, degenerate triangles, large
+    boxes).  It must also decide nearly every test of generic sub-pixel triangles, or it would not be a fast path."""
+    lib = emul.lib
+    lib.fr_emul_check_tile_arith.restype = ctypes.c_longlong
+    lib.fr_emul_check_tile_arith.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.POINTER(ctypes.c_longlong)]
+    for (w, h, n, seed) in ((200, 200, 2_000_000, 1), (7, 5, 300_000, 2), (16000, 9000, 300_000, 3)):
+        total = ctypes.c_longlong(0)
+        decided = lib.fr_emul_check_tile_arith(w, h, n, seed, ctypes.byref(total))
+        assert decided >= 0, (w, h, decided)
+        assert total.value > n // 10 and decided > 0.5 * total.value, (w, h, decided, total.value)
