@@ -10,7 +10,6 @@
 #include "fr_common.cuh"
 #include "mesh_table.h"
 #include "raster.cuh"
-#include "raster_cluster.cuh"
 #include "raster_tile.cuh"
 #include "recon.cuh"
 #include "recon_f16.cuh"
@@ -123,11 +122,6 @@ const int32_t* mesh_rank_vert(const fr_mesh_table* mesh) {
 const int32_t* mesh_vert_rank(const fr_mesh_table* mesh) {
   return mesh ? reinterpret_cast<const int32_t*>(mesh->dev + mesh->hdr.off_vert_rank) : nullptr;
 }
-// The vertex behind every row of the tensor-core forward operand tiles: cluster lists (FR_CLUSTER_TILES), rank order (any
-// other basis packed with a mesh table), null = consecutive vertex ids (packed without a table).
-const int32_t* mesh_row_vert(const fr_mesh_table* mesh, unsigned flags) {
-  return (flags & FR_CLUSTER_TILES) ? mesh_cluster_vert(mesh) : mesh_rank_vert(mesh);
-}
 
 // Tensor-core path for this batch?  (FR_RECON_PATH = simt | f16 overrides the dispatch, for A/B comparisons.)
 bool use_f16_forward(const BasisGeom& g, int batch, bool raster) {
@@ -156,12 +150,13 @@ int recon_project_forward_impl(const float* params, const float* packed, const f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + ndim_shape + ndim_exp;
-  const int32_t* cluster_vert = mesh_row_vert(mesh, flags);
 
   if (target != nullptr || use_f16_forward(g, batch, false)) {
     const bool fold = clear_keys != nullptr && clear_bytes % 16 == 0;     // the prep kernel clears the keys itself, 16 bytes at a time
     if (clear_keys != nullptr && !fold) FR_CUDA(cudaMemsetAsync(clear_keys, 0, clear_bytes, st));
-    return launch_recon_fwd_f16(params, packed, w.bsplit16, w.pose16, out, target, cluster_vert, fold ? clear_keys : nullptr,
+    // row map of the operand tiles: the cluster lists for the raster flavour, else rank order (null without a table)
+    const int32_t* row_vert = target != nullptr ? mesh_cluster_vert(mesh) : mesh_rank_vert(mesh);
+    return launch_recon_fwd_f16(params, packed, w.bsplit16, w.pose16, out, target, row_vert, fold ? clear_keys : nullptr,
                                 fold ? clear_bytes : 0, batch, nver, g, im_size, flags, sm_count(), st);
   }
   if (clear_keys != nullptr) FR_CUDA(cudaMemsetAsync(clear_keys, 0, clear_bytes, st));
@@ -399,12 +394,18 @@ int fr_pack_basis(const float* mu, const float* pc_shape, const float* pc_exp, i
   FR_LAUNCHED("basis_colmax_kernel");
   f16::basis_colscale_kernel<<<ceil_div(g.kpad16, 256), 256, 0, st>>>(scale, g.kreal, g.kpad16);
   FR_LAUNCHED("basis_colscale_kernel");
-  const size_t pieces = (size_t)g.nclusters * 3 * g.nch16 * 2 * kTileVerts;       // one 128-row tile per cluster (mesh_table.h)
+  const size_t pieces = (size_t)g.ntiles * 3 * g.nch16 * 2 * kTileVerts;          // tiles of 128 consecutive vertices / ranks
   f16::pack_basis_f16_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(mu, pc_shape, pc_exp, scale, nver, ndim_shape, ndim_exp,
-                                                                              g.nch16, g.nclusters, layout_flags,
-                                                                              mesh_row_vert(mesh, layout_flags),
+                                                                              g.nch16, g.ntiles, layout_flags, mesh_rank_vert(mesh),
                                                                               reinterpret_cast<uint4*>(base + g.f16_offset()));
   FR_LAUNCHED("pack_basis_f16_kernel");
+  if (g.nclusters > 0) {                                                         // ... and one 128-row tile per cluster (mesh_table.h)
+    const size_t cpieces = (size_t)g.nclusters * 3 * g.nch16 * 2 * kTileVerts;
+    f16::pack_basis_f16_kernel<<<(unsigned)((cpieces + 255) / 256), 256, 0, st>>>(mu, pc_shape, pc_exp, scale, nver, ndim_shape, ndim_exp,
+                                                                                 g.nch16, g.nclusters, layout_flags, mesh_cluster_vert(mesh),
+                                                                                 reinterpret_cast<uint4*>(base + g.f16c_offset()));
+    FR_LAUNCHED("pack_basis_f16_kernel");
+  }
   // ... and the same pairs transposed for the backward contraction over the vertices
   const size_t bpieces = (size_t)g.ntiles * 3 * (kTileVerts / 16) * g.mtiles() * 2 * kTileVerts;
   b16::pack_basis_bwd_kernel<<<(unsigned)((bpieces + 255) / 256), 256, 0, st>>>(pc_shape, pc_exp, scale, nver, ndim_shape, ndim_exp,

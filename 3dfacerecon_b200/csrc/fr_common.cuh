@@ -65,15 +65,19 @@ struct BasisGeom {
   int kpad16;  // kreal rounded up to 16 (fp16-pair sections: one f16 MMA K step per chunk)
   int nch16;   // kpad16 / 16 chunks per (tile, coordinate) row
   int ntiles;  // ceil(nver / 128): tiles of consecutive vertices (fp32 section, backward section, mean)
-  int nclusters;  // row tiles of the tensor-core forward section: the mesh table's clusters (mesh_table.h), or ntiles
-                  // tiles of consecutive vertices when the basis is packed without a mesh table
+  int nclusters;  // > 0: the packed basis carries a SECOND tensor-core forward section whose row tiles are the mesh table's
+                  // clusters (FR_CLUSTER_TILES; the fused call rasterizes from it); 0: none
   // Sections of the packed basis (DESIGN.md "Packed basis"), in this order; only the last one depends on the mesh table:
   //   [0, f32_bytes)                  fp32, float4-tiled: SIMT forward (small batches) and SIMT backward
   //   [scale_offset, +4 kpad16)       2^-s_k per column (what a coefficient is multiplied by to undo the column scale)
   //   [bwd_offset, +bwd_bytes)        fp16 hi/lo pairs of the column-scaled basis, transposed for the backward contraction over
   //                                   the vertices: per (tile, coordinate, 16-vertex chunk)  [hi m0 | hi m1 | lo m0 | lo m1]  with 128 k rows each
   //   [mean_offset, +mean_bytes)      the mean once more as plain fp32 [3][ntiles*128] (the backward contracts it in fp32)
-  //   [f16_offset, +f16_bytes)        fp16 hi/lo pairs in tcgen05 operand tiles, one 128-row tile per cluster: tensor-core forward
+  //   [f16_offset, +f16_bytes)        fp16 hi/lo pairs in tcgen05 operand tiles of 128 consecutive vertices (vertex RANKS when
+  //                                   packed with a mesh table): tensor-core forward writing vertex_proj / vertex records
+  //   [f16c_offset, +f16c_bytes)      the same operand tiles once more, one 128-row tile per CLUSTER of the mesh table (border
+  //                                   vertices repeated in every member cluster): tensor-core forward with the tile
+  //                                   rasterizer in its epilogue (only with FR_CLUSTER_TILES)
   size_t tile_floats() const { return (size_t)3 * kg * kTileVerts * 4; }
   size_t f32_bytes() const { return (size_t)ntiles * tile_floats() * sizeof(float); }
   size_t scale_offset() const { return (f32_bytes() + 1023) / 1024 * 1024; }
@@ -83,8 +87,10 @@ struct BasisGeom {
   size_t mean_offset() const { return bwd_offset() + bwd_bytes(); }
   size_t mean_bytes() const { return (size_t)3 * ntiles * kTileVerts * sizeof(float); }
   size_t f16_offset() const { return (mean_offset() + mean_bytes() + 1023) / 1024 * 1024; }
-  size_t f16_bytes() const { return (size_t)nclusters * 3 * nch16 * 8192; }
-  size_t bytes() const { return f16_offset() + f16_bytes(); }
+  size_t f16_bytes() const { return (size_t)ntiles * 3 * nch16 * 8192; }
+  size_t f16c_offset() const { return f16_offset() + f16_bytes(); }
+  size_t f16c_bytes() const { return (size_t)nclusters * 3 * nch16 * 8192; }
+  size_t bytes() const { return f16c_offset() + f16c_bytes(); }
 };
 inline BasisGeom basis_geom(int nver, int ks, int ke, int nclusters = 0) {
   BasisGeom g;
@@ -97,7 +103,7 @@ inline BasisGeom basis_geom(int nver, int ks, int ke, int nclusters = 0) {
   g.kpad16 = (g.kreal + 15) / 16 * 16;
   g.nch16 = g.kpad16 / 16;
   g.ntiles = (nver + kTileVerts - 1) / kTileVerts;
-  g.nclusters = nclusters > 0 ? nclusters : g.ntiles;
+  g.nclusters = nclusters > 0 ? nclusters : 0;
   return g;
 }
 

@@ -283,11 +283,15 @@ FR_HD uint32_t fr_snap_code_literal(float x, float y, int width, int height) {  
 // NaN) both clamp to 0 -> e = 1; at or above extent both clamp to extent + 1 -> e = 2 extent + 3.
 // tests/host_emul checks it against fr_snap_code_literal over a sweep of float bit patterns.
 FR_HD uint32_t fr_snap_code_axis(float v, int extent) {
-  const float t = floorf(v);
-  uint32_t e = (uint32_t)(2 * (int)t + 4) - ((t == v) ? 1u : 0u);
-  if (!(v > -1.0f)) e = 1u;
-  if (v >= (float)extent) e = 2u * (uint32_t)extent + 3u;
-  return e;
+  // clamp first: at -1 (also NaN: fmaxf returns the other operand) floor = -1 and "integer" give e = 1, at extent e = 2 extent + 3
+#if defined(__CUDA_ARCH__)
+  const float c = fminf(fmaxf(v, -1.0f), (float)extent);        // (CUDA's fmaxf returns the non-NaN operand)
+#else
+  const float lo = (v > -1.0f) ? v : -1.0f;                      // NaN -> -1, spelled out: host fmaxf may be lowered to maxss
+  const float c = (lo < (float)extent) ? lo : (float)extent;
+#endif
+  const float t = floorf(c);
+  return (uint32_t)(2 * (int)t + 3) + ((t != c) ? 1u : 0u);
 }
 
 FR_HD uint32_t fr_snap_code(float x, float y, int width, int height) {
@@ -438,6 +442,65 @@ FR_HD int fr_fast_classify(const FrTriFast* f, int px, int py) {
   if (!f->ok) return -1;
   if (mn > f->tol) return 1;                                   // all three numerators positive and above the threshold
   if (mx > (0x80000000u | (uint32_t)f->tol)) return 0;         // one of them negative and below minus the threshold
+  return -1;
+}
+
+// The same test for the pixels of a larger box: the three numerators are linear in the pixel, so they are evaluated as
+// plane equations around the box origin (x0, y0):  c(x0 + dx, y0 + dy) = c0 + dx cx + dy cy  (two fused multiply-adds each,
+// dx / dy small exact integers).  Error budget: c0 as in fr_fast_classify (< 2^-21 Lb^2, cw' < 2^-18.9 Lb^2), the slopes are
+// the edge components themselves (cw's: one float addition, 2^-24 relative), each fma rounds once (<= 2^-23 Lb^2): the
+// totals stay below 2^-20.4 Lb^2 resp. 2^-18.6 Lb^2, inside the same thresholds.
+struct FrTriPlanes {
+  float u0, ux, uy;     // cu'
+  float v0, vx, vy;     // cv'
+  float w0, wx, wy;     // cw' = C - cu' - cv'
+  int32_t tol;
+  bool ok;
+};
+
+FR_HD void fr_planes_setup(float x1, float y1, float x2, float y2, float x3, float y3, int x0, int y0, int32_t tol, FrTriPlanes* p) {
+  FrTriFast f;
+  fr_fast_setup(x1, y1, x2, y2, x3, y3, tol, &f);
+  const float v2x = (float)x0 - f.ax, v2y = (float)y0 - f.ay;
+  const float cu = f.v1x * v2y - f.v1y * v2x;
+  const float cv = f.v0x * v2y - f.v0y * v2x;
+  const uint32_t su = f.sigma, sv = f.sigma ^ 0x80000000u;
+  p->u0 = fr_fxor(cu, su);                 // cu = v1x (y - ay) - v1y (x - ax):  d/dx = -v1y,  d/dy = v1x
+  p->ux = fr_fxor(f.v1y, su ^ 0x80000000u);
+  p->uy = fr_fxor(f.v1x, su);
+  p->v0 = fr_fxor(cv, sv);
+  p->vx = fr_fxor(f.v0y, sv ^ 0x80000000u);
+  p->vy = fr_fxor(f.v0x, sv);
+  p->w0 = (f.cabs - p->u0) - p->v0;
+  p->wx = -(p->ux + p->vx);
+  p->wy = -(p->uy + p->vy);
+  p->tol = tol;
+  p->ok = f.ok;
+}
+
+// dx, dy: pixel offsets from the box origin as floats.  1 = inside, 0 = outside, -1 = undecided.
+FR_HD int fr_planes_classify(const FrTriPlanes* p, float dx, float dy) {
+#if defined(__CUDA_ARCH__)
+  const float cu = __fmaf_rn(dy, p->uy, __fmaf_rn(dx, p->ux, p->u0));
+  const float cv = __fmaf_rn(dy, p->vy, __fmaf_rn(dx, p->vx, p->v0));
+  const float cw = __fmaf_rn(dy, p->wy, __fmaf_rn(dx, p->wx, p->w0));
+#else
+  const float cu = fmaf(dy, p->uy, fmaf(dx, p->ux, p->u0));
+  const float cv = fmaf(dy, p->vy, fmaf(dx, p->vx, p->v0));
+  const float cw = fmaf(dy, p->wy, fmaf(dx, p->wx, p->w0));
+#endif
+  const int32_t hu = (int32_t)fr_fbits(cu), hv = (int32_t)fr_fbits(cv), hw = (int32_t)fr_fbits(cw);
+#if defined(__CUDA_ARCH__)
+  const int32_t mn = __vimin3_s32(hu, hv, hw);
+  const uint32_t mx = __vimax3_u32((uint32_t)hu, (uint32_t)hv, (uint32_t)hw);
+#else
+  const int32_t mn = hu < hv ? (hu < hw ? hu : hw) : (hv < hw ? hv : hw);
+  const uint32_t a = (uint32_t)hu, b = (uint32_t)hv, c = (uint32_t)hw;
+  const uint32_t mx = a > b ? (a > c ? a : c) : (b > c ? b : c);
+#endif
+  if (!p->ok) return -1;
+  if (mn > p->tol) return 1;
+  if (mx > (0x80000000u | (uint32_t)p->tol)) return 0;
   return -1;
 }
 

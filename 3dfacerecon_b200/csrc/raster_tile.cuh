@@ -74,9 +74,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a) {
 // the face is kept, and the pointer it used moves on (ps up, pm down; byte addresses in the shared window).  Spelled in PTX
 // so that every face costs three predicate tests, one select, one store and two pointer bumps -- the compiler's own
 // lowering of the equivalent C++ rebuilds the addresses for every face.
-template <int NF, int J>
+template <int NFACES, int J>
 __device__ __forceinline__ void emit_faces(unsigned kmask, unsigned smask, unsigned mmask, uint32_t& ps, uint32_t& pm, unsigned idt) {
-  if constexpr (J < NF) {
+  if constexpr (J < NFACES) {
     asm volatile(
         "{\n\t.reg .pred k, s, m;\n\t.reg .b32 t, a;\n\t.reg .b16 v;\n\t"
         "and.b32 t, %2, %5;\n\tsetp.ne.b32 k, t, 0;\n\t"
@@ -90,7 +90,7 @@ __device__ __forceinline__ void emit_faces(unsigned kmask, unsigned smask, unsig
         : "+r"(ps), "+r"(pm)
         : "r"(kmask), "r"(smask), "r"(mmask), "n"(1u << J), "r"(idt), "n"(J)
         : "memory");
-    emit_faces<NF, J + 1>(kmask, smask, mmask, ps, pm, idt);
+    emit_faces<NFACES, J + 1>(kmask, smask, mmask, ps, pm, idt);
   }
 }
 
@@ -122,25 +122,29 @@ __device__ __forceinline__ bool draw_fast(const TileSmem<NF>& s, uint32_t a_rec,
   const int xb = (int)(lo & 0xFFFFu), yb = (int)(lo >> 16);       // biased by +1
   // pixel (x, y) of face f: keys0[f * npix + y * width + x], a 32-bit offset (the API bounds batch * npix)
   const unsigned face_off = (entry & (unsigned)(NF - 1)) * (unsigned)npix - (unsigned)(width + 1);
-  FrTriFast ff;
   if (kSingle) {
+    FrTriFast ff;
     fr_fast_setup(r1.x, r1.y, r2.x, r2.y, r3.x, r3.y, fr_fast_tol(1), &ff);
     const int in = fr_fast_classify(&ff, xb - 1, yb - 1);
     if (in > 0) red_max_key(keys0, face_off + (unsigned)(yb * width + xb), key);
     return in >= 0;
   } else {
-    const int xe = (int)(hi & 0xFFFFu), ye = (int)(hi >> 16);
-    fr_fast_setup(r1.x, r1.y, r2.x, r2.y, r3.x, r3.y, fr_fast_tol(max(xe - xb, ye - yb) + 1), &ff);
+    // larger box: the three numerators as plane equations around the box origin, two fused multiply-adds each per pixel
+    const int w = (int)(hi & 0xFFFFu) - xb, h = (int)(hi >> 16) - yb;   // width - 1, height - 1
+    FrTriPlanes pl;
+    fr_planes_setup(r1.x, r1.y, r2.x, r2.y, r3.x, r3.y, xb - 1, yb - 1, fr_fast_tol(max(w, h) + 1), &pl);
     bool certified = true;
-    int x = xb, y = yb;
-    while (y <= ye) {                                             // flat walk over the box
-      const int in = fr_fast_classify(&ff, x - 1, y - 1);
-      if (in > 0) red_max_key(keys0, face_off + (unsigned)(y * width + x), key);
+    unsigned off = face_off + (unsigned)(yb * width + xb);
+    const float fw = (float)w;
+    float dx = 0.0f, dy = 0.0f;
+    for (int left = (w + 1) * (h + 1); left > 0; --left) {        // flat walk over the box
+      const int in = fr_planes_classify(&pl, dx, dy);
+      if (in > 0) red_max_key(keys0, off, key);
       certified = certified && in >= 0;
-      if (++x > xe) {
-        x = xb;
-        ++y;
-      }
+      const bool wrap = dx >= fw;
+      off += wrap ? (unsigned)(width - w) : 1u;
+      dy += wrap ? 1.0f : 0.0f;
+      dx = wrap ? 0.0f : dx + 1.0f;
     }
     return certified;
   }
@@ -170,6 +174,93 @@ __device__ __forceinline__ void draw_literal(const TileSmem<NF>& s, unsigned ent
       if (fr_point_in_tri(&e, x, y)) red_max_key(keys0, face_off + (unsigned)(y * width + x), key);
 }
 
+// ---- building blocks shared by the stand-alone kernel below and the fused reconstruction epilogue (recon_f16.cuh) --------
+// The cluster's triangle list -> s.tri, by `nthreads` threads.  Returns the number of triangles (0: loose vertices only).
+template <int NF>
+__device__ __forceinline__ int load_tris(TileSmem<NF>& s, const TableView& tv, int cluster, int tid, int nthreads) {
+  const int tb = __ldg(tv.tri_begin + cluster);
+  const int ntri_c = __ldg(tv.tri_begin + cluster + 1) - tb;
+  for (int i = tid; i < ntri_c; i += nthreads) {
+    const uint2 e = __ldg(tv.tri_entry + tb + i);
+    // byte offsets of the three vertex slots within a face's records (and within a code4 row); fr_pack_key's low word
+    // without the zero-sign bit
+    s.tri[i] = make_uint4((e.x & 0xFFu) << 4, ((e.x >> 8) & 0xFFu) << 4, ((e.x >> 16) & 0xFFu) << 4, (0x7FFFFFFFu - e.y) << 1);
+  }
+  return ntri_c;
+}
+
+// Cull of one triangle per lane (whole warp, converged) over the NQ face quads starting at quad q0; `live` = the faces of
+// those quads that exist (bit j = face 4 q0 + j) -- 0 for a lane without a triangle.  Survivors go to the block-wide list.
+template <int NF, int NQ>
+__device__ __forceinline__ void cull_triangle(TileSmem<NF>& s, int t, int q0, unsigned live, int lane) {
+  constexpr int kFaceBits = NF == 16 ? 4 : 3;
+  constexpr int kCap = kClusterTris * NF;
+  const uint4 te = s.tri[live != 0u ? t : 0];
+  const unsigned char* cbase = reinterpret_cast<const unsigned char*>(&s.code4[0][0]) + q0 * (kClusterVerts * 16);
+  unsigned kmask = 0u, smask = 0u;                                // kept / kept with a one-pixel box
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const uint4 a = *reinterpret_cast<const uint4*>(cbase + q * (kClusterVerts * 16) + te.x);
+    const uint4 b = *reinterpret_cast<const uint4*>(cbase + q * (kClusterVerts * 16) + te.y);
+    const uint4 c = *reinterpret_cast<const uint4*>(cbase + q * (kClusterVerts * 16) + te.z);
+    const uint32_t e1[4] = {a.x, a.y, a.z, a.w}, e2[4] = {b.x, b.y, b.z, b.w}, e3[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t mn = __vimin3_u16x2(e1[j], e2[j], e3[j]), mx = __vimax3_u16x2(e1[j], e2[j], e3[j]);
+      if (fr_code_nonempty(mn, mx)) kmask |= 1u << (4 * q + j);
+      if (fr_code_single(mn, mx)) smask |= 1u << (4 * q + j);
+    }
+  }
+  kmask &= live;
+  smask &= kmask;
+  const unsigned mine = (unsigned)__popc(smask) | ((unsigned)__popc(kmask ^ smask) << 16);
+  unsigned incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  const unsigned total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  if (total != 0u) {                                              // warp-uniform
+    unsigned base = 0u;
+    if (lane == 31) base = atomicAdd(&s.count, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31) + (incl - mine);
+    // one-pixel survivors fill the list from the front, the others from the back: byte addresses, one predicated store
+    // and one predicated pointer bump per kept face
+    const uint32_t a_q = shared_addr(s.queue);
+    uint32_t ps = a_q + 2u * (base & 0xFFFFu), pm = a_q + 2u * ((unsigned)kCap - 1u - (base >> 16));
+    emit_faces<4 * NQ, 0>(kmask, smask, kmask ^ smask, ps, pm, ((unsigned)t << kFaceBits) | (unsigned)(4 * q0));
+  }
+}
+
+// Drains the block-wide survivor list with `nthreads` threads (one-pixel survivors first), one survivor per thread and
+// trip; keys = visibility keys of the tile's face 0.
+template <int NF>
+__device__ __forceinline__ void draw_list(const TileSmem<NF>& s, int tid, int nthreads, unsigned long long* __restrict__ keys, int npix,
+                                          int width, int height) {
+  constexpr int kCap = kClusterTris * NF;
+  const unsigned cnt = s.count;
+  const int n_single = (int)(cnt & 0xFFFFu), n_total = n_single + (int)(cnt >> 16);
+  const uint32_t limit = (uint32_t)width | ((uint32_t)height << 16);
+  const uint32_t a_rec = shared_addr(&s.rec[0][0]);
+  const unsigned long long keys0 = (unsigned long long)__cvta_generic_to_global(keys);
+  unsigned redo = 0u;                                             // trips whose survivor needs the literal inside test
+  int trip = 0;
+  for (int i = tid; i < n_total; i += nthreads, ++trip) {
+    bool certified;
+    if (i < n_single) certified = draw_fast<NF, true>(s, a_rec, s.queue[i], keys0, npix, width, limit);
+    else certified = draw_fast<NF, false>(s, a_rec, s.queue[kCap - 1 - (i - n_single)], keys0, npix, width, limit);
+    if (!certified) redo |= 1u << trip;
+  }
+  while (redo != 0u) {                                            // rare (pixel centres on an edge, slivers, degenerate triangles)
+    const int k = __ffs((int)redo) - 1;
+    redo &= redo - 1u;
+    const int i = tid + k * nthreads;
+    draw_literal<NF>(s, s.queue[i < n_single ? i : kCap - 1 - (i - n_single)], keys0, npix, width, limit);
+  }
+}
+
+// ---- stand-alone visibility pass -----------------------------------------------------------------------------------------
 // grid = (clusters, ceil(batch / NF)); rec = vertex records by rank [batch][nver]; keys cleared by a predecessor.
 #ifndef FR_TILE_MINB16
 #define FR_TILE_MINB16 4
@@ -183,21 +274,12 @@ raster_tile_keys_kernel(const float4* __restrict__ rec, const unsigned char* __r
                         int batch, int nver, int height, int width) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<NF>& s = *reinterpret_cast<TileSmem<NF>*>(smem_raw);
-  constexpr int kFaceBits = NF == 16 ? 4 : 3;
-  constexpr int kCap = kClusterTris * NF;
   const int tid = threadIdx.x, lane = tid & 31;
   const int cluster = blockIdx.x, b0 = blockIdx.y * NF;
   const TableView tv = table_view(table);
   pdl_trigger();   // the resolve pass may become resident once every block of this grid has started
-  const int tb = __ldg(tv.tri_begin + cluster);
-  const int ntri_c = __ldg(tv.tri_begin + cluster + 1) - tb;
+  const int ntri_c = load_tris(s, tv, cluster, tid, kTileThreads);   // static data: no need to wait
   if (ntri_c == 0) return;                                        // a cluster of loose vertices only
-  if (tid < ntri_c) {                                             // triangle list (static data: no need to wait)
-    const uint2 e = __ldg(tv.tri_entry + tb + tid);
-    // byte offsets of the three vertex slots within a face's records (and within a code4 row); fr_pack_key's low word
-    // without the zero-sign bit
-    s.tri[tid] = make_uint4((e.x & 0xFFu) << 4, ((e.x >> 8) & 0xFFu) << 4, ((e.x >> 16) & 0xFFu) << 4, (0x7FFFFFFFu - e.y) << 1);
-  }
   if (tid == 0) s.count = 0u;
   pdl_wait();      // records and cleared keys of the producing kernels are complete
 
@@ -223,73 +305,15 @@ raster_tile_keys_kernel(const float4* __restrict__ rec, const unsigned char* __r
   }
   __syncthreads();
 
-  // ---- cull: thread = triangle (warps entirely beyond the cluster's list skip to the barrier)
+  // ---- cull: thread = triangle, all NF faces (warps entirely beyond the cluster's list skip to the barrier)
   if ((tid & ~31) < ntri_c) {
-    const bool valid = tid < ntri_c;
-    const uint4 te = s.tri[valid ? tid : 0];
-    const unsigned char* cbase = reinterpret_cast<const unsigned char*>(&s.code4[0][0]);
-    unsigned kmask = 0u, smask = 0u;                              // kept / kept with a one-pixel box
-#pragma unroll
-    for (int q = 0; q < NF / 4; ++q) {
-      const uint4 a = *reinterpret_cast<const uint4*>(cbase + q * (kClusterVerts * 16) + te.x);
-      const uint4 b = *reinterpret_cast<const uint4*>(cbase + q * (kClusterVerts * 16) + te.y);
-      const uint4 c = *reinterpret_cast<const uint4*>(cbase + q * (kClusterVerts * 16) + te.z);
-      const uint32_t e1[4] = {a.x, a.y, a.z, a.w}, e2[4] = {b.x, b.y, b.z, b.w}, e3[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t mn = __vimin3_u16x2(e1[j], e2[j], e3[j]), mx = __vimax3_u16x2(e1[j], e2[j], e3[j]);
-        if (fr_code_nonempty(mn, mx)) kmask |= 1u << (4 * q + j);
-        if (fr_code_single(mn, mx)) smask |= 1u << (4 * q + j);
-      }
-    }
-    const int nlive = min(NF, batch - b0);                        // faces beyond the batch / threads beyond the list
-    kmask &= valid ? ((1u << nlive) - 1u) : 0u;
-    smask &= kmask;
-    const unsigned mine = (unsigned)__popc(smask) | ((unsigned)__popc(kmask ^ smask) << 16);
-    unsigned incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-      if (lane >= d) incl += up;
-    }
-    const unsigned total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (total != 0u) {                                            // warp-uniform
-      unsigned base = 0u;
-      if (lane == 31) base = atomicAdd(&s.count, total);
-      base = __shfl_sync(0xFFFFFFFFu, base, 31) + (incl - mine);
-      // one-pixel survivors fill the list from the front, the others from the back: byte addresses, one predicated store
-      // and one predicated pointer bump per kept face
-      const uint32_t a_q = shared_addr(s.queue);
-      uint32_t ps = a_q + 2u * (base & 0xFFFFu), pm = a_q + 2u * ((unsigned)kCap - 1u - (base >> 16));
-      const unsigned idt = (unsigned)tid << kFaceBits;
-      emit_faces<NF, 0>(kmask, smask, kmask ^ smask, ps, pm, idt);
-    }
+    const int nlive = min(NF, batch - b0);                        // faces beyond the batch / lanes beyond the list: not live
+    cull_triangle<NF, NF / 4>(s, tid, 0, tid < ntri_c ? ((1u << nlive) - 1u) : 0u, lane);
   }
   __syncthreads();
 
-  // ---- draw: one work list (one-pixel survivors first), one survivor per thread and trip
-  {
-    const unsigned cnt = s.count;
-    const int n_single = (int)(cnt & 0xFFFFu), n_total = n_single + (int)(cnt >> 16);
-    const uint32_t limit = (uint32_t)width | ((uint32_t)height << 16);
-    const int npix = height * width;
-    const uint32_t a_rec = shared_addr(&s.rec[0][0]);
-    const unsigned long long keys0 = (unsigned long long)__cvta_generic_to_global(keys + (size_t)b0 * (size_t)npix);
-    unsigned redo = 0u;                                           // trips whose survivor needs the literal inside test
-    int trip = 0;
-    for (int i = tid; i < n_total; i += kTileThreads, ++trip) {
-      bool certified;
-      if (i < n_single) certified = draw_fast<NF, true>(s, a_rec, s.queue[i], keys0, npix, width, limit);
-      else certified = draw_fast<NF, false>(s, a_rec, s.queue[kCap - 1 - (i - n_single)], keys0, npix, width, limit);
-      if (!certified) redo |= 1u << trip;
-    }
-    while (redo != 0u) {                                          // rare (pixel centres on an edge, slivers, degenerate triangles)
-      const int k = __ffs((int)redo) - 1;
-      redo &= redo - 1u;
-      const int i = tid + k * kTileThreads;
-      draw_literal<NF>(s, s.queue[i < n_single ? i : kCap - 1 - (i - n_single)], keys0, npix, width, limit);
-    }
-  }
+  // ---- draw
+  draw_list(s, tid, kTileThreads, keys + (size_t)b0 * (size_t)(height * width), height * width, width, height);
 }
 
 }  // namespace rt

@@ -16,10 +16,12 @@
 //   epilogue    8 / 16 warps: tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices),
 //                        (2^-t f.R).v + t, y flip; double-buffered against the next tile's MMAs.  Two flavours:
 //       planar  (8 warps)   coalesced stores of vertex_proj [B,3,N]                  (fr_recon_project_forward)
-//       raster  (16 warps)  the row tile is a CLUSTER of the mesh table (mesh_table.h): the projected vertices go
-//                           to a shared-memory stage and the same warps rasterize the cluster's triangles from there
-//                           (raster_cluster.cuh) while the tensor pipe works on the next cluster -- the vertices of the
-//                           fused params -> depth-map call never touch global memory   (fr_recon_render_forward)
+//       raster  (28 warps)  the row tile is a CLUSTER of the mesh table (mesh_table.h): the projected vertices go, 16 faces
+//                           at a time, to the shared-memory tile of the tile rasterizer (raster_tile.cuh) and the same
+//                           warps cull and draw the cluster's triangles from there while the tensor pipe works on the
+//                           next cluster -- the vertices of the fused params -> depth-map call never touch global
+//                           memory, and the rasterizer's instruction stream fills the issue slots the HBM-bound basis
+//                           stream leaves idle   (fr_recon_render_forward with FR_CLUSTER_TILES)
 // Measured on B200 (tools/mma_bench3.cu): an SS-form M128 N64 MMA takes 48 cycles (operand reads at 128 B/clk), K8 tf32
 // and K16 f16 alike, so a 16-k chunk costs 144 tensor cycles here against 192 for the 3xTF32 TS-form kernel
 // (tools/experiments/recon_tc_3xtf32.cuh) -- and that kernel also needs 8 converter warps and a TMEM operand ring only 4 chunks deep.
@@ -28,13 +30,10 @@
 
 #include <cuda_fp16.h>
 
-#include "raster_cluster.cuh"
+#include "raster_tile.cuh"
 #include "recon.cuh"
 #include "tcgen05_common.cuh"
 
-#ifndef FR_FUSED_EPI_WARPS
-#define FR_FUSED_EPI_WARPS 28    // epilogue warps of the raster flavour (16 of them read the accumulators); + producer + MMA issuer = 960 threads
-#endif
 #ifndef FR_BASIS_EVICT_FIRST
 #define FR_BASIS_EVICT_FIRST 1   // A/B on B200: 102.8 -> 101.6 us per step (the records / keys stay in L2 for the rasterizer)
 #endif
@@ -69,17 +68,20 @@ constexpr int kPose16Stride = 16;      // floats per face: 2^-t f.R [9] | t [3] 
 // Flavour of the forward kernel (see the header comment).
 template <bool kRaster>
 struct Cfg {
-  // Epilogue warps; every one of them reads accumulators (its TMEM lane quarter = warp % 4) and, in the raster flavour,
-  // rasterizes.  Planar: 8 warps, 16 consecutive faces per warp and step.  Raster: 28 warps (7 per lane quarter), a
-  // warp reads the faces wq, wq + 7, ... of the 32-face stage one column at a time.
-  static constexpr int kEpiWarps = kRaster ? FR_FUSED_EPI_WARPS : 8;
+  // Epilogue warps; every one of them reads accumulators (its TMEM lane quarter = warp % 4).
+  //   planar: 8 warps, 16 consecutive faces per warp and 32-face step.
+  //   raster: 24 warps in kGroups = 3 independent GROUPS of 8 (two warps per lane quarter).  A group stages 8 faces
+  //           (an "octet") of the cluster in its own shared-memory tile, culls (thread = triangle) and draws them, and
+  //           moves on to its next octet; the groups only meet at the accumulator hand-over, so while one group waits
+  //           at its own barrier or runs its short cull phase the others keep the issue slots busy.
+  static constexpr int kGroups = kRaster ? 3 : 1;
+  static constexpr int kGroupWarps = 8;
+  static constexpr int kEpiWarps = kGroups * kGroupWarps;
   static constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   static constexpr int kThreads = (kEpiWarps + 2) * 32;
-  static constexpr int kStages = kRaster ? 3 : kMaxStages;     // the raster flavour needs 82 KB for its stage and survivor list
-  static constexpr int kStepFaces = 32;                          // faces per epilogue step (raster: one stage)
-  static constexpr int kWarpsPerQuarter = kEpiWarps / 4;
-  static constexpr int kFacesPerWarp = (kStepFaces + kWarpsPerQuarter - 1) / kWarpsPerQuarter;   // planar: 16; raster: up to 5
-  static_assert(kEpiWarps % 4 == 0, "whole lane quarters");
+  static constexpr int kStages = kRaster ? 3 : kMaxStages;       // the raster flavour's three tiles need 86 KB: 224 KB in all
+  static constexpr int kStepFaces = kRaster ? 8 : 32;            // faces per epilogue step (raster: one staged octet)
+  static constexpr int kFacesPerWarp = kRaster ? 4 : 16;         // consecutive faces a warp reads per step
 };
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 at [4,6), a = b = F16 (0) at [7,10) / [10,13), K-major
@@ -96,11 +98,7 @@ struct Barriers {
   uint32_t pad;
 };
 
-struct RasterSmem {                    // raster flavour only
-  rc::Stage<Cfg<true>::kStepFaces> stage;
-  rc::TriList tris;
-  rc::StageQueue queue;
-};
+using RasterSmem = rt::TileSmem<Cfg<true>::kStepFaces>;   // raster flavour only
 
 struct SmemLayout {
   uint32_t b0, b1, raw, pose, bars, raster, total;
@@ -117,7 +115,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nch16) {
   L.pose = L.raw + Cfg<kRaster>::kStages * kStageBytes;
   L.bars = L.pose + kN * kPose16Stride * 4;
   L.raster = (L.bars + (uint32_t)sizeof(Barriers) + 15u) / 16u * 16u;
-  L.total = L.raster + (kRaster ? (uint32_t)sizeof(RasterSmem) : 0u);
+  L.total = L.raster + (kRaster ? (uint32_t)(Cfg<true>::kGroups * sizeof(RasterSmem)) : 0u);
   return L;
 }
 
@@ -492,96 +490,139 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     }
   } else {
     // ================================================================== epilogue (warps 0 .. kEpiWarps-1)
-    constexpr int kFPW = C::kFacesPerWarp, kWPQ = C::kWarpsPerQuarter;
-    const int qd = warp & 3, wq = warp >> 2;                      // TMEM lane quarter == warp % 4; position within the quarter
+    constexpr int kFPW = C::kFacesPerWarp;
+    const int qd = warp & 3;                                      // TMEM lane quarter == warp % 4
     const int v = qd * 32 + lane;                                 // row of the tile == vertex slot of the cluster
     const uint32_t lane_field = (uint32_t)(qd * 32) << 16;
-    RasterSmem* rs = reinterpret_cast<RasterSmem*>(smem + L.raster);
-    rc::TableView tv = {nullptr, nullptr, nullptr, 0};
-    if (kRaster) {
-      tv = rc::table_view(target.table);
-      if (threadIdx.x == 0) {
-        rs->queue.count = 0u;
-        rs->queue.next = 0u;
-      }
-    }
-    const int npix = target.width * target.height;
     pdl_wait();                                                   // the prep kernel's poses (and the cleared keys)
     for (int i = threadIdx.x; i < kN * kPose16Stride; i += kEpiWarps * 32) s_pose[i] = pose16[(size_t)b0 * kPose16Stride + i];
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // the epilogue warps only
-    uint32_t tcount = 0;
-    for (TileWalk tw(nclusters, nsteps); tw.next(); ++tcount) {
-      const int tile = tw.tile;
-      const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
-      // vertex of this row, and whether this cluster is the one that writes it to the planar tensor
-      int n = tile * kTileVerts + v;
-      bool owner = n < nver;
-      if (cluster_vert != nullptr && (out.planar != nullptr || out.rec != nullptr)) {
-        const int32_t raw = __ldg(cluster_vert + (size_t)tile * kTileVerts + v);
-        n = (int)((uint32_t)raw & kVertIdMask);
-        owner = raw >= 0 && ((uint32_t)raw & kVertOwner) != 0u;
-      }
-      const bool store = (out.planar != nullptr || out.rec != nullptr) && owner;
-      int ntri_c = 0;
-      if (kRaster) {                                              // the cluster's triangle list (the previous tile's last
-        const int tb = __ldg(tv.tri_begin + tile);                // barrier has released tris and stage)
-        ntri_c = __ldg(tv.tri_begin + tile + 1) - tb;
-        rc::load_tri_list(rs->tris, tv.tri_entry + tb, ntri_c, threadIdx.x, kEpiWarps * 32);
-      }
-      mbar_wait(&bars->d_full[dbuf], dph);
-      tc_fence_after();
-      const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
+    if constexpr (!kRaster) {
+      const int wq = warp >> 2;                                   // position within the quarter: faces wq * 16 ... of a step
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // the epilogue warps only
+      uint32_t tcount = 0;
+      for (TileWalk tw(nclusters, nsteps); tw.next(); ++tcount) {
+        const int tile = tw.tile;
+        const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
+        // vertex of this row, and whether this tile is the one that writes it
+        int n = tile * kTileVerts + v;
+        bool owner = n < nver;
+        if (cluster_vert != nullptr) {
+          const int32_t raw = __ldg(cluster_vert + (size_t)tile * kTileVerts + v);
+          n = (int)((uint32_t)raw & kVertIdMask);
+          owner = raw >= 0 && ((uint32_t)raw & kVertOwner) != 0u;
+        }
+        mbar_wait(&bars->d_full[dbuf], dph);
+        tc_fence_after();
+        const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
 #pragma unroll 1
-      for (int step = tw.step0; step < tw.step1; ++step) {
-        // faces of this warp within the step: planar -- kFPW consecutive ones; raster -- wq, wq + kWPQ, ...
-        float x[kFPW], y[kFPW], z[kFPW];
-        if constexpr (kRaster) {
-#pragma unroll
-          for (int j = 0; j < kFPW; ++j) {
-            const int fl = min(wq + j * kWPQ, kStepFaces - 1);    // (clamped: the last round is short for some warps)
-            tmem_ld1(d_addr + 0 * kN + step * kStepFaces + fl, &x[j]);
-            tmem_ld1(d_addr + 1 * kN + step * kStepFaces + fl, &y[j]);
-            tmem_ld1(d_addr + 2 * kN + step * kStepFaces + fl, &z[j]);
-          }
-        } else {
+        for (int step = tw.step0; step < tw.step1; ++step) {
+          float x[kFPW], y[kFPW], z[kFPW];                        // kFPW consecutive faces of the step per warp
           const int jb = step * kStepFaces + wq * kFPW;
           tmem_ld<kFPW>(d_addr + 0 * kN + jb, x);
           tmem_ld<kFPW>(d_addr + 1 * kN + jb, y);
           tmem_ld<kFPW>(d_addr + 2 * kN + jb, z);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (step == tw.step1 - 1) {                             // accumulators drained: the tensor pipe may reuse them
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+          }
+#pragma unroll
+          for (int j = 0; j < kFPW; ++j) {
+            const int jf = jb + j;                                // face of the batch tile
+            const float4* pp = reinterpret_cast<const float4*>(s_pose + jf * kPose16Stride);
+            const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+            const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+            float X, Y, Z;
+            project_vertex(P, x[j], y[j], z[j], im_size, flags, &X, &Y, &Z);
+            if (owner && b0 + jf < batch) {
+              if (out.planar != nullptr) store_planar(out.planar, b0 + jf, nver, n, X, Y, Z);
+              // records go by rank: with a row map in rank order that is the row itself
+              if (out.rec != nullptr) store_record(out, b0 + jf, nver, cluster_vert != nullptr ? tile * kTileVerts + v : n, X, Y, Z);
+            }
+          }
         }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (step == tw.step1 - 1) {                               // accumulators drained: the tensor pipe may reuse them
-          tc_fence_before();
+      }
+    } else {
+      // ---- raster flavour: three groups of 8 warps, each with its own shared-memory tile (raster_tile.cuh)
+      constexpr int kGW = C::kGroupWarps, kGT = kGW * 32;
+      const int grp = warp / kGW, gw = warp % kGW;                // group; warp within the group
+      const int fh = gw >> 2;                                     // which 4 faces of an octet this warp stages
+      const int gtid = gw * 32 + lane;                            // thread within the group == triangle slot in the cull
+      const int gbar = 1 + grp;                                   // the group's hardware barrier
+      RasterSmem& ts = reinterpret_cast<RasterSmem*>(smem + L.raster)[grp];
+      const rt::TableView tv = rt::table_view(target.table);
+      const int npix = target.width * target.height;
+      asm volatile("bar.sync 4, %0;" ::"n"(kEpiWarps * 32) : "memory");   // poses in place (all epilogue warps)
+      uint32_t tcount = 0;
+      for (TileWalk tw(nclusters, nsteps); tw.next(); ++tcount) {
+        const int tile = tw.tile;
+        const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
+        // octets of this tile that belong to the group: o = first, first + 3, ... (rotated from tile to tile)
+        const int first = tw.step0 + ((grp + 3 * 128 - (int)(tcount % 3u) - tw.step0 % 3) % 3);
+        // the accumulators are only handed back by warps that have seen them complete: a warp without work in this tile
+        // must not run ahead and arrive for a later tile in this one's phase
+        mbar_wait(&bars->d_full[dbuf], dph);
+        if (first >= tw.step1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+          continue;
         }
+        tc_fence_after();
+        // vertex of this row and whether this cluster owns it (optional vertex_proj output only)
+        int n = 0;
+        bool owner = false;
+        if (out.planar != nullptr) {
+          const int32_t raw = __ldg(cluster_vert + (size_t)tile * kTileVerts + v);
+          n = (int)((uint32_t)raw & kVertIdMask);
+          owner = raw >= 0 && ((uint32_t)raw & kVertOwner) != 0u;
+        }
+        // the cluster's triangle list: this thread's entry travels in registers until the group's tile is free
+        const int tb = __ldg(tv.tri_begin + tile);
+        const int ntri_c = __ldg(tv.tri_begin + tile + 1) - tb;
+        uint2 te = make_uint2(0u, 0u);
+        if (gtid < ntri_c) te = __ldg(tv.tri_entry + tb + gtid);
+        const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
+#pragma unroll 1
+        for (int o = first; o < tw.step1; o += 3) {
+          // ---- this warp's share of the octet (faces fh * 4 ...) from the accumulators, projected, in registers: overlaps
+          // the tail of the group's previous draw phase
+          float x[kFPW], y[kFPW], z[kFPW];
+          const int jb = o * kStepFaces + fh * kFPW;              // first of the four faces within the batch tile
+          tmem_ld<kFPW>(d_addr + 0 * kN + jb, x);
+          tmem_ld<kFPW>(d_addr + 1 * kN + jb, y);
+          tmem_ld<kFPW>(d_addr + 2 * kN + jb, z);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (o + 3 >= tw.step1) {                                // the group's last octet: accumulators drained
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+          }
+          const int fb = b0 + o * kStepFaces;                     // first face of the octet
+          const int nlive = min(kStepFaces, batch - fb);
+          float4 r[kFPW];
 #pragma unroll
-        for (int j = 0; j < kFPW; ++j) {
-          const int fl = kRaster ? wq + j * kWPQ : wq * kFPW + j;                       // face of the step
-          if (kRaster && fl >= kStepFaces) continue;                                    // (warp-uniform: the last round is short)
-          const int jf = step * kStepFaces + fl;                                        // face of the batch tile
-          const float4* pp = reinterpret_cast<const float4*>(s_pose + jf * kPose16Stride);
-          const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
-          const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
-          float X, Y, Z;
-          project_vertex(P, x[j], y[j], z[j], im_size, flags, &X, &Y, &Z);
-          if (store && b0 + jf < batch) {
-            if (out.planar != nullptr) store_planar(out.planar, b0 + jf, nver, n, X, Y, Z);
-            // records go by rank: with a row map in rank order that is the row itself (cluster tiles never write records)
-            if (out.rec != nullptr) store_record(out, b0 + jf, nver, cluster_vert != nullptr ? tile * kTileVerts + v : n, X, Y, Z);
+          for (int j = 0; j < kFPW; ++j) {
+            const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPose16Stride);
+            const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+            const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+            project_vertex(P, x[j], y[j], z[j], im_size, flags, &r[j].x, &r[j].y, &r[j].z);
+            r[j].w = __uint_as_float(fr_snap_code(r[j].x, r[j].y, target.width, target.height));
+            if (owner && fh * kFPW + j < nlive) store_planar(out.planar, fb + fh * kFPW + j, nver, n, r[j].x, r[j].y, r[j].z);
           }
-          if (kRaster) {
-            rs->stage.x[fl][v] = X;
-            rs->stage.y[fl][v] = Y;
-            rs->stage.z[fl][v] = Z;
-            rs->stage.code[fl][v] = fr_snap_code(X, Y, target.width, target.height);
-          }
-        }
-        if (kRaster) {
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");     // stage (and triangle list) complete
-          const int fb = b0 + step * kStepFaces;                                // first face of the stage
-          rc::raster_stage(rs->stage, rs->tris, rs->queue, ntri_c, min(kStepFaces, batch - fb), warp, kEpiWarps, lane, 1,
-                           target.keys + (size_t)fb * npix, npix, target.width, target.height);
+          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // the group's previous draw is complete
+          if (o == first && gtid < ntri_c)                        // (same packing as rt::load_tris)
+            ts.tri[gtid] = make_uint4((te.x & 0xFFu) << 4, ((te.x >> 8) & 0xFFu) << 4, ((te.x >> 16) & 0xFFu) << 4, (0x7FFFFFFFu - te.y) << 1);
+          if (gtid == 0) ts.count = 0u;
+#pragma unroll
+          for (int j = 0; j < kFPW; ++j) ts.rec[fh * kFPW + j][v] = r[j];                // the staged records ...
+          ts.code4[fh][v] = make_uint4(__float_as_uint(r[0].w), __float_as_uint(r[1].w), __float_as_uint(r[2].w),
+                                       __float_as_uint(r[3].w));                         // ... and their code words again
+          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // staged octet (and triangle list) complete
+          if ((gw << 5) < ntri_c)                                 // cull: thread = triangle, the octet's 8 faces
+            rt::cull_triangle<kStepFaces, kStepFaces / 4>(ts, gtid, 0, (gtid < ntri_c) ? ((1u << nlive) - 1u) : 0u, lane);
+          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // survivor list complete
+          rt::draw_list(ts, gtid, kGT, target.keys + (size_t)fb * npix, npix, target.width, target.height);
         }
       }
     }
@@ -629,20 +670,21 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
   const int nbt = ceil_div(batch, f16::kN);
   int ctas = nsm / nbt;
   if (ctas < 1) ctas = 1;
-  if (ctas > g.nclusters) ctas = g.nclusters;
+  const int ntiles_f = target != nullptr ? g.nclusters : g.ntiles;             // row tiles of the section this flavour streams
+  if (ctas > ntiles_f) ctas = ntiles_f;
   const f16::RasterTarget none = {nullptr, nullptr, 0, 0};
   if (target != nullptr) {
     const f16::SmemLayout L = f16::smem_layout<true>(g.nch16);
     FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<true>, dim3(ctas, nbt), dim3(f16::Cfg<true>::kThreads), L.total, st, pdl_enabled(),
-                       base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
+                       base + g.f16c_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
                        out, *target, batch, nver, g.nch16, g.nclusters, im_size, flags));
   } else {
     const f16::SmemLayout L = f16::smem_layout<false>(g.nch16);
     FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<false>, dim3(ctas, nbt), dim3(f16::Cfg<false>::kThreads), L.total, st, pdl_enabled(),
                        base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
-                       out, none, batch, nver, g.nch16, g.nclusters, im_size, flags));
+                       out, none, batch, nver, g.nch16, g.ntiles, im_size, flags));
   }
   FR_LAUNCHED("recon_fwd_f16_kernel");
   return FR_OK;

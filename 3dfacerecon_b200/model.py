@@ -34,7 +34,7 @@ class DeviceModel:
     """Packed basis + triangles + textures of one 3DMM on one GPU."""
 
     def __init__(self, model: dict, device="cuda:0", convention: str = "network", validate_tri: bool = True,
-                 tri_base: int | None = None, cache_dir: str | None = None, cluster_tiles: bool = False):
+                 tri_base: int | None = None, cache_dir: str | None = None, cluster_tiles: bool = True):
         if convention not in _CONVENTIONS:
             raise ValueError("convention must be one of %s" % sorted(_CONVENTIONS))
         self.device = torch.device(device)
@@ -43,6 +43,7 @@ class DeviceModel:
         self.convention = convention
         self.pack_flags, self.run_flags = _CONVENTIONS[convention]
         if cluster_tiles:       # FR_CLUSTER_TILES (include/facerecon_b200.h): the fused call rasterizes inside the reconstruction epilogue
+                                # (default; costs a second, cluster-ordered copy of the forward operand tiles: +184 MB for BFM)
             self.pack_flags |= _lib.FR_CLUSTER_TILES
             self.run_flags |= _lib.FR_CLUSTER_TILES
         self.cluster_tiles = bool(cluster_tiles)

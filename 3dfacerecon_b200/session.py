@@ -22,7 +22,7 @@ def _fptr(a):
 
 
 class Session:
-    def __init__(self, model: dict, height=200, width=200, max_batch=64, device=0, convention="network"):
+    def __init__(self, model: dict, height=200, width=200, max_batch=64, device=0, convention="network", cluster_tiles=True):
         mu = np.ascontiguousarray(np.asarray(model["mu"], np.float32).reshape(-1))
         ps = np.ascontiguousarray(model["pc_shape"], np.float32)
         pe = np.ascontiguousarray(model["pc_exp"], np.float32)
@@ -34,7 +34,8 @@ class Session:
         self._h = ctypes.c_void_p()
         self._inflight = {}
         check(lib().fr_session_create(_fptr(mu), _fptr(ps), _fptr(pe), _fptr(tri), self.nver, self.ntri, self.ks, self.ke,
-                                      self.height, self.width, self.max_batch, _CONV[convention], int(device),
+                                      self.height, self.width, self.max_batch,
+                                      _CONV[convention] | (_lib.FR_CLUSTER_TILES if cluster_tiles else 0), int(device),
                                       ctypes.byref(self._h)))
 
     def forward(self, params, im_size=200.0, depth=None, tri_ind=None, vertex_proj=None, want_tri_ind=True):

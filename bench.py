@@ -15,13 +15,13 @@ One step = one pass of the hot path over one batch.  Prints ONE JSON line (rank 
   e2e        the same metric through the host-buffer C-ABI session: params copied in from pinned host memory and the depth
              maps copied back inside the timed region; next to it a D2H-only loop over the same pinned buffers (the host
              link's ceiling for this result size)
-  roofline   dominant kernel (the visibility pass): algorithmic bytes of its part / its device time, measured live with
-             CUDA events the library records between its kernels, vs the measured HBM copy bandwidth; the whole step under
-             three byte conventions beside it
+  roofline   dominant kernel (tensor-core reconstruction with the tile rasterizer in its epilogue): algorithmic bytes / its
+             device time, measured live with CUDA events the library records between its kernels, vs the measured HBM copy
+             bandwidth; the whole step under three byte conventions beside it
   config3    BASELINE configs[2]: 4096 faces sharded by batch over the N ranks (shard_batch), the same fused call
   cpu_baseline  one P-thread float32 GEMM for the whole batch + the reference CPU op (oracle/_ref) on P processes
   extras     (N = 1) configs[0] (batch 1, sample_test conventions, HBM GB/s), configs[3] (batch 256 forward + backward),
-             the same step on a mesh with shuffled vertex / triangle numbering, and the FR_CLUSTER_TILES flavour
+             the same step on a mesh with shuffled vertex / triangle numbering, and the records pipeline (no FR_CLUSTER_TILES)
 """
 from __future__ import annotations
 
@@ -531,17 +531,25 @@ def run_ours(args):
                                                "mesh table's rank order supplies the locality"}
         del fp, dm_p, model_p
 
-        # FR_CLUSTER_TILES flavour: cluster rasterizer inside the reconstruction epilogue
-        dm_c = pkg.DeviceModel(model, dev, cluster_tiles=True)
-        fc = Fused(dm_c, params_host)
-        ms_tiles = timed(fc, 10, 3, barrier=False)
+        # the records pipeline (a basis packed without FR_CLUSTER_TILES): reconstruction kernel writing 16-byte vertex
+        # records, stand-alone tile rasterizer reading them back from L2, resolve -- the step split by the library's events
+        dm_r = pkg.DeviceModel(model, dev, cluster_tiles=False)
+        fr_ = Fused(dm_r, params_host)
+        ms_rec_pipe = timed(fr_, 10, 3, barrier=False)
+        parts_r = timed_parts(fr_, 10, 3)
         torch.cuda.synchronize(dev)
         main()
         torch.cuda.synchronize(dev)
-        same = bool(torch.equal(fc.depth, main.depth) and torch.equal(fc.tri_ind, main.tri_ind))
-        extras["cluster_tiles_b64"] = {"ms": ms_tiles, "vs_default": ms_tiles / ms_full_max, "bit_identical_to_default": same,
-                                       "clusters": dm_c.mesh.nclusters, "vertex_slots": dm_c.mesh.vertex_slots}
-        del fc, dm_c
+        same = bool(torch.equal(fr_.depth, main.depth) and torch.equal(fr_.tri_ind, main.tri_ind))
+        rb_, nb_ = algorithmic_bytes(B, nver, ntri, K)
+        extras["records_pipeline_b64"] = {"ms": ms_rec_pipe, "vs_default": ms_rec_pipe / ms_full_max, "bit_identical_to_default": same,
+                                          "recon_kernels": roof(rb_, parts_r[0]),
+                                          "tile_keys_kernel": roof(nb_ - 8 * B * H * W, parts_r[1]),
+                                          "resolve_kernel": roof(16 * B * H * W, parts_r[2]),
+                                          "clusters": dm_r.mesh.nclusters, "vertex_slots": dm_r.mesh.vertex_slots,
+                                          "note": "kernels serialised by the events; fr::rt::raster_tile_keys_kernel<16> is the "
+                                                  "visibility pass of fr_render_depth_forward as well"}
+        del fr_, dm_r
 
     # end to end through the host-buffer C-ABI session: every step copies its params in from pinned host memory and its
     # depth maps back to pinned host memory inside the timed region.  The session's slots are used round-robin
@@ -616,12 +624,14 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "arithmetic": "f32 results; reconstruction on tcgen05 with fp16 hi/lo operand pairs (22 significant bits) and "
-                                     "fp32 accumulation, rasterizer cull in packed integers and inside tests in separately rounded f64 "
-                                     "(bit-exact with the reference)",
+                                     "fp32 accumulation; rasterizer cull in packed integers, inside tests by a certified float filter "
+                                     "that falls back to the reference's separately rounded f64 sequence whenever rounding could "
+                                     "matter (bit-exact with the reference)",
                        "batch_per_gpu": B, "nver": nver, "ntri": ntri, "ndim_shape": ks, "ndim_exp": ke, "image": [H, W],
                        "l2": "flushed before every timed step (512 MiB write, outside the events)",
-                       "call": "fr_recon_render_forward with the model's mesh table, depth + tri_ind out; the optional vertex_proj "
-                               "output is not requested in the timed loop (the parity check re-runs the call with it)",
+                       "call": "fr_recon_render_forward with the model's mesh table and FR_CLUSTER_TILES (rasterizer inside the "
+                               "reconstruction epilogue), depth + tri_ind out; the optional vertex_proj output is not requested in the "
+                               "timed loop (the parity check re-runs the call with it)",
                        "parallelism": "batch-sharded x%d, basis replicated, no collective" % world},
             "e2e": {"value": faces_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                     "h2d_bytes_per_step": int(pin_params[0].numel() * 4), "d2h_bytes_per_step": d2h_bytes,
@@ -634,15 +644,16 @@ def run_ours(args):
                             "the end-to-end step: near 1 means the host link, not the library, bounds e2e",
                     "numa": numa, "matches_device_path": e2e_ok},
             "gpu_launches": launches_total,
-            "roofline": dict(roof(nb - out_bytes, ms_keys), bound="hbm", kernel="fr::raster_keys_kernel<8, true> (visibility pass)",
-                             peak=peak, unit="GB/s", traffic=_traffic("raster_keys_kernel"), peak_source=peak_src,
-                             how="device time between the CUDA events the library records before and after this kernel inside one "
-                                 "real fused call (stage_events, kernels serialised), L2 flushed before the call; bytes = SURVEY 8(d) "
-                                 "render part minus the resolve pass's outputs (tri + vertex data read)",
-                             limiter="instruction issue, not HBM: ~34 M warp instructions for 6.8 M (triangle, face) pairs "
-                                     "(exact integer cull + separately rounded FP64 inside tests), DESIGN.md 4.2",
-                             recon_kernels=roof(rb, ms_rec), resolve_kernel=roof(2 * out_bytes, ms_res),
-                             render_part=roof(nb, ms_keys + ms_res),
+            "roofline": dict(roof(rb + nb - out_bytes, ms_rec + ms_keys), bound="hbm",
+                             kernel="fr::f16::recon_fwd_f16_kernel<true> (tcgen05 reconstruction + projection with the tile "
+                                    "rasterizer's cull / draw in its epilogue; the 4.5 us prep kernel in front of it is inside the time)",
+                             peak=peak, unit="GB/s", traffic=_traffic("recon_fwd_f16_kernel_raster"), peak_source=peak_src,
+                             how="device time between the CUDA events the library records around its kernels inside one real fused "
+                                 "call (stage_events), L2 flushed before the call; bytes = SURVEY 8(d) bytes_fwd(B) minus the resolve "
+                                 "pass's outputs (basis + mean + params + tri read, projected vertices written and read once)",
+                             limiter="instruction issue of the rasterizer half (DESIGN.md 4): ~36 M warp instructions per step, 24 "
+                                     "rasterizing warps per SM at ~55 % issue utilisation; the basis stream (200 MB) would take ~46 us",
+                             resolve_kernel=roof(2 * out_bytes, ms_res),
                              whole_step={"survey_8d_bytes": roof(rb + nb, ms_full_max),
                                          "with_vertex_proj_materialised": roof(rb + nb, ms_full_vertex_max),
                                          "fused_compulsory_bytes": roof(fused_compulsory_bytes(B, nver, ntri, K), ms_full_max)},

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FR_VERSION 200
+#define FR_VERSION 201
 
 /* status codes */
 #define FR_OK 0
@@ -52,10 +52,12 @@ extern "C" {
 #define FR_MEAN_INTERLEAVED 0x10u /* mu[3*n+c]      rendering_layer/sample_test.py:101 */
 #define FR_BASIS_PLANAR 0x0u      /* pc[c*N+n,k]    nets/network.py:154,156 (default) */
 #define FR_BASIS_INTERLEAVED 0x20u/* pc[3*n+c,k]    prepare_data/Project2D.m:8-9 */
-/* Pack-time AND run-time flag: the row tiles of the tensor-core forward operands follow the clusters of the mesh table
- * (instead of 128 consecutive vertices), and fr_recon_render_forward rasterizes each cluster inside the reconstruction
- * epilogue from shared memory.  A basis packed with this flag must always be used with it and with the same mesh table.
- * Same results either way; measured slower on B200 than the default pipeline, kept as an option. */
+/* Pack-time AND run-time flag.  At pack time: the packed basis also carries the tensor-core forward operands with one row
+ * tile per CLUSTER of the mesh table (+20 % of that section: border vertices are repeated in every member cluster).  At run
+ * time: fr_recon_render_forward streams that section and rasterizes every cluster inside the reconstruction epilogue from
+ * shared memory (raster_tile.cuh), so the projected vertices of the fused call never touch global memory and the rasterizer
+ * runs in the issue slots the HBM-bound basis stream leaves idle.  Needs a basis packed with the flag and the same mesh
+ * table; every other entry point ignores the flag.  Same results either way (bit-identical depth maps). */
 #define FR_CLUSTER_TILES 0x40u
 
 /* number of pose parameters in front of the shape/expression coefficients (utils/parser_3dmm.py:49) */

@@ -265,15 +265,20 @@ extern "C" long long fr_emul_check_tile_arith(int width, int height, int ntrials
     const int ext = (bb.x_max - bb.x_min > bb.y_max - bb.y_min ? bb.x_max - bb.x_min : bb.y_max - bb.y_min) + 1;
     FrTriFast ff;
     fr_fast_setup(x[0], y[0], x[1], y[1], x[2], y[2], fr_fast_tol(ext), &ff);
+    FrTriPlanes pl;                                     // the plane-equation form the multi-pixel path runs
+    fr_planes_setup(x[0], y[0], x[1], y[1], x[2], y[2], bb.x_min, bb.y_min, fr_fast_tol(ext), &pl);
     for (int py = bb.y_min; py <= bb.y_max; ++py)
       for (int px = bb.x_min; px <= bb.x_max; ++px) {
         const int fast = fr_fast_classify(&ff, px, py);
+        const int plane = fr_planes_classify(&pl, (float)(px - bb.x_min), (float)(py - bb.y_min));
         const bool exact = fr_point_in_tri(&e, px, py);
         ++total;
         if (fast >= 0) {
           ++decided;
           if ((fast == 1) != exact) return -10 - family;
         }
+        if (plane >= 0 && (plane == 1) != exact) return -30 - family;
+        if (family >= 7 && plane < 0 && fast >= 0 && ext <= 2) return -50;   // generic small boxes: both forms decide alike
       }
   }
   if (out) out[0] = total;
