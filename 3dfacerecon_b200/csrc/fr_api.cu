@@ -207,7 +207,7 @@ int launch_resolve(const unsigned long long* keys, const float* vertex, const fl
 // Visibility pass on 16-byte vertex records: one thread per (triangle, face group); with a mesh table the triangles come
 // from it (integer ids, cluster order), else from the reference's float index tensor.
 int launch_keys(const float4* rec, const float* tri, const fr_mesh_table* mesh, unsigned long long* keys, int batch, int nver,
-                int ntri, int height, int width, bool dependent, cudaStream_t st) {
+                int ntri, int height, int width, bool dependent, bool early_ok, cudaStream_t st) {
   const bool table = mesh != nullptr;
   const int nt = table ? mesh->hdr.ntri_slots : ntri;
   if (nt == 0) return FR_OK;
@@ -220,8 +220,11 @@ int launch_keys(const float4* rec, const float* tri, const fr_mesh_table* mesh, 
     constexpr int NF = FR_TILE_NF;
     const size_t smem = sizeof(rt::TileSmem<NF>);
     FR_CUDA(cudaFuncSetAttribute(rt::raster_tile_keys_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (dependent launch only behind the persistent reconstruction kernel: behind the pack pass its blocks, 53 KB of shared
+    // memory each, would become resident early and starve the HBM-bound pack kernel -- measured 1.35 ms vs 1.12 ms per
+    // batch-256 forward + backward)
     FR_CUDA(launch_pdl(rt::raster_tile_keys_kernel<NF>, dim3(mesh->hdr.nclusters, ceil_div(batch, NF)), dim3(rt::kTileThreads), smem, st,
-                       dependent, rec, static_cast<const unsigned char*>(mesh->dev), keys, batch, nver, height, width));
+                       dependent && early_ok, rec, static_cast<const unsigned char*>(mesh->dev), keys, batch, nver, height, width));
     FR_LAUNCHED("raster_tile_keys_kernel");
     return FR_OK;
   }
@@ -271,7 +274,7 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
           vertex, rec, keys, mesh_vert_rank(mesh), nver, npix, width, height);
       FR_LAUNCHED("raster_pack_kernel");
     }
-    if (int rc = launch_keys(rec, tri, mesh, keys, batch, nver, ntri, height, width, pdl, st)) return rc;
+    if (int rc = launch_keys(rec, tri, mesh, keys, batch, nver, ntri, height, width, pdl, records_ready, st)) return rc;
     if (after_keys != nullptr) FR_CUDA(cudaEventRecord(after_keys, st));
   } else if (!records_ready) {
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
