@@ -459,23 +459,21 @@ struct FrTriPlanes {
 };
 
 FR_HD void fr_planes_setup(float x1, float y1, float x2, float y2, float x3, float y3, int x0, int y0, int32_t tol, FrTriPlanes* p) {
-  FrTriFast f;
-  fr_fast_setup(x1, y1, x2, y2, x3, y3, tol, &f);
-  const float v2x = (float)x0 - f.ax, v2y = (float)y0 - f.ay;
-  const float cu = f.v1x * v2y - f.v1y * v2x;
-  const float cv = f.v0x * v2y - f.v0y * v2x;
-  const uint32_t su = f.sigma, sv = f.sigma ^ 0x80000000u;
-  p->u0 = fr_fxor(cu, su);                 // cu = v1x (y - ay) - v1y (x - ax):  d/dx = -v1y,  d/dy = v1x
-  p->ux = fr_fxor(f.v1y, su ^ 0x80000000u);
-  p->uy = fr_fxor(f.v1x, su);
-  p->v0 = fr_fxor(cv, sv);
-  p->vx = fr_fxor(f.v0y, sv ^ 0x80000000u);
-  p->vy = fr_fxor(f.v0x, sv);
-  p->w0 = (f.cabs - p->u0) - p->v0;
+  const float v0x = x3 - x1, v0y = y3 - y1, v1x = x2 - x1, v1y = y2 - y1;
+  const float c10 = v1x * v0y - v1y * v0x;
+  const uint32_t bits = fr_fbits(c10), su = bits & 0x80000000u, sv = su ^ 0x80000000u;
+  const float v2x = (float)x0 - x1, v2y = (float)y0 - y1;
+  p->u0 = fr_fxor(v1x * v2y - v1y * v2x, su);      // cu = v1x (y - ay) - v1y (x - ax):  d/dx = -v1y,  d/dy = v1x
+  p->ux = fr_fxor(v1y, sv);
+  p->uy = fr_fxor(v1x, su);
+  p->v0 = fr_fxor(v0x * v2y - v0y * v2x, sv);      // cv' = -s cv
+  p->vx = fr_fxor(v0y, su);
+  p->vy = fr_fxor(v0x, sv);
+  p->w0 = (fr_fxor(c10, su) - p->u0) - p->v0;
   p->wx = -(p->ux + p->vx);
   p->wy = -(p->uy + p->vy);
   p->tol = tol;
-  p->ok = f.ok;
+  p->ok = (int32_t)(bits & 0x7FFFFFFFu) > tol + (1 << 23);
 }
 
 // dx, dy: pixel offsets from the box origin as floats.  1 = inside, 0 = outside, -1 = undecided.
