@@ -190,15 +190,16 @@ int tile_keys_min_batch() {
 }
 
 // Resolve pass: keys -> depth / tri_ind (+ normals, texture, rendering-layer post-processing).
-int launch_resolve(const unsigned long long* keys, const float* vertex, const float* tri, const float* texture,
+int launch_resolve(const unsigned long long* keys, const float* vertex, const float4* rec, const int32_t* vert_rank, const float* tri,
+                   const float* texture,
                    long long texture_batch_stride, float* depth, float* texture_image, float* normal, float* tri_ind, int batch,
                    int nver, int ntri, int npix, const LayerOut& layer, bool dependent, cudaStream_t st) {
   const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
   if (texture_image != nullptr || normal != nullptr)
-    FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, tri, texture,
+    FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, rec, vert_rank, tri, texture,
                        texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
   else
-    FR_CUDA(launch_pdl(raster_resolve_kernel<false>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, tri, texture,
+    FR_CUDA(launch_pdl(raster_resolve_kernel<false>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, rec, vert_rank, tri, texture,
                        texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
   FR_LAUNCHED("raster_resolve_kernel");
   return FR_OK;
@@ -279,8 +280,9 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
   } else if (!records_ready) {
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   }
-  return launch_resolve(keys, vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver, ntri,
-                        npix, layer, pdl && draws && after_keys == nullptr, st);
+  // (the records hold this batch's vertices whenever something was drawn; normals then gather them instead of the planar tensor)
+  return launch_resolve(keys, vertex, draws ? rec : nullptr, mesh_vert_rank(mesh), tri, texture, texture_batch_stride, depth, texture_image,
+                        normal, tri_ind, batch, nver, ntri, npix, layer, pdl && draws && after_keys == nullptr, st);
 }
 
 }  // namespace
@@ -564,8 +566,10 @@ int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg
 // ------------------------------------------------------------------------------------------------ fused
 // Workspace of fr_recon_render_forward: [reconstruction | visibility keys | vertex records].
 // Does the call run with the rasterizer inside the reconstruction epilogue?  (cluster tiles, tensor-core batch size)
-static bool fused_raster(const fr_mesh_table* mesh, unsigned flags, int batch, int nver, int ndim_shape, int ndim_exp) {
+static bool fused_raster(const fr_mesh_table* mesh, unsigned flags, int batch, int nver, int ndim_shape, int ndim_exp, int height,
+                         int width) {
   if (mesh == nullptr || !(flags & FR_CLUSTER_TILES) || mesh->hdr.ntri_slots == 0) return false;
+  if (height > rt::kMaxExtent || width > rt::kMaxExtent) return false;     // the tile rasterizer's cull needs code fields < 2^15
   return use_f16_forward(basis_geom(nver, ndim_shape, ndim_exp, mesh->hdr.nclusters), batch, true);
 }
 
@@ -595,7 +599,7 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
     return (stage_events != nullptr && stage_events[i] != nullptr) ? cudaEventRecord(static_cast<cudaEvent_t>(stage_events[i]), st)
                                                                    : cudaSuccess;
   };
-  if (fused_raster(mesh, flags, batch, nver, ndim_shape, ndim_exp)) {
+  if (fused_raster(mesh, flags, batch, nver, ndim_shape, ndim_exp, height, width)) {
     // prep kernel (clears the keys) -> tensor-core reconstruction with the cluster rasterizer in its epilogue -> resolve
     const f16::RasterTarget target = {static_cast<const unsigned char*>(mesh->dev), keys, width, height};
     const ReconOut out = {vertex_proj, nullptr, 0, 0, nullptr};
@@ -605,7 +609,7 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
     FR_CUDA(record(0));
     FR_CUDA(record(1));
     const LayerOut layer = {nullptr, nullptr, nullptr, false};
-    if (int rc = launch_resolve(keys, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height * width,
+    if (int rc = launch_resolve(keys, nullptr, nullptr, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height * width,
                                 layer, pdl_enabled() && !timed, st))
       return rc;
     FR_CUDA(record(2));

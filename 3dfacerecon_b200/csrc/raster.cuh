@@ -213,8 +213,9 @@ struct LayerOut {
 
 template <bool kAttributes>
 __global__ void __launch_bounds__(kRasterThreads)
-raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ vertex,
-                      const float* __restrict__ tri, const float* __restrict__ texture, long long texture_batch_stride,
+raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ vertex, const float4* __restrict__ rec,
+                      const int32_t* __restrict__ vert_rank, const float* __restrict__ tri, const float* __restrict__ texture,
+                      long long texture_batch_stride,
                       float* __restrict__ depth, float* __restrict__ texture_image, float* __restrict__ normal,
                       float* __restrict__ tri_ind, int nver, int ntri, int npix, LayerOut layer) {
   __shared__ __align__(16) float s_attr[kAttributes ? 2 : 1][kAttributes ? 3 * kRasterThreads * kResolvePerThread : 4];
@@ -245,11 +246,19 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
       if (kAttributes) {               // the winner's vertices are only needed for normals / texture
         const int p1 = (int)__ldg(tri + t), p2 = (int)__ldg(tri + ntri + t), p3 = (int)__ldg(tri + 2 * (size_t)ntri + t);
         if (normal != nullptr) {
-          const float* vx = vertex + (size_t)b * 3 * nver;
-          const float* vy = vx + nver;
-          const float* vz = vy + nver;
-          fr_tri_normal(__ldg(vx + p1), __ldg(vy + p1), __ldg(vz + p1), __ldg(vx + p2), __ldg(vy + p2), __ldg(vz + p2),
-                        __ldg(vx + p3), __ldg(vy + p3), __ldg(vz + p3), n);
+          if (rec != nullptr) {        // the rasterizer's 16-byte records (by rank with a mesh table): three gathers, not nine
+            const float4* rb = rec + (size_t)b * nver;
+            const int q1 = vert_rank ? __ldg(vert_rank + p1) : p1, q2 = vert_rank ? __ldg(vert_rank + p2) : p2,
+                      q3 = vert_rank ? __ldg(vert_rank + p3) : p3;
+            const float4 r1 = __ldg(rb + q1), r2 = __ldg(rb + q2), r3 = __ldg(rb + q3);
+            fr_tri_normal(r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r3.x, r3.y, r3.z, n);
+          } else {
+            const float* vx = vertex + (size_t)b * 3 * nver;
+            const float* vy = vx + nver;
+            const float* vz = vy + nver;
+            fr_tri_normal(__ldg(vx + p1), __ldg(vy + p1), __ldg(vz + p1), __ldg(vx + p2), __ldg(vy + p2), __ldg(vz + p2),
+                          __ldg(vx + p3), __ldg(vy + p3), __ldg(vz + p3), n);
+          }
         }
         if (texture_image != nullptr) {
           const float* tex = texture + (size_t)b * texture_batch_stride;

@@ -72,7 +72,7 @@ int fr_version(void);
  * triangles ONCE per model (host side) into clusters of <= 128 unique vertices / <= 256 triangles with pre-validated
  * 8-bit local indices; the rasterizer then stages a cluster's vertices in shared memory once per face, and the
  * tensor-core reconstruction uses the clusters as its row tiles, so that in the fused params -> depth-map call the
- * vertices never pass through global memory (3dfacerecon_b200/csrc/mesh_table.h, raster_cluster.cuh).
+ * vertices never pass through global memory (3dfacerecon_b200/csrc/mesh_table.h, raster_tile.cuh).
  *   tri        HOST pointer, [3,ntri] float 0-based indices as rendering_layer/ops.py:78 takes them; triangles with an
  *              index outside [0,nver) are dropped (the reference reads out of bounds)
  *   positions  HOST pointer or NULL: any vertex positions that reflect the mesh's locality -- the mean shape `mu`
@@ -125,7 +125,7 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
  * Outputs: depth [batch,H,W,1], texture_image [batch,H,W,3], normal [batch,H,W,3], tri_ind [batch,H,W,1]
  * (float, -1 = background).  texture_image and normal may be NULL to skip them (texture may then be NULL).
  * Triangles whose indices fall outside [0,nver) are skipped (the reference reads out of bounds).
- * mesh: the mesh table of `tri` (cluster rasterizer) or NULL (generic per-triangle path); same outputs either way.
+ * mesh: the mesh table of `tri` (shared-memory tile rasterizer, raster_tile.cuh) or NULL (generic per-triangle gather kernel); same outputs either way.
  * At most 65535 faces per call. */
 size_t fr_render_workspace_bytes(int batch, int nver, int height, int width);
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,

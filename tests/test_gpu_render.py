@@ -334,3 +334,38 @@ def test_full_size_properties_batch_256():
     x = torch.stack([vp[:, 0, :][bidx, i] for i in (i1, i2, i3)])
     y = torch.stack([vp[:, 1, :][bidx, i] for i in (i1, i2, i3)])
     assert bool(((x.min(0).values <= px) & (px <= x.max(0).values) & (y.min(0).values <= py) & (py <= y.max(0).values)).all())   # (d)
+
+
+@pytest.mark.parametrize("B", [9, 17, 33])
+def test_tile_rasterizer_on_golden_cases(render_golden, B):
+    """The stand-alone tile rasterizer (raster_tile.cuh) only runs from 8 faces up: the golden cases (degenerate, duplicate,
+    off-screen, NaN / inf-depth triangles, -0.0 depths, known answers T1-T6) replicated to B faces in rotated order, every face
+    bit-identical to the reference op's output for that face; B = 9 / 17 / 33 leave a ragged last tile."""
+    for name, c in render_golden.items():
+        b0, H, W, _ = [int(x) for x in c["image_shape"]]
+        sel = (np.arange(B) * 3 + 1) % b0
+        got = _gpu_render(c["vertex"][sel], c["tri"], c["texture"][sel] if c["texture"].shape[0] == b0 else c["texture"], H, W, mesh="now")
+        _assert_same(got, [c[k][sel] for k in NAMES], "%s B=%d" % (name, B))
+
+
+def test_tile_rasterizer_large_boxes_and_exact_grid():
+    """Close-up faces: every triangle covers tens of pixels (the plane-equation path of the certified inside test with large
+    boxes and its growing thresholds), vertices on integer coordinates (pixel centres on shared edges and vertices: everything
+    goes through the literal PointInTri pass) and a mix with sub-pixel slivers, at 12 faces through the tile rasterizer."""
+    synth = fr("synth")
+    m = synth.make_synthetic_model(grid=(19, 23), ndim_shape=4, ndim_exp=2, seed=5, jitter=0.3)
+    B, S = 12, 96
+    p = synth.sample_params_constrained(B, 4, 2, S, seed=9)
+    p[:, 6] *= np.linspace(0.6, 1.4, B)                                 # ~4 .. 10 px between grid vertices
+    p[:, 7:11] *= 3.0
+    vp = recon.vertices_transform(p, m, S, dtype=np.float32).astype(np.float32)
+    vp[3] = np.round(vp[3])                                             # integer vertices
+    vp[4, 0:2] = np.round(vp[4, 0:2] * 2.0) / 2.0                       # half-integer
+    vp[5, 1] = vp[5, 1] * 1e-3 + 40.0                                   # squashed: slivers along a pixel row
+    vp[6, 0:2] += 1e4                                                   # entirely off-screen
+    vp[7, 2, ::7] = np.nan                                              # NaN depths never draw
+    want = oracle.oracle_render_depth_forward(vp, m["tri"], m["vertex"], S, S)
+    assert (want[3][0] >= 0).mean() > 0.2 and (want[3][6] < 0).all()
+    for mesh in ("now", None):
+        got = _gpu_render(vp, m["tri"], m["vertex"], S, S, expand_texture=True, mesh=mesh)
+        _assert_same(got, want, "close-up mesh=%r" % (mesh,))
