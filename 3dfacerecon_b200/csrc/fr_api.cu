@@ -600,7 +600,7 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
                                                                    : cudaSuccess;
   };
   if (fused_raster(mesh, flags, batch, nver, ndim_shape, ndim_exp, height, width)) {
-    // prep kernel (clears the keys) -> tensor-core reconstruction with the cluster rasterizer in its epilogue -> resolve
+    // prep kernel (clears the keys) -> tensor-core reconstruction with the tile rasterizer in its epilogue -> resolve
     const f16::RasterTarget target = {static_cast<const unsigned char*>(mesh->dev), keys, width, height};
     const ReconOut out = {vertex_proj, nullptr, 0, 0, nullptr};
     if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, keys, kbytes, batch, nver, ndim_shape, ndim_exp, im_size,

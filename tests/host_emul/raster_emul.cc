@@ -117,10 +117,12 @@ extern "C" int fr_emul_render_forward(const float* vertex, const float* tri, con
   return 0;
 }
 
-// Data flow of the CLUSTER rasterizer (raster_cluster.cuh / the fused reconstruction epilogue): walk the mesh table
-// cluster by cluster, "stage" the cluster's vertices with their snap codes, cull every triangle on the codes of its
-// three LOCAL slots, draw the survivors from the staged coordinates with the packed-key maximum, then resolve depth and
-// index from the keys alone.  Outputs: depth and tri_ind.
+// Data flow of the TILE rasterizer (raster_tile.cuh, stand-alone and inside the fused reconstruction epilogue): walk the mesh
+// table cluster by cluster, "stage" the cluster's vertices with their snap codes, cull every triangle on the raw packed
+// min / max of the codes of its three LOCAL slots (fr_code_nonempty), check the image range on the survivors, run the
+// certified fast inside test (direct form for one-pixel boxes, plane equations for larger ones) with the literal PointInTri for
+// the pixels it leaves undecided, take the packed-key maximum, then resolve depth and index from the keys alone.
+// Outputs: depth and tri_ind.
 extern "C" int fr_emul_render_forward_clustered(const float* vertex, const unsigned char* table, int batch, int nver, int height,
                                                 int width, float* depth, float* tri_ind) {
   fr::MeshTableHeader h;
@@ -152,21 +154,32 @@ extern "C" int fr_emul_render_forward_clustered(const float* vertex, const unsig
         const uint32_t w = te[2 * (size_t)i];
         const int t = (int)te[2 * (size_t)i + 1];
         const unsigned l1 = w & 0xFFu, l2 = (w >> 8) & 0xFFu, l3 = (w >> 16) & 0xFFu;
-        uint32_t lo, hi;
-        if (!fr_code_keep(code[l1], code[l2], code[l3], limit, &lo, &hi)) continue;
+        const uint32_t mn = fr_min3_u16x2(code[l1], code[l2], code[l3]), mx = fr_max3_u16x2(code[l1], code[l2], code[l3]);
+        if (!fr_code_nonempty(mn, mx)) continue;                           // cull phase
+        const bool single = fr_code_single(mn, mx);
+        const uint32_t lo = fr_code_lo(mn), hi = single ? lo : fr_code_hi(mx);
+        if (!fr_box_in_image(lo, hi, limit)) continue;                     // draw phase: image range (:282)
         const float hgt = fr_tri_depth(sz[l1], sz[l2], sz[l3]);
         if (!fr_depth_draws(hgt)) continue;
         FrTriEdge e;
-        fr_tri_edge_setup(sx[l1], sy[l1], sx[l2], sy[l2], sx[l3], sy[l3], &e);
+        fr_tri_edge_setup(sx[l1], sy[l1], sx[l2], sy[l2], sx[l3], sy[l3], &e);   // (only used for undecided pixels)
         const unsigned long long key = fr_pack_key(hgt, t);
         FrBBox bb;
         fr_snap_bbox(lo, hi, &bb);
+        const int ext = (bb.x_max - bb.x_min > bb.y_max - bb.y_min ? bb.x_max - bb.x_min : bb.y_max - bb.y_min) + 1;
+        FrTriFast ff;
+        FrTriPlanes pl;
+        fr_fast_setup(sx[l1], sy[l1], sx[l2], sy[l2], sx[l3], sy[l3], fr_fast_tol(1), &ff);
+        fr_planes_setup(sx[l1], sy[l1], sx[l2], sy[l2], sx[l3], sy[l3], bb.x_min, bb.y_min, fr_fast_tol(ext), &pl);
         for (int y = bb.y_min; y <= bb.y_max; ++y)
-          for (int x = bb.x_min; x <= bb.x_max; ++x)
-            if (fr_point_in_tri(&e, x, y)) {
+          for (int x = bb.x_min; x <= bb.x_max; ++x) {
+            int in = single ? fr_fast_classify(&ff, x, y) : fr_planes_classify(&pl, (float)(x - bb.x_min), (float)(y - bb.y_min));
+            if (in < 0) in = fr_point_in_tri(&e, x, y) ? 1 : 0;
+            if (in) {
               unsigned long long& k = keys[(size_t)y * width + x];
               if (key > k) k = key;
             }
+          }
       }
     }
     for (size_t p = 0; p < npix; ++p) {

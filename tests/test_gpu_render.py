@@ -155,7 +155,7 @@ def test_signed_zero_depths_and_zero_params():
             _assert_same(_gpu_render(v, tri, np.zeros_like(v), 8, 8, mesh=mesh), want, "signed zero")
     lib, check = fr("_lib").lib(), fr("_lib").check
     model = fr("synth").make_synthetic_model(grid=(23, 31), ndim_shape=12, ndim_exp=5, seed=3, jitter=0.2)
-    for tiles, B in ((False, 3), (False, 20), (True, 20)):                 # FFMA path / tcgen05 + records / tcgen05 + cluster rasterizer
+    for tiles, B in ((False, 3), (False, 20), (True, 20)):                 # FFMA path / tcgen05 + records / tcgen05 + tile rasterizer in the epilogue
         dm = fr("model").DeviceModel(model, DEV, cluster_tiles=tiles)
         S = 32
         params = torch.zeros((B, dm.ndim), device=DEV)

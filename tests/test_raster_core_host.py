@@ -105,7 +105,8 @@ def test_snap_code_short_form_matches_definition(emul):
 
 
 def test_clustered_emulation_matches_oracle(emul, render_golden):
-    """The data flow of the cluster rasterizer (mesh table -> staged vertices -> cull on local slots -> packed-key maximum ->
+    """The data flow of the tile rasterizer (mesh table -> staged vertices -> raw min/max cull on local slots -> certified fast inside
+    test with literal fallback -> packed-key maximum ->
     depth / index decoded from the key alone), re-enacted on the host with the real table builder, equals the oracle bit for
     bit: golden cases (degenerate / duplicate / off-screen / NaN-depth triangles, -0.0 depths), a grid mesh and a soup."""
     lib = emul.lib
