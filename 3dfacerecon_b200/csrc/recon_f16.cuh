@@ -372,7 +372,7 @@ template <bool kRaster>
 __global__ void __launch_bounds__(Cfg<kRaster>::kThreads, 1)
 recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned char* __restrict__ bsplit,
                      const float* __restrict__ pose16, const int32_t* __restrict__ cluster_vert, ReconOut out,
-                     RasterTarget target, int batch, int nver, int nch16, int nclusters, float im_size, unsigned flags) {
+                     RasterTarget target, int batch, int nver, int nch16, int nclusters, float im_size, unsigned flags, int bt0) {
   using C = Cfg<kRaster>;
   constexpr int kStages = C::kStages, kEpiWarps = C::kEpiWarps;
   constexpr int kProducerWarp = C::kProducerWarp, kMmaWarp = C::kMmaWarp;
@@ -381,7 +381,8 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
   Barriers* bars = reinterpret_cast<Barriers*>(smem + L.bars);
   float* s_pose = reinterpret_cast<float*>(smem + L.pose);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int b0 = blockIdx.y * kN;
+  const int bt = bt0 + (int)blockIdx.y;                           // batch tile of this CTA (a launch covers tiles bt0 ...)
+  const int b0 = bt * kN;
   const size_t tile_bytes = (size_t)3 * nch16 * kChunkBytes;
   constexpr int kStepFaces = C::kStepFaces;                        // faces the epilogue warps read per step (raster: one stage)
   const int nsteps = (min(kN, batch - b0) + kStepFaces - 1) / kStepFaces;
@@ -422,8 +423,8 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         pdl_wait();
         const uint32_t bbytes = (kN / 8) * L.sbo;
         mbar_arrive_expect_tx(&bars->b_full, 2u * bbytes);
-        bulk_load(smem + L.b0, bsplit + (size_t)blockIdx.y * 2 * bbytes, bbytes, &bars->b_full);
-        bulk_load(smem + L.b1, bsplit + (size_t)blockIdx.y * 2 * bbytes + bbytes, bbytes, &bars->b_full);
+        bulk_load(smem + L.b0, bsplit + (size_t)bt * 2 * bbytes, bbytes, &bars->b_full);
+        bulk_load(smem + L.b1, bsplit + (size_t)bt * 2 * bbytes + bbytes, bbytes, &bars->b_full);
         b_loaded = true;
       };
       uint32_t it = 0;
@@ -668,25 +669,37 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
                                                            clear_bytes / 16);   // normal launch: waits for everything before
   FR_LAUNCHED("recon_prep_f16_kernel");
   const int nbt = ceil_div(batch, f16::kN);
-  int ctas = nsm / nbt;
-  if (ctas < 1) ctas = 1;
   const int ntiles_f = target != nullptr ? g.nclusters : g.ntiles;             // row tiles of the section this flavour streams
-  if (ctas > ntiles_f) ctas = ntiles_f;
   const f16::RasterTarget none = {nullptr, nullptr, 0, 0};
-  if (target != nullptr) {
-    const f16::SmemLayout L = f16::smem_layout<true>(g.nch16);
+  const f16::SmemLayout L = target != nullptr ? f16::smem_layout<true>(g.nch16) : f16::smem_layout<false>(g.nch16);
+  if (target != nullptr)
     FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<true>, dim3(ctas, nbt), dim3(f16::Cfg<true>::kThreads), L.total, st, pdl_enabled(),
-                       base + g.f16c_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
-                       out, *target, batch, nver, g.nch16, g.nclusters, im_size, flags));
-  } else {
-    const f16::SmemLayout L = f16::smem_layout<false>(g.nch16);
+  else
     FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<false>, dim3(ctas, nbt), dim3(f16::Cfg<false>::kThreads), L.total, st, pdl_enabled(),
-                       base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
-                       out, none, batch, nver, g.nch16, g.ntiles, im_size, flags));
+  // One persistent CTA per SM; a batch tile (64 faces) is shared by `ctas` CTAs.  When nsm / nbt leaves many SMs without a
+  // CTA (64 batch tiles: 2 x 64 = 128 of 148), the batch tiles go out in several launches that each fill the GPU: the
+  // first groups with one CTA more per batch tile (49 tiles x 3 CTAs, then 15 x 9: 227 cluster passes per SM instead of 255).
+  for (int bt0 = 0; bt0 < nbt;) {
+    const int rem = nbt - bt0;
+    int ctas = nsm / rem, nb = rem;
+    if (ctas < 1) ctas = 1;
+    if (ctas < ntiles_f && rem * ctas * 10 < nsm * 9 && nsm / (ctas + 1) >= 1) {   // < 90 % of the SMs: one CTA more, fewer tiles
+      ++ctas;
+      nb = nsm / ctas;
+    }
+    if (ctas > ntiles_f) ctas = ntiles_f;
+    if (target != nullptr) {
+      FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<true>, dim3(ctas, nb), dim3(f16::Cfg<true>::kThreads), L.total, st, pdl_enabled(),
+                         base + g.f16c_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
+                         out, *target, batch, nver, g.nch16, g.nclusters, im_size, flags, bt0));
+    } else {
+      FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<false>, dim3(ctas, nb), dim3(f16::Cfg<false>::kThreads), L.total, st, pdl_enabled(),
+                         base + g.f16_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
+                         out, none, batch, nver, g.nch16, g.ntiles, im_size, flags, bt0));
+    }
+    FR_LAUNCHED("recon_fwd_f16_kernel");
+    bt0 += nb;
   }
-  FR_LAUNCHED("recon_fwd_f16_kernel");
   return FR_OK;
 }
 

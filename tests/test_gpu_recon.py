@@ -181,10 +181,11 @@ def test_fused_call_matches_separate_calls(bfm, B, tiles):
 
 
 @pytest.mark.parametrize("tiles", [False, True])
-@pytest.mark.parametrize("B,H,W", [(70, 33, 31), (9, 48, 64), (130, 20, 20)])
+@pytest.mark.parametrize("B,H,W", [(70, 33, 31), (9, 48, 64), (130, 20, 20), (1500, 16, 16)])
 def test_fused_call_small_model_odd_shapes(small_model, B, H, W, tiles):
     """The fused call on a small model (K = 18: one 16-k chunk pair, one M tile), several 64-face batch tiles, non-square images
-    and an odd pixel count (keys cleared by memset instead of the reconstruction epilogue): bit-identical to the two calls."""
+    and an odd pixel count (keys cleared by memset instead of the reconstruction epilogue): bit-identical to the two calls.
+    1500 faces = 24 batch tiles: the reconstruction kernel goes out in several launches that each fill the GPU."""
     lib, check = fr("_lib").lib(), fr("_lib").check
     ks, ke = small_model["ndim_shape"], small_model["ndim_exp"]
     p = fr("synth").sample_params_constrained(B, ks, ke, max(H, W), seed=7 + B)
