@@ -195,6 +195,15 @@ int launch_resolve(const unsigned long long* keys, const float* vertex, const fl
                    long long texture_batch_stride, float* depth, float* texture_image, float* normal, float* tri_ind, int batch,
                    int nver, int ntri, int npix, const LayerOut& layer, bool dependent, cudaStream_t st) {
   const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
+  const bool plain = texture_image == nullptr && normal == nullptr && !layer.enabled;
+  if (plain && ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(depth) | reinterpret_cast<uintptr_t>(tri_ind)) & 15u) == 0) {
+    const unsigned long long n = (unsigned long long)batch * (unsigned long long)npix;      // all faces as one flat array
+    const unsigned long long groups = (n >> 2) > 0 ? (n >> 2) : 1ull;
+    FR_CUDA(launch_pdl(raster_resolve_depth_kernel, dim3((unsigned)((groups + kRasterThreads - 1) / kRasterThreads)), dim3(kRasterThreads), 0, st,
+                       dependent, keys, depth, tri_ind, n));
+    FR_LAUNCHED("raster_resolve_depth_kernel");
+    return FR_OK;
+  }
   if (texture_image != nullptr || normal != nullptr)
     FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, rec, vert_rank, tri, texture,
                        texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));

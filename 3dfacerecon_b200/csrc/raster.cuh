@@ -323,6 +323,33 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
   }
 }
 
+// Depth + index only (the fused params -> depth-map call): a pure streaming pass over the keys of ALL faces as one flat array,
+// four consecutive pixels per thread -- two 16-byte key loads, one 16-byte store per output (render_depth_op.cc:187,192 for
+// the background values).  The caller guarantees 16-byte aligned pointers and n4 = n / 4 groups; the last (n % 4) pixels are
+// done by the first threads of block 0.
+__global__ void __launch_bounds__(kRasterThreads)
+raster_resolve_depth_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ depth, float* __restrict__ tri_ind,
+                            unsigned long long n) {
+  pdl_wait();      // every atomicMax of the visibility pass has landed
+  const unsigned long long i = (unsigned long long)blockIdx.x * kRasterThreads + threadIdx.x;
+  const unsigned long long n4 = n >> 2;
+  auto decode = [](unsigned long long key, float* d, float* t) {
+    *d = key != 0ull ? fr_key_depth(key) : __uint_as_float(FR_BACKGROUND_DEPTH_BITS);
+    *t = key != 0ull ? (float)fr_key_triangle(key) : -1.0f;
+  };
+  if (i < n4) {
+    const ulonglong2 a = reinterpret_cast<const ulonglong2*>(keys)[2 * i], b = reinterpret_cast<const ulonglong2*>(keys)[2 * i + 1];
+    float4 d, t;
+    decode(a.x, &d.x, &t.x);
+    decode(a.y, &d.y, &t.y);
+    decode(b.x, &d.z, &t.z);
+    decode(b.y, &d.w, &t.w);
+    reinterpret_cast<float4*>(depth)[i] = d;
+    reinterpret_cast<float4*>(tri_ind)[i] = t;
+  }
+  if (i < (n & 3ull)) decode(keys[4 * n4 + i], depth + 4 * n4 + i, tri_ind + 4 * n4 + i);
+}
+
 // Backward (render_depth_op.cc:325-368).  vertex_grad must be zero on entry (the API memsets it).
 __global__ void __launch_bounds__(kRasterThreads)
 render_backward_kernel(const float* __restrict__ depth_grad, const float* __restrict__ tri,
@@ -358,9 +385,16 @@ render_backward_kernel(const float* __restrict__ depth_grad, const float* __rest
   }
   // warp aggregation: lanes that hit the same triangle add their shares once (lane order => deterministic
   // within the warp); skipped when every lane has its own triangle, the common case for sub-pixel meshes.
-  const unsigned peers = __match_any_sync(0xFFFFFFFFu, t);
+  // Pixels of one large triangle sit next to each other in a row: only when some lane shares its triangle with its right-hand
+  // neighbour is the (slow) match_any / shuffle aggregation worth running; sub-pixel meshes skip it (batch-256 backward:
+  // 212 -> 190 us without it).
+  const int t_next = __shfl_down_sync(0xFFFFFFFFu, t, 1);       // (every lane takes part: no short-circuit in front of it)
+  const bool share_next = t >= 0 && t_next == t && lane != 31u;
+  unsigned peers = 1u << lane;
+  const bool aggregate = __any_sync(0xFFFFFFFFu, share_next);
+  if (aggregate) peers = __match_any_sync(0xFFFFFFFFu, t);
   const bool leader = (peers & ((1u << lane) - 1u)) == 0u;
-  if (__any_sync(0xFFFFFFFFu, t >= 0 && peers != (1u << lane))) {
+  if (aggregate) {
     float sum = 0.0f;
     for (int src = 0; src < 32; ++src) {
       const float v = __shfl_sync(0xFFFFFFFFu, share, src);
