@@ -75,7 +75,10 @@ struct Cfg {
   //           moves on to its next octet; the groups only meet at the accumulator hand-over, so while one group waits
   //           at its own barrier or runs its short cull phase the others keep the issue slots busy.
   static constexpr int kGroups = kRaster ? 3 : 1;
-  static constexpr int kGroupWarps = 8;
+#ifndef FR_FUSED_GROUP_WARPS
+#define FR_FUSED_GROUP_WARPS 8      // 10: two more warps per group that only draw (A/B)
+#endif
+  static constexpr int kGroupWarps = kRaster ? FR_FUSED_GROUP_WARPS : 8;
   static constexpr int kEpiWarps = kGroups * kGroupWarps;
   static constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   static constexpr int kThreads = (kEpiWarps + 2) * 32;
@@ -588,12 +591,15 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         for (int o = first; o < tw.step1; o += 3) {
           // ---- this warp's share of the octet (faces fh * 4 ...) from the accumulators, projected, in registers: overlaps
           // the tail of the group's previous draw phase
+          const bool stager = gw < 8;                             // (warps beyond the first eight of a group only draw)
           float x[kFPW], y[kFPW], z[kFPW];
-          const int jb = o * kStepFaces + fh * kFPW;              // first of the four faces within the batch tile
-          tmem_ld<kFPW>(d_addr + 0 * kN + jb, x);
-          tmem_ld<kFPW>(d_addr + 1 * kN + jb, y);
-          tmem_ld<kFPW>(d_addr + 2 * kN + jb, z);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int jb = o * kStepFaces + (fh & 1) * kFPW;        // first of the four faces within the batch tile
+          if (stager) {
+            tmem_ld<kFPW>(d_addr + 0 * kN + jb, x);
+            tmem_ld<kFPW>(d_addr + 1 * kN + jb, y);
+            tmem_ld<kFPW>(d_addr + 2 * kN + jb, z);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
           if (o + 3 >= tw.step1) {                                // the group's last octet: accumulators drained
             tc_fence_before();
             __syncwarp();
@@ -602,23 +608,27 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
           const int fb = b0 + o * kStepFaces;                     // first face of the octet
           const int nlive = min(kStepFaces, batch - fb);
           float4 r[kFPW];
+          if (stager) {
 #pragma unroll
-          for (int j = 0; j < kFPW; ++j) {
-            const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPose16Stride);
-            const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
-            const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
-            project_vertex(P, x[j], y[j], z[j], im_size, flags, &r[j].x, &r[j].y, &r[j].z);
-            r[j].w = __uint_as_float(fr_snap_code(r[j].x, r[j].y, target.width, target.height));
-            if (owner && fh * kFPW + j < nlive) store_planar(out.planar, fb + fh * kFPW + j, nver, n, r[j].x, r[j].y, r[j].z);
+            for (int j = 0; j < kFPW; ++j) {
+              const float4* pp = reinterpret_cast<const float4*>(s_pose + (jb + j) * kPose16Stride);
+              const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+              const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+              project_vertex(P, x[j], y[j], z[j], im_size, flags, &r[j].x, &r[j].y, &r[j].z);
+              r[j].w = __uint_as_float(fr_snap_code(r[j].x, r[j].y, target.width, target.height));
+              if (owner && fh * kFPW + j < nlive) store_planar(out.planar, fb + fh * kFPW + j, nver, n, r[j].x, r[j].y, r[j].z);
+            }
           }
           asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // the group's previous draw is complete
           if (o == first && gtid < ntri_c)                        // (same packing as rt::load_tris)
             ts.tri[gtid] = make_uint4((te.x & 0xFFu) << 4, ((te.x >> 8) & 0xFFu) << 4, ((te.x >> 16) & 0xFFu) << 4, (0x7FFFFFFFu - te.y) << 1);
           if (gtid == 0) ts.count = 0u;
+          if (stager) {
 #pragma unroll
-          for (int j = 0; j < kFPW; ++j) ts.rec[fh * kFPW + j][v] = r[j];                // the staged records ...
-          ts.code4[fh][v] = make_uint4(__float_as_uint(r[0].w), __float_as_uint(r[1].w), __float_as_uint(r[2].w),
-                                       __float_as_uint(r[3].w));                         // ... and their code words again
+            for (int j = 0; j < kFPW; ++j) ts.rec[fh * kFPW + j][v] = r[j];              // the staged records ...
+            ts.code4[fh][v] = make_uint4(__float_as_uint(r[0].w), __float_as_uint(r[1].w), __float_as_uint(r[2].w),
+                                         __float_as_uint(r[3].w));                       // ... and their code words again
+          }
           asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // staged octet (and triangle list) complete
           if ((gw << 5) < ntri_c)                                 // cull: thread = triangle, the octet's 8 faces
             rt::cull_triangle<kStepFaces, kStepFaces / 4>(ts, gtid, 0, (gtid < ntri_c) ? ((1u << nlive) - 1u) : 0u, lane);

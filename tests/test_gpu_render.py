@@ -369,3 +369,20 @@ def test_tile_rasterizer_large_boxes_and_exact_grid():
     for mesh in ("now", None):
         got = _gpu_render(vp, m["tri"], m["vertex"], S, S, expand_texture=True, mesh=mesh)
         _assert_same(got, want, "close-up mesh=%r" % (mesh,))
+
+
+def test_images_beyond_the_tile_rasterizer_limit():
+    """The tile rasterizer's packed cull needs snap codes below 2^15 (images up to 16 000 px a side); a 16 500 x 2 image at 9
+    faces with a mesh table must take the gather kernel and still match the reference bit for bit."""
+    rng = np.random.default_rng(11)
+    nv, B, H, W = 60, 9, 2, 16500
+    v = np.empty((B, 3, nv), np.float32)
+    v[:, 0] = rng.uniform(16380.0, 16499.0, (B, nv))            # around and beyond x = 16384
+    v[:, 1] = rng.uniform(-0.5, 1.9, (B, nv))
+    v[:, 2] = rng.uniform(-1, 1, (B, nv))
+    tri = rng.integers(0, nv, (3, 200)).astype(np.float32)
+    tex = rng.uniform(0, 1, (B, 3, nv)).astype(np.float32)
+    want = oracle.oracle_render_depth_forward(v, tri, tex, H, W)
+    assert (want[3] >= 0).sum() > 50
+    for mesh in MESH_MODES:
+        _assert_same(_gpu_render(v, tri, tex, H, W, mesh=mesh), want, "wide image mesh=%r" % (mesh,))
