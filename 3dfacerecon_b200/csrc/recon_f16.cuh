@@ -323,30 +323,53 @@ __device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
 }
 
 // Tile schedule of one CTA: the clusters are dealt round-robin to the gridDim.x CTAs of a batch tile.  When the last round
-// is short (nclusters % gridDim.x != 0) its clusters are SPLIT by epilogue steps (32-face halves of the batch tile) over
-// several CTAs, each of which repeats the cluster's (cheap) tensor-core pass but projects / rasterizes only its share of
-// the faces: the per-SM epilogue work, which bounds the raster flavour, then ends together instead of leaving most SMs idle
-// for a whole cluster time (510 clusters on 148 SMs: 3.5 cluster times instead of 4).
+// is short (nclusters % gridDim.x != 0) its clusters are SPLIT by epilogue steps over several CTAs, each of which repeats the
+// cluster's (cheap) tensor-core pass but projects / rasterizes only its share of the faces: the per-SM epilogue work, which
+// bounds the raster flavour, then ends together instead of leaving most SMs idle for a whole cluster time.
+// share_first (raster flavour): the FIRST round is shared by PAIRS of CTAs -- both stream cluster j / 2 (the second reader
+// hits the lines the first one is fetching: half the HBM bytes) and each rasterizes half of its steps.  Nothing can be
+// rasterized before a CTA's first cluster is complete, and with every SM pulling its own 360 KB that takes ~11 us of a
+// 90 us step; halving the bytes of the first round halves that wait, and the half-size first job is still long enough to
+// cover the stream of the next cluster.  Measured: 91.3 -> 89.0 us per step at 64 faces; with several batch tiles per launch the
+// wait is amortised and the pairing only costs balance (4096 faces: 4.08 -> 4.14 ms), so it is used for single-tile launches only.
+#ifndef FR_SHARE_FIRST_ROUND
+#define FR_SHARE_FIRST_ROUND 1
+#endif
 struct TileWalk {
   int tile, step0, step1;          // current cluster and its epilogue steps [step0, step1)
-  int g, j, nfullw, rem, split, nsteps, k;
-  __device__ TileWalk(int nclusters, int nsteps_) : g((int)gridDim.x), j((int)blockIdx.x), nsteps(nsteps_), k(-1) {
-    nfullw = nclusters / g;
-    rem = nclusters - nfullw * g;
+  int g, j, nfullw, rem, split, nsteps, k, c0;
+  __device__ TileWalk(int nclusters, int nsteps_, bool share_first = false)
+      : g((int)gridDim.x), j((int)blockIdx.x), nsteps(nsteps_), k(-1), c0(0) {
+    if (FR_SHARE_FIRST_ROUND && share_first && g >= 2 && nsteps >= 2 && nclusters >= g) c0 = (g + 1) / 2;   // clusters of the shared round
+    const int n = nclusters - c0;
+    nfullw = n / g;
+    rem = n - nfullw * g;
     split = (rem > 0) ? min(nsteps, g / rem) : 1;
     if (split < 1) split = 1;
     tile = step0 = step1 = 0;
   }
   __device__ bool next() {
     ++k;
-    if (k < nfullw) {
-      tile = j + k * g;
+    int kk = k;
+    if (c0 > 0) {
+      if (k == 0) {                                  // shared round: CTAs 2 t and 2 t + 1 take the two halves of cluster t
+        tile = j >> 1;
+        const bool alone = (j == g - 1) && (g & 1);  // odd CTA count: the last CTA has its cluster to itself
+        const int half = nsteps >> 1;
+        step0 = (alone || !(j & 1)) ? 0 : half;
+        step1 = (alone || (j & 1)) ? nsteps : half;
+        return true;
+      }
+      kk = k - 1;
+    }
+    if (kk < nfullw) {
+      tile = c0 + j + kk * g;
       step0 = 0;
       step1 = nsteps;
       return true;
     }
-    if (k == nfullw && j < rem * split) {
-      tile = nfullw * g + j / split;
+    if (kk == nfullw && j < rem * split) {
+      tile = c0 + nfullw * g + j / split;
       const int part = j - (j / split) * split;
       step0 = part * nsteps / split;
       step1 = (part + 1) * nsteps / split;
@@ -434,7 +457,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
 #if FR_BASIS_EVICT_FIRST
       const uint64_t stream_policy = tc::l2_evict_first_policy();
 #endif
-      for (TileWalk tw(nclusters, nsteps); tw.next();) {
+      for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next();) {
         const unsigned char* src = tiles + (size_t)tw.tile * tile_bytes;
         for (int sg = 0; sg < nch16; ++sg, ++it) {             // nch16 stages of 3 chunks per tile
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
@@ -458,7 +481,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     const uint64_t db1 = tc::make_smem_desc(smem_u32(smem + L.b1), 128u, L.sbo);
     const uint64_t da0 = tc::make_smem_desc(smem_u32(smem + L.raw), 2048u, 128u);   // same descriptor format for A
     uint32_t it = 0, tcount = 0;
-    for (TileWalk tw(nclusters, nsteps); tw.next(); ++tcount) {
+    for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next(); ++tcount) {
       const uint32_t dbuf = tcount % kDBufs;
       mbar_wait(&bars->d_empty[dbuf], ((tcount / kDBufs) & 1u) ^ 1u);          // epilogue has drained this accumulator set
       tc_fence_after();
@@ -504,7 +527,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       const int wq = warp >> 2;                                   // position within the quarter: faces wq * 16 ... of a step
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // the epilogue warps only
       uint32_t tcount = 0;
-      for (TileWalk tw(nclusters, nsteps); tw.next(); ++tcount) {
+      for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next(); ++tcount) {
         const int tile = tw.tile;
         const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
         // vertex of this row, and whether this tile is the one that writes it
@@ -559,7 +582,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       const int npix = target.width * target.height;
       asm volatile("bar.sync 4, %0;" ::"n"(kEpiWarps * 32) : "memory");   // poses in place (all epilogue warps)
       uint32_t tcount = 0;
-      for (TileWalk tw(nclusters, nsteps); tw.next(); ++tcount) {
+      for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next(); ++tcount) {
         const int tile = tw.tile;
         const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
         // octets of this tile that belong to the group: o = first, first + 3, ... (rotated from tile to tile)
