@@ -414,3 +414,53 @@ def test_device_model_tri_base_and_mesh_cache(small_model, tmp_path):
     want = fr("nets.network").recon_project(p, dm_zero, 64)
     for dm in (dm_auto, dm_cached, dm_rebuilt):
         assert torch.equal(fr("nets.network").recon_project(p, dm, 64), want)
+
+
+@pytest.mark.parametrize("tiles", [False, True])
+def test_fused_call_on_adversarial_geometry(tiles):
+    """The fused params -> depth-map call on geometry that lands EXACTLY on pixel centres and edges (integer mean grid, f = 1 and
+    f = 0.5, integer translations: the certified fast inside test must hand every such pixel to the literal PointInTri pass),
+    partly off-screen faces, and NaN / inf / huge mean entries (culled like the reference culls them) -- through both fused
+    flavours (records pipeline / tile rasterizer inside the reconstruction epilogue), against the reference semantics
+    evaluated on the vertices the planar reconstruction call returns for the same parameters."""
+    lib, check = fr("_lib").lib(), fr("_lib").check
+    synth = fr("synth")
+    m = synth.make_synthetic_model(grid=(23, 31), ndim_shape=2, ndim_exp=1, seed=3, jitter=0.0)
+    n = 23 * 31
+    col, row = np.meshgrid(np.arange(23, dtype=np.float32), np.arange(31, dtype=np.float32))
+    mu = np.stack([col.ravel() + 2.0, row.ravel() + 1.0, ((col + 2 * row) % 5).ravel()]).astype(np.float32)      # integer grid
+    mu[0, 40], mu[1, 77], mu[2, 200] = np.nan, np.inf, np.nan
+    mu[0, 300], mu[1, 333] = 3.0e30, -3.0e30
+    m["mu"] = mu.reshape(3 * n, 1)
+    m["pc_shape"] = np.zeros_like(m["pc_shape"])
+    m["pc_exp"] = np.zeros_like(m["pc_exp"])
+    B, S = 12, 40
+    p = np.zeros((B, 7 + 2 + 1), np.float32)
+    p[:, 6] = 1.0
+    p[6:, 6] = 0.5                                                        # half-integer coordinates
+    p[:, 3] = np.arange(B) % 6 - 2                                        # integer shifts, some faces partly off-screen
+    p[:, 4] = (np.arange(B) * 3) % 7
+    p[10, 3] = 1000.0                                                     # one face entirely off-screen
+    dm = fr("model").DeviceModel(m, DEV, cluster_tiles=tiles)
+    pt = torch.from_numpy(p).to(DEV)
+    sp = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(lib.fr_pipeline_workspace_bytes(B, dm.nver, 2, 1, S, S), dtype=torch.uint8, device=DEV)
+    rb = lib.fr_recon_workspace_bytes(B, dm.nver, 2, 1)
+    vp = torch.empty((B, 3, dm.nver), device=DEV)
+    check(lib.fr_recon_project_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.mesh.handle, vp.data_ptr(), B, dm.nver, 2, 1, float(S),
+                                       dm.run_flags, ws.data_ptr(), rb, sp))
+    torch.cuda.synchronize()
+    v = vp.cpu().numpy()
+    ok = np.isfinite(mu).all(axis=0) & (np.abs(mu) < 1e29).all(axis=0)
+    assert (v[0, 0, ok] == mu[0, ok] + p[0, 3]).all() and (v[0, 1, ok] == S - (mu[1, ok] + p[0, 4]) - 1).all()   # exact integers
+    assert np.isnan(v[:, 0, 40]).all() and not np.isfinite(v[:, 1, 77]).any()
+    want = oracle.oracle_render_depth_forward(v, m["tri"], np.zeros_like(v), S, S)
+    assert (want[3][0] >= 0).sum() > 300 and (want[3][10] < 0).all()
+    d, t = torch.empty((B, S, S, 1), device=DEV), torch.empty((B, S, S, 1), device=DEV)
+    ws.fill_(0xA5)
+    check(lib.fr_recon_render_forward(pt.data_ptr(), dm.packed.data_ptr(), dm.tri.data_ptr(), dm.mesh.handle, None, d.data_ptr(),
+                                      t.data_ptr(), B, dm.nver, dm.ntri, 2, 1, S, S, float(S), dm.run_flags, ws.data_ptr(), ws.numel(),
+                                      sp, None))
+    torch.cuda.synchronize()
+    assert t.cpu().numpy().tobytes() == want[3].tobytes()
+    assert d.cpu().numpy().tobytes() == want[0].tobytes()
