@@ -190,8 +190,8 @@ int tile_keys_min_batch() {
 }
 
 // Resolve pass: keys -> depth / tri_ind (+ normals, texture, rendering-layer post-processing).
-int launch_resolve(const unsigned long long* keys, const float* vertex, const float4* rec, const int32_t* vert_rank, const float* tri,
-                   const float* texture,
+int launch_resolve(const unsigned long long* keys, const float* vertex, const float4* rec, const int32_t* vert_rank,
+                   const uint4* tri_rank4, const float4* tex4, const float* tri, const float* texture,
                    long long texture_batch_stride, float* depth, float* texture_image, float* normal, float* tri_ind, int batch,
                    int nver, int ntri, int npix, const LayerOut& layer, bool dependent, cudaStream_t st) {
   const dim3 rgrid(ceil_div(npix, kRasterThreads * kResolvePerThread), batch);
@@ -205,10 +205,10 @@ int launch_resolve(const unsigned long long* keys, const float* vertex, const fl
     return FR_OK;
   }
   if (texture_image != nullptr || normal != nullptr)
-    FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, rec, vert_rank, tri, texture,
+    FR_CUDA(launch_pdl(raster_resolve_kernel<true>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, rec, vert_rank, tri_rank4, tex4, tri, texture,
                        texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
   else
-    FR_CUDA(launch_pdl(raster_resolve_kernel<false>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, rec, vert_rank, tri, texture,
+    FR_CUDA(launch_pdl(raster_resolve_kernel<false>, rgrid, dim3(kRasterThreads), 0, st, dependent, keys, vertex, rec, vert_rank, tri_rank4, tex4, tri, texture,
                        texture_batch_stride, depth, texture_image, normal, tri_ind, nver, ntri, npix, layer));
   FR_LAUNCHED("raster_resolve_kernel");
   return FR_OK;
@@ -289,9 +289,20 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
   } else if (!records_ready) {
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
   }
-  // (the records hold this batch's vertices whenever something was drawn; normals then gather them instead of the planar tensor)
-  return launch_resolve(keys, vertex, draws ? rec : nullptr, mesh_vert_rank(mesh), tri, texture, texture_batch_stride, depth, texture_image,
-                        normal, tri_ind, batch, nver, ntri, npix, layer, pdl && draws && after_keys == nullptr, st);
+  // (the records hold this batch's vertices whenever something was drawn; normals then gather them instead of the planar tensor;
+  // with a mesh table the winner's vertex ranks come from one 16-byte gather, and a texture shared by all faces is repacked
+  // once per call as float4 by rank)
+  const uint4* tri_rank4 = (mesh != nullptr && draws) ? reinterpret_cast<const uint4*>(mesh->dev + mesh_off_tri_rank4(mesh->hdr)) : nullptr;
+  float4* tex4 = nullptr;
+  if (tri_rank4 != nullptr && texture_image != nullptr && texture_batch_stride == 0) {
+    tex4 = reinterpret_cast<float4*>(static_cast<char*>(workspace) + key_bytes(batch, height, width) +
+                                     align_up(sizeof(float4) * (size_t)batch * nver, kAlign));
+    raster_pack_texture_kernel<<<ceil_div(nver, kRasterThreads), kRasterThreads, 0, st>>>(texture, mesh_vert_rank(mesh), tex4, nver);
+    FR_LAUNCHED("raster_pack_texture_kernel");
+  }
+  return launch_resolve(keys, vertex, draws ? rec : nullptr, mesh_vert_rank(mesh), tri_rank4, tex4, tri, texture, texture_batch_stride,
+                        depth, texture_image, normal, tri_ind, batch, nver, ntri, npix, layer,
+                        pdl && draws && after_keys == nullptr && tex4 == nullptr, st);
 }
 
 }  // namespace
@@ -351,7 +362,7 @@ int fr_mesh_table_from_blob(const void* blob, size_t bytes, int device, fr_mesh_
                  (size_t)h.off_tri_begin + ((size_t)h.nclusters + 1) * 4 <= h.off_tri &&
                  (size_t)h.off_tri + (size_t)h.ntri_slots * 8 <= h.off_tri_vid &&
                  (size_t)h.off_tri_vid + (size_t)h.ntri_slots * 16 <= h.off_rank_vert && h.off_rank_vert <= h.off_vert_rank &&
-                 h.nver > 0 && (size_t)mesh_off_cluster_rank(h) + (size_t)h.nclusters * kClusterVerts * 4 <= bytes,
+                 h.nver > 0 && h.ntri >= 0 && (size_t)mesh_off_tri_rank4(h) + (size_t)h.ntri * 16 <= bytes,
              "mesh table blob is inconsistent");
   const unsigned char* p = static_cast<const unsigned char*>(blob);
   uint32_t hash = 2166136261u;
@@ -514,7 +525,8 @@ int fr_recon_project_backward(const float* params, const float* packed, const fl
 size_t fr_render_workspace_bytes(int batch, int nver, int height, int width) {
   if (batch <= 0 || nver <= 0 || height <= 0 || width <= 0) return 0;
   return key_bytes(batch, height, width) +                                   // visibility keys
-         align_up(sizeof(float4) * (size_t)batch * nver, kAlign);            // vertex records
+         align_up(sizeof(float4) * (size_t)batch * nver, kAlign) +           // vertex records
+         align_up(sizeof(float4) * (size_t)nver, kAlign);                    // a shared texture repacked by vertex rank
 }
 
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
@@ -618,7 +630,7 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
     FR_CUDA(record(0));
     FR_CUDA(record(1));
     const LayerOut layer = {nullptr, nullptr, nullptr, false};
-    if (int rc = launch_resolve(keys, nullptr, nullptr, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height * width,
+    if (int rc = launch_resolve(keys, nullptr, nullptr, nullptr, nullptr, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height * width,
                                 layer, pdl_enabled() && !timed, st))
       return rc;
     FR_CUDA(record(2));

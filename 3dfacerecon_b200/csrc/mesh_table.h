@@ -24,7 +24,7 @@ namespace fr {
 constexpr int kClusterVerts = 128;   // == kTileVerts (TMEM lanes of one reconstruction tile)
 constexpr int kClusterTris = 256;    // local triangle ids fit 8 bits
 constexpr uint32_t kMeshMagic = 0x544D5246u;   // "FRMT"
-constexpr uint32_t kMeshVersion = 3u;
+constexpr uint32_t kMeshVersion = 4u;
 constexpr uint32_t kVertOwner = 0x40000000u;   // cluster_vert flag: this cluster writes the vertex to planar outputs
 constexpr uint32_t kVertIdMask = 0x00FFFFFFu;  // nver <= 2^24 (float triangle indices are exact up to there)
 
@@ -40,6 +40,9 @@ constexpr uint32_t kVertIdMask = 0x00FFFFFFu;  // nver <= 2^24 (float triangle i
 //   cluster_rank  int32 [nclusters][128]   rank of the vertex in every cluster slot (-1 = unused slot): where the tile
 //                                          rasterizer (raster_tile.cuh) finds the slot's 16-byte record; starts at
 //                                          mesh_off_cluster_rank(header) (derived: the 64-byte header is full)
+//   tri_rank4     uint4 [ntri]             by ORIGINAL triangle index: { r1, r2, r3 (vertex ranks), 1 } or all zero for a
+//                                          triangle that was dropped: one 16-byte gather resolves a winner's vertices in the
+//                                          resolve pass; starts at mesh_off_tri_rank4(header)
 // RANK = the position of a vertex in cluster order (clusters in table order, within a cluster its owned vertices in slot
 // order).  Kernels that keep per-vertex data in global memory (the 16-byte vertex records of raster.cuh, the row order of
 // the packed basis) use ranks instead of the mesh's own numbering: the vertices a block of triangles touches are then
@@ -60,6 +63,10 @@ static_assert(sizeof(MeshTableHeader) == 64, "header is 64 bytes");
 __host__ __device__
 #endif
 inline uint32_t mesh_off_cluster_rank(const MeshTableHeader& h) { return (h.off_vert_rank + (uint32_t)h.nver * 4u + 15u) / 16u * 16u; }
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t mesh_off_tri_rank4(const MeshTableHeader& h) { return mesh_off_cluster_rank(h) + (uint32_t)h.nclusters * 128u * 4u; }
 
 }  // namespace fr
 
@@ -430,7 +437,7 @@ class MeshTableBuilder {
     const uint32_t nrank = (uint32_t)((nver_ + kClusterVerts - 1) / kClusterVerts * kClusterVerts);
     h.off_rank_vert = h.off_tri_vid + (uint32_t)nvalid_ * 16u;
     h.off_vert_rank = h.off_rank_vert + nrank * 4u;
-    h.total_bytes = (mesh_off_cluster_rank(h) + (uint32_t)ncl * kClusterVerts * 4u + 255u) / 256u * 256u;
+    h.total_bytes = (mesh_off_tri_rank4(h) + (uint32_t)ntri_ * 16u + 255u) / 256u * 256u;
     std::vector<unsigned char> blob(h.total_bytes, 0);
     int32_t* cv = reinterpret_cast<int32_t*>(blob.data() + h.off_vert);
     int32_t* tb = reinterpret_cast<int32_t*>(blob.data() + h.off_tri_begin);
@@ -503,6 +510,12 @@ class MeshTableBuilder {
     int32_t* cluster_rank = reinterpret_cast<int32_t*>(blob.data() + mesh_off_cluster_rank(h));
     for (size_t i = 0; i < (size_t)ncl * kClusterVerts; ++i)
       cluster_rank[i] = cv[i] >= 0 ? vert_rank[(uint32_t)cv[i] & kVertIdMask] : -1;
+    uint32_t* tr4 = reinterpret_cast<uint32_t*>(blob.data() + mesh_off_tri_rank4(h));       // (zero-initialised: dropped triangles)
+    for (int i = 0; i < nvalid_; ++i) {
+      uint32_t* e = tr4 + 4 * (size_t)orig_[i];
+      for (int k = 0; k < 3; ++k) e[k] = (uint32_t)vert_rank[tv_[3 * i + k]];
+      e[3] = 1u;
+    }
     h.max_cluster_tris = max_tris;
     h.nvert_slots = nslots;
     uint32_t hash = 2166136261u;

@@ -196,6 +196,17 @@ raster_keys_kernel(const float4* __restrict__ rec, const float* __restrict__ tri
   }
 }
 
+// A texture shared by all faces (texture_batch_stride == 0: [3, nver] planar, the reference's tiled vertex colours) repacked once
+// per call as one float4 per vertex RANK, so that the resolve pass fetches a winner's three texture vectors with three 16-byte
+// gathers instead of nine 4-byte ones.
+__global__ void __launch_bounds__(kRasterThreads)
+raster_pack_texture_kernel(const float* __restrict__ texture, const int32_t* __restrict__ vert_rank, float4* __restrict__ tex4, int nver) {
+  const int n = blockIdx.x * kRasterThreads + threadIdx.x;
+  if (n >= nver) return;
+  tex4[vert_rank != nullptr ? __ldg(vert_rank + n) : n] =
+      make_float4(__ldg(texture + n), __ldg(texture + nver + n), __ldg(texture + 2 * (size_t)nver + n), 0.0f);
+}
+
 // kResolvePerThread pixels per thread (keys loaded up front, coalesced).  Depth and triangle index are decoded straight
 // from the key (a pure streaming pass that never touches the vertices); the vertex gathers only happen when normals /
 // texture are requested.
@@ -214,8 +225,8 @@ struct LayerOut {
 template <bool kAttributes>
 __global__ void __launch_bounds__(kRasterThreads)
 raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ vertex, const float4* __restrict__ rec,
-                      const int32_t* __restrict__ vert_rank, const float* __restrict__ tri, const float* __restrict__ texture,
-                      long long texture_batch_stride,
+                      const int32_t* __restrict__ vert_rank, const uint4* __restrict__ tri_rank4, const float4* __restrict__ tex4,
+                      const float* __restrict__ tri, const float* __restrict__ texture, long long texture_batch_stride,
                       float* __restrict__ depth, float* __restrict__ texture_image, float* __restrict__ normal,
                       float* __restrict__ tri_ind, int nver, int ntri, int npix, LayerOut layer) {
   __shared__ __align__(16) float s_attr[kAttributes ? 2 : 1][kAttributes ? 3 * kRasterThreads * kResolvePerThread : 4];
@@ -244,6 +255,30 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
       ti = (float)t;
       d = fr_key_depth(key);           // exact bits of the winner's depth, including the sign of a zero (raster_core.h)
       if (kAttributes) {               // the winner's vertices are only needed for normals / texture
+        if (tri_rank4 != nullptr && rec != nullptr) {
+          // mesh table: ONE 16-byte gather gives the three vertex ranks; records and the packed texture are indexed by rank
+          const uint4 tr = __ldg(tri_rank4 + t);
+          if (normal != nullptr) {
+            const float4* rb = rec + (size_t)b * nver;
+            const float4 r1 = __ldg(rb + tr.x), r2 = __ldg(rb + tr.y), r3 = __ldg(rb + tr.z);
+            fr_tri_normal(r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r3.x, r3.y, r3.z, n);
+          }
+          if (texture_image != nullptr) {
+            if (tex4 != nullptr) {
+              const float4 a = __ldg(tex4 + tr.x), bb = __ldg(tex4 + tr.y), c = __ldg(tex4 + tr.z);
+              tx[0] = fr_tri_mean(a.x, bb.x, c.x);
+              tx[1] = fr_tri_mean(a.y, bb.y, c.y);
+              tx[2] = fr_tri_mean(a.z, bb.z, c.z);
+            } else {                   // per-face textures: planar gathers by vertex id
+              const int p1 = (int)__ldg(tri + t), p2 = (int)__ldg(tri + ntri + t), p3 = (int)__ldg(tri + 2 * (size_t)ntri + t);
+              const float* tex = texture + (size_t)b * texture_batch_stride;
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                tx[c] = fr_tri_mean(__ldg(tex + (size_t)c * nver + p1), __ldg(tex + (size_t)c * nver + p2),
+                                    __ldg(tex + (size_t)c * nver + p3));
+            }
+          }
+        } else {
         const int p1 = (int)__ldg(tri + t), p2 = (int)__ldg(tri + ntri + t), p3 = (int)__ldg(tri + 2 * (size_t)ntri + t);
         if (normal != nullptr) {
           if (rec != nullptr) {        // the rasterizer's 16-byte records (by rank with a mesh table): three gathers, not nine
@@ -266,6 +301,7 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
           for (int c = 0; c < 3; ++c)
             tx[c] = fr_tri_mean(__ldg(tex + (size_t)c * nver + p1), __ldg(tex + (size_t)c * nver + p2),
                                 __ldg(tex + (size_t)c * nver + p3));
+        }
         }
       }
     }

@@ -73,6 +73,8 @@ class MeshTable:
         out["vert_rank"] = b[off_vr:off_vr + out["nver"] * 4].view(np.int32)
         off_cr = (off_vr + out["nver"] * 4 + 15) // 16 * 16
         out["cluster_rank"] = b[off_cr:off_cr + ncl * 128 * 4].view(np.int32).reshape(ncl, 128)
+        off_t4 = off_cr + ncl * 128 * 4
+        out["tri_rank4"] = b[off_t4:off_t4 + out["ntri"] * 16].view(np.uint32).reshape(out["ntri"], 4)
         return out
 
     def close(self):

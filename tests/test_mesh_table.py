@@ -54,6 +54,10 @@ def _check_table(tri, nver, table):
     assert (np.diff(first_owner[rv[:nver] & 0x00FFFFFF]) >= 0).all()       # ranks follow the cluster order
     cr = p["cluster_rank"]                                                   # where the tile rasterizer finds a slot's record
     assert cr.shape == cv.shape and (cr[~used] == -1).all() and (cr[used] == vr[ids[used]]).all()
+    t4 = p["tri_rank4"]                                                      # by original index: ranks of the three vertices, or zeros
+    assert t4.shape == (ntri, 4) and (t4[:, 3] == valid.astype(np.uint32)).all() and not t4[~valid].any()
+    for k in range(3):
+        assert (t4[valid, k].astype(np.int64) == vr[tri[k, valid].astype(np.int64)]).all(), k
     tq = p["tri_vid"]
     assert (tq[:, 3].astype(np.int64) == orig).all()
     for k in range(3):
