@@ -447,6 +447,9 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       bool b_loaded = false;
       auto load_b = [&]() {                                    // the prep kernel's output: wait for it (programmatic dependent launch)
         pdl_wait();
+        // the operands were written by the prep kernel's ordinary (generic-proxy) stores and are read here by the bulk-copy
+        // engine (async proxy): order the two proxies explicitly instead of relying on the dependency wait alone
+        asm volatile("fence.proxy.async;" ::: "memory");
         const uint32_t bbytes = (kN / 8) * L.sbo;
         mbar_arrive_expect_tx(&bars->b_full, 2u * bbytes);
         bulk_load(smem + L.b0, bsplit + (size_t)bt * 2 * bbytes, bbytes, &bars->b_full);
