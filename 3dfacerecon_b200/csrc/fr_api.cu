@@ -825,3 +825,12 @@ int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float
 }
 
 }  // extern "C"
+
+#ifdef FR_TIMELINE
+extern "C" int fr_debug_timeline(long long* out) {   // developer build only (tools/timeline.py): clock64 stamps of the last forward kernel
+  return cudaMemcpyFromSymbol(out, fr::f16::g_timeline, sizeof(long long) * 160 * 16) == cudaSuccess ? 0 : 1;
+}
+extern "C" int fr_debug_cluster_cost(float* out) {   // [1024] cycles per octet of every cluster in the last fused kernel
+  return cudaMemcpyFromSymbol(out, fr::f16::g_cluster_cost, sizeof(float) * 1024) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -41,6 +41,16 @@
 namespace fr {
 namespace f16 {
 
+#ifdef FR_TIMELINE   // developer build (tools/timeline.py): per-CTA clock64 stamps of the forward kernel, per-cluster raster time
+__device__ long long g_timeline[160][16];
+__device__ float g_cluster_cost[1024];       // cycles per octet group 0 spent on the cluster (accumulators complete -> last draw)
+#define FR_TL(slot) do { if (blockIdx.y == 0) g_timeline[blockIdx.x][slot] = clock64(); } while (0)
+#define FR_TLG(slot) do { if (blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_timeline[blockIdx.x][slot] = (long long)t_; } } while (0)
+#else
+#define FR_TL(slot) do {} while (0)
+#define FR_TLG(slot) do {} while (0)
+#endif
+
 using tc::bulk_load;
 using tc::elect_one;
 using tc::mbar_arrive;
@@ -412,6 +422,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
   const size_t tile_bytes = (size_t)3 * nch16 * kChunkBytes;
   constexpr int kStepFaces = C::kStepFaces;                        // faces the epilogue warps read per step (raster: one stage)
   const int nsteps = (min(kN, batch - b0) + kStepFaces - 1) / kStepFaces;
+  if (threadIdx.x == 0) { FR_TL(0); FR_TLG(15); }
 
   // ---- one-time setup: barriers, TMEM, poses
   if (threadIdx.x == 0) {
@@ -440,6 +451,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  if (threadIdx.x == 0) FR_TL(1);
 
   if (warp == kProducerWarp) {
     // ================================================================== producer (TMA engine)
@@ -480,6 +492,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     // ================================================================== MMA issuer (whole warp converged, one elected lane issues)
     mbar_wait(&bars->b_full, 0);
     tc_fence_after();
+    if (lane == 0) FR_TL(5);
     const uint64_t db0 = tc::make_smem_desc(smem_u32(smem + L.b0), 128u, L.sbo);
     const uint64_t db1 = tc::make_smem_desc(smem_u32(smem + L.b1), 128u, L.sbo);
     const uint64_t da0 = tc::make_smem_desc(smem_u32(smem + L.raw), 2048u, 128u);   // same descriptor format for A
@@ -494,6 +507,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         const uint32_t s = it % kStages;
         mbar_wait(&bars->raw_full[s], (it / kStages) & 1u);
         tc_fence_after();
+        if (lane == 0 && it == 0) FR_TL(6);
         uint32_t cj[kStageChunks], cij[kStageChunks];                          // (coordinate, chunk-in-row) of the stage's chunks
 #pragma unroll
         for (int j = 0; j < kStageChunks; ++j) {
@@ -514,6 +528,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
           }
           tc_commit(&bars->raw_empty[s]);                                      // stage reusable once these MMAs have retired
           if (sg == nch16 - 1) tc_commit(&bars->d_full[dbuf]);                 // all three accumulators of the tile complete
+          if (sg == nch16 - 1 && tcount < 4) FR_TL(10 + tcount);
         }
         __syncwarp();
       }
@@ -525,6 +540,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     const int v = qd * 32 + lane;                                 // row of the tile == vertex slot of the cluster
     const uint32_t lane_field = (uint32_t)(qd * 32) << 16;
     pdl_wait();                                                   // the prep kernel's poses (and the cleared keys)
+    if (threadIdx.x == 0) FR_TL(4);
     for (int i = threadIdx.x; i < kN * kPose16Stride; i += kEpiWarps * 32) s_pose[i] = pose16[(size_t)b0 * kPose16Stride + i];
     if constexpr (!kRaster) {
       const int wq = warp >> 2;                                   // position within the quarter: faces wq * 16 ... of a step
@@ -593,6 +609,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         // the accumulators are only handed back by warps that have seen them complete: a warp without work in this tile
         // must not run ahead and arrive for a later tile in this one's phase
         mbar_wait(&bars->d_full[dbuf], dph);
+        if (threadIdx.x == 0 && tcount == 0) FR_TL(8);
         if (first >= tw.step1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
@@ -613,6 +630,9 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         uint2 te = make_uint2(0u, 0u);
         if (gtid < ntri_c) te = __ldg(tv.tri_entry + tb + gtid);
         const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
+#ifdef FR_TIMELINE
+        const long long tl_t0 = clock64();
+#endif
 #pragma unroll 1
         for (int o = first; o < tw.step1; o += 3) {
           // ---- this warp's share of the octet (faces fh * 4 ...) from the accumulators, projected, in registers: overlaps
@@ -661,13 +681,20 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
           asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // survivor list complete
           rt::draw_list(ts, gtid, kGT, target.keys + (size_t)fb * npix, npix, target.width, target.height);
         }
+#ifdef FR_TIMELINE
+        asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");
+        if (grp == 0 && gtid == 0 && blockIdx.y == 0)
+          g_cluster_cost[tile] = (float)(clock64() - tl_t0) / (float)((tw.step1 - first + 2) / 3);
+#endif
       }
     }
   }
 
   // ---- teardown
+  if (threadIdx.x == 0) FR_TL(9);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FR_TL(14);
   if (warp == kProducerWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
