@@ -830,6 +830,13 @@ int fr_session_backward(fr_session* s, const float* depth_grad, int batch, float
 extern "C" int fr_debug_timeline(long long* out) {   // developer build only (tools/timeline.py): clock64 stamps of the last forward kernel
   return cudaMemcpyFromSymbol(out, fr::f16::g_timeline, sizeof(long long) * 160 * 16) == cudaSuccess ? 0 : 1;
 }
+extern "C" int fr_debug_marks(unsigned long long* out, int reset) {   // [8] globaltimer marks (fr_common.cuh); reset: min slots = ~0, max slots = 0
+  if (reset) {
+    const unsigned long long init[8] = {~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
+    return cudaMemcpyToSymbol(fr::g_marks, init, sizeof(init)) == cudaSuccess ? 0 : 1;
+  }
+  return cudaMemcpyFromSymbol(out, fr::g_marks, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : 1;
+}
 extern "C" int fr_debug_cluster_cost(float* out) {   // [1024] cycles per octet of every cluster in the last fused kernel
   return cudaMemcpyFromSymbol(out, fr::f16::g_cluster_cost, sizeof(float) * 1024) == cudaSuccess ? 0 : 1;
 }

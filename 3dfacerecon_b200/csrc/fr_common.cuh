@@ -108,6 +108,17 @@ inline BasisGeom basis_geom(int nver, int ks, int ke, int nclusters = 0) {
 }
 
 #ifdef __CUDACC__
+#ifdef FR_TIMELINE   // developer build (tools/timeline.py): globaltimer marks of the kernels of one fused step
+// [0] prep first start  [1] prep last end  [2] forward first CTA entry  [3] forward last CTA done  [4] resolve first CTA past its
+// dependency wait  [5] resolve last end  [6] resolve first CTA entry
+__device__ unsigned long long g_marks[8];
+__device__ __forceinline__ unsigned long long fr_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define FR_MARK_MIN(i) do { if (threadIdx.x == 0) atomicMin(&g_marks[i], fr_gtime()); } while (0)
+#define FR_MARK_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_marks[i], fr_gtime()); } while (0)
+#else
+#define FR_MARK_MIN(i) do {} while (0)
+#define FR_MARK_MAX(i) do {} while (0)
+#endif
 // Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become resident while its predecessor in
 // the stream is still running; it must call pdl_wait() before touching anything the predecessor writes (and before
 // writing anything the predecessor reads).  The predecessor calls pdl_trigger() once its blocks are resident.  Both are

@@ -366,7 +366,9 @@ raster_resolve_kernel(const unsigned long long* __restrict__ keys, const float* 
 __global__ void __launch_bounds__(kRasterThreads)
 raster_resolve_depth_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ depth, float* __restrict__ tri_ind,
                             unsigned long long n) {
+  FR_MARK_MIN(6);
   pdl_wait();      // every atomicMax of the visibility pass has landed
+  FR_MARK_MIN(4);
   const unsigned long long i = (unsigned long long)blockIdx.x * kRasterThreads + threadIdx.x;
   const unsigned long long n4 = n >> 2;
   auto decode = [](unsigned long long key, float* d, float* t) {
@@ -384,6 +386,7 @@ raster_resolve_depth_kernel(const unsigned long long* __restrict__ keys, float* 
     reinterpret_cast<float4*>(tri_ind)[i] = t;
   }
   if (i < (n & 3ull)) decode(keys[4 * n4 + i], depth + 4 * n4 + i, tri_ind + 4 * n4 + i);
+  FR_MARK_MAX(5);
 }
 
 // Backward (render_depth_op.cc:325-368).  vertex_grad must be zero on entry (the API memsets it).

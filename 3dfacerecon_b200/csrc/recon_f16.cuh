@@ -109,6 +109,7 @@ struct Barriers {
   uint64_t b_full;
   uint32_t tmem_base;
   uint32_t pad;
+  uint32_t oct_taken[4];   // raster flavour: octets of tile t handed out beyond the three static ones, slot t % 4 (FR_DYNAMIC_OCTETS)
 };
 
 using RasterSmem = rt::TileSmem<Cfg<true>::kStepFaces>;   // raster flavour only
@@ -235,6 +236,7 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
   __shared__ float s_pose[kPoseStride];
   __shared__ double s_sc[6];
   pdl_trigger();                                   // the reconstruction kernel may become resident (it waits before reading our output)
+  FR_MARK_MIN(0);
   const int tid = threadIdx.x;
   // fused call: the CTAs behind the (padded) faces only clear the visibility keys for the rasterizer that follows, 16 bytes
   // per store (the consumer kernels wait for this whole grid before their first atomicMax)
@@ -242,6 +244,7 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
     uint4* kv = reinterpret_cast<uint4*>(keys);
     const size_t stride = (size_t)(gridDim.x - bpad) * 256;
     for (size_t i = (size_t)((int)blockIdx.x - bpad) * 256 + tid; i < key_vecs; i += stride) kv[i] = make_uint4(0u, 0u, 0u, 0u);
+    FR_MARK_MAX(1);
     return;
   }
   const int b = blockIdx.x;
@@ -423,6 +426,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
   constexpr int kStepFaces = C::kStepFaces;                        // faces the epilogue warps read per step (raster: one stage)
   const int nsteps = (min(kN, batch - b0) + kStepFaces - 1) / kStepFaces;
   if (threadIdx.x == 0) { FR_TL(0); FR_TLG(15); }
+  FR_MARK_MIN(2);
 
   // ---- one-time setup: barriers, TMEM, poses
   if (threadIdx.x == 0) {
@@ -435,6 +439,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       mbar_init(&bars->d_empty[i], kEpiWarps);
     }
     mbar_init(&bars->b_full, 1);
+    for (int i = 0; i < 4; ++i) bars->oct_taken[i] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kProducerWarp) {
@@ -604,13 +609,21 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next(); ++tcount) {
         const int tile = tw.tile;
         const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
-        // octets of this tile that belong to the group: o = first, first + 3, ... (rotated from tile to tile)
-        const int first = tw.step0 + ((grp + 3 * 128 - (int)(tcount % 3u) - tw.step0 % 3) % 3);
+        // Octets of this tile: every group starts with one static octet (rotated from tile to tile), the rest are handed out
+        // on demand through a shared-memory counter (FR_DYNAMIC_OCTETS): a group that drew a cheap octet -- faces differ a
+        // lot with their poses -- takes the next one instead of idling until the others finish their fixed share.
+        // Counter protocol: slot t % 4 serves tile t; a group only touches it between the tile's d_full and its own
+        // d_empty arrivals; slot (t + 2) % 4 is reset (by each group, before its arrivals for tile t): tile t + 2 cannot be
+        // complete before all those arrivals, and tile t - 2, which used that slot last, was finished by every group
+        // before tile t could be computed.
+        const int first = tw.step0 + (int)((grp + tcount) % 3u);
+        uint32_t* const taken = &bars->oct_taken[tcount & 3u];
         // the accumulators are only handed back by warps that have seen them complete: a warp without work in this tile
         // must not run ahead and arrive for a later tile in this one's phase
         mbar_wait(&bars->d_full[dbuf], dph);
         if (threadIdx.x == 0 && tcount == 0) FR_TL(8);
         if (first >= tw.step1) {
+          if (gtid == 0) bars->oct_taken[(tcount + 2u) & 3u] = 0u;
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
           continue;
@@ -632,9 +645,11 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         const uint32_t d_addr = tmem + lane_field + dbuf * kDCols;
 #ifdef FR_TIMELINE
         const long long tl_t0 = clock64();
+        int tl_octets = 0;
 #endif
+        int nxt = -1;
 #pragma unroll 1
-        for (int o = first; o < tw.step1; o += 3) {
+        for (int o = first; o >= 0; o = nxt) {
           // ---- this warp's share of the octet (faces fh * 4 ...) from the accumulators, projected, in registers: overlaps
           // the tail of the group's previous draw phase
           const bool stager = gw < 8;                             // (warps beyond the first eight of a group only draw)
@@ -645,11 +660,6 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
             tmem_ld<kFPW>(d_addr + 1 * kN + jb, y);
             tmem_ld<kFPW>(d_addr + 2 * kN + jb, z);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          }
-          if (o + 3 >= tw.step1) {                                // the group's last octet: accumulators drained
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
           }
           const int fb = b0 + o * kStepFaces;                     // first face of the octet
           const int nlive = min(kStepFaces, batch - fb);
@@ -666,9 +676,13 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
             }
           }
           asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // the group's previous draw is complete
-          if (o == first && gtid < ntri_c)                        // (same packing as rt::load_tris)
+          if (o == first && gtid < ntri_c)                        // (same packing as rt::load_tris; o == first only once: grabs are > first)
             ts.tri[gtid] = make_uint4((te.x & 0xFFu) << 4, ((te.x >> 8) & 0xFFu) << 4, ((te.x >> 16) & 0xFFu) << 4, (0x7FFFFFFFu - te.y) << 1);
-          if (gtid == 0) ts.count = 0u;
+          if (gtid == 0) {
+            ts.count = 0u;
+            const int want = tw.step0 + 3 + (int)atomicAdd(taken, 1u);          // the group's next octet of this tile, if any is left
+            ts.pad[0] = (unsigned)(want < tw.step1 ? want : -1);
+          }
           if (stager) {
 #pragma unroll
             for (int j = 0; j < kFPW; ++j) ts.rec[fh * kFPW + j][v] = r[j];              // the staged records ...
@@ -676,15 +690,24 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
                                          __float_as_uint(r[3].w));                       // ... and their code words again
           }
           asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // staged octet (and triangle list) complete
+          nxt = (int)ts.pad[0];
+          if (nxt < 0) {                                          // the group's last octet of this tile: accumulators drained
+            if (gtid == 0) bars->oct_taken[(tcount + 2u) & 3u] = 0u;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->d_empty[dbuf]);
+          }
           if ((gw << 5) < ntri_c)                                 // cull: thread = triangle, the octet's 8 faces
             rt::cull_triangle<kStepFaces, kStepFaces / 4>(ts, gtid, 0, (gtid < ntri_c) ? ((1u << nlive) - 1u) : 0u, lane);
           asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // survivor list complete
           rt::draw_list(ts, gtid, kGT, target.keys + (size_t)fb * npix, npix, target.width, target.height);
+#ifdef FR_TIMELINE
+          ++tl_octets;
+#endif
         }
 #ifdef FR_TIMELINE
         asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");
-        if (grp == 0 && gtid == 0 && blockIdx.y == 0)
-          g_cluster_cost[tile] = (float)(clock64() - tl_t0) / (float)((tw.step1 - first + 2) / 3);
+        if (grp == 0 && gtid == 0 && blockIdx.y == 0) g_cluster_cost[tile] = (float)(clock64() - tl_t0) / (float)max(tl_octets, 1);
 #endif
       }
     }
@@ -695,6 +718,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) FR_TL(14);
+  FR_MARK_MAX(3);
   if (warp == kProducerWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");

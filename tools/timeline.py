@@ -24,6 +24,9 @@ names = {1: "setup done", 2: "inputs staged", 3: "operands built", 4: "prep grid
          10: "MMA: tile 0 committed", 11: "MMA: tile 1 committed", 12: "MMA: tile 2 committed", 13: "MMA: tile 3 committed",
          8: "epilogue: first accumulators", 9: "thread 0 leaves the loop", 14: "CTA done"}
 for rep in range(4):
+    if hasattr(raw, "fr_debug_marks"):
+        torch.cuda.synchronize()
+        raw.fr_debug_marks(None, 1)
     flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -32,6 +35,14 @@ for rep in range(4):
     b.record()
     torch.cuda.synchronize()
     print("call %d: %.1f us" % (rep, a.elapsed_time(b) * 1e3))
+if hasattr(raw, "fr_debug_marks"):
+    m = np.zeros(8, np.uint64)
+    assert raw.fr_debug_marks(ctypes.c_void_p(m.ctypes.data), 0) == 0
+    m = m.astype(np.int64)
+    t0 = m[0]
+    for i, name in ((0, "prep first start"), (1, "prep last key-clearing block done"), (2, "forward first CTA entry"), (3, "forward last CTA done"),
+                    (6, "resolve first CTA entry"), (4, "resolve first CTA past its dependency wait"), (5, "resolve last block done")):
+        print("  mark %-44s %7.2f us" % (name, (m[i] - t0) / 1e3))
 tl = np.zeros((160, 16), np.int64)
 assert raw.fr_debug_timeline(ctypes.c_void_p(tl.ctypes.data)) == 0
 g0 = tl[:148, 15].min()
