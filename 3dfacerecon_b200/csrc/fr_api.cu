@@ -622,10 +622,14 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
   };
   if (fused_raster(mesh, flags, batch, nver, ndim_shape, ndim_exp, height, width)) {
     // prep kernel (clears the keys) -> tensor-core reconstruction with the tile rasterizer in its epilogue -> resolve
-    const f16::RasterTarget target = {static_cast<const unsigned char*>(mesh->dev), keys, width, height};
+    // (the pool counter of the forward kernel's item schedule sits behind the keys, where the records pipeline keeps its
+    // vertex records, and is cleared with them)
+    const size_t kpad_bytes = key_bytes(batch, height, width);
+    const f16::RasterTarget target = {static_cast<const unsigned char*>(mesh->dev), keys, width, height,
+                                      reinterpret_cast<unsigned*>(rws + kpad_bytes)};
     const ReconOut out = {vertex_proj, nullptr, 0, 0, nullptr};
-    if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, keys, kbytes, batch, nver, ndim_shape, ndim_exp, im_size,
-                                            flags, workspace, rb, stream))
+    if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, keys, kpad_bytes + 16, batch, nver, ndim_shape, ndim_exp,
+                                            im_size, flags, workspace, rb, stream))
       return rc;
     FR_CUDA(record(0));
     FR_CUDA(record(1));

@@ -109,7 +109,11 @@ struct Barriers {
   uint64_t b_full;
   uint32_t tmem_base;
   uint32_t pad;
-  uint32_t oct_taken[4];   // raster flavour: octets of tile t handed out beyond the three static ones, slot t % 4 (FR_DYNAMIC_OCTETS)
+  uint32_t oct_taken[4];   // raster flavour: octets of tile t handed out beyond the three static ones, slot t % 4
+  uint64_t item_full[8];   // dynamic pool (ItemWalk): entry d % 8 of item_ring is valid
+  int32_t item_ring[8];    // ... the d-th item this CTA took from the pool, -1 = the pool is empty
+  uint32_t raster_pos;     // items whose rasterization has begun (the fastest group's count): throttles the draws from the pool
+  uint32_t pad2;
 };
 
 using RasterSmem = rt::TileSmem<Cfg<true>::kStepFaces>;   // raster flavour only
@@ -351,12 +355,20 @@ __device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
 struct TileWalk {
   int tile, step0, step1;          // current cluster and its epilogue steps [step0, step1)
   int g, j, nfullw, rem, split, nsteps, k, c0;
-  __device__ TileWalk(int nclusters, int nsteps_, bool share_first = false)
-      : g((int)gridDim.x), j((int)blockIdx.x), nsteps(nsteps_), k(-1), c0(0) {
+  int pool0, npool;                // dynamic pool: clusters [pool0, pool0 + npool) are not part of the static schedule
+  __device__ TileWalk(int nclusters, int nsteps_, bool share_first = false, bool pool = false)
+      : g((int)gridDim.x), j((int)blockIdx.x), nsteps(nsteps_), k(-1), c0(0), pool0(nclusters), npool(0) {
     if (FR_SHARE_FIRST_ROUND && share_first && g >= 2 && nsteps >= 2 && nclusters >= g) c0 = (g + 1) / 2;   // clusters of the shared round
     const int n = nclusters - c0;
     nfullw = n / g;
     rem = n - nfullw * g;
+    if (pool && nsteps >= 2 && nfullw >= 1) {
+      // the last, partial round -- plus a full one when it is short -- is left to the pool (ItemWalk)
+      if (rem < g / 2 && nfullw >= 2) --nfullw;
+      pool0 = c0 + nfullw * g;
+      npool = nclusters - pool0;
+      rem = 0;
+    }
     split = (rem > 0) ? min(nsteps, g / rem) : 1;
     if (split < 1) split = 1;
     tile = step0 = step1 = 0;
@@ -392,6 +404,78 @@ struct TileWalk {
   }
 };
 
+// The CTA's sequence of work items (cluster, epilogue steps): the static schedule (TileWalk), then -- single-tile launches of
+// the raster flavour -- items from a POOL shared by all CTAs of the launch.  Per-cluster raster times differ by +-16 % and
+// every CTA only sees three or four clusters, so with a purely static deal the slowest CTA ran ~10 us behind the median of
+// a 70 us kernel (tools/timeline.py).  The clusters of the last round are therefore cut into FR_POOL_PARTS step ranges
+// and handed out through a global counter (workspace, zeroed by the prep kernel): a CTA that is early takes more of them.
+// The producer warp draws (atomicAdd) and publishes the item in a shared-memory ring guarded by mbarriers; the MMA warp and
+// the epilogue warps read it there.  -1 ends the kernel.  The draw for the CTA's item number T waits until the rasterizing
+// warps have begun item T - FR_POOL_LOOKAHEAD (Barriers::raster_pos): left to the pipeline's own back-pressure (three stages,
+// two accumulator sets) the producers run two to three items ahead and empty the pool in a round-robin long before the
+// CTAs' raster times have diverged (measured: no gain); one item of lookahead is what the tile's stream and MMAs need.
+#ifndef FR_POOL_PARTS
+#define FR_POOL_PARTS 2
+#endif
+#ifndef FR_POOL_LOOKAHEAD
+#define FR_POOL_LOOKAHEAD 1
+#endif
+
+struct ItemWalk {
+  TileWalk tw;
+  Barriers* bars;
+  unsigned* counter;               // null: static schedule only
+  uint32_t d;                      // pool items seen so far
+  uint32_t nstatic;                // items of the static schedule seen so far
+  bool static_done;
+  int tile, step0, step1;
+  __device__ ItemWalk(int nclusters, int nsteps, bool share_first, unsigned* counter_, Barriers* bars_)
+      : tw(nclusters, nsteps, share_first, counter_ != nullptr), bars(bars_), counter(tw.npool > 0 ? counter_ : nullptr), d(0),
+        nstatic(0), static_done(false), tile(0), step0(0), step1(0) {}
+  __device__ bool take_static() {
+    if (!static_done && tw.next()) {
+      tile = tw.tile, step0 = tw.step0, step1 = tw.step1;
+      ++nstatic;
+      return true;
+    }
+    static_done = true;
+    return false;
+  }
+  __device__ int parts() const { return min(FR_POOL_PARTS, tw.nsteps); }
+  __device__ int nitems() const { return tw.npool * parts(); }
+  __device__ bool decode(int item) {
+    if (item < 0) return false;
+    const int p = parts(), part = item % p;
+    tile = tw.pool0 + item / p;
+    step0 = part * tw.nsteps / p;
+    step1 = (part + 1) * tw.nsteps / p;
+    return true;
+  }
+  // producer (one thread): draws from the pool and publishes
+  __device__ bool next_producer() {
+    if (take_static()) return true;
+    if (counter == nullptr) return false;
+    if (d == 0) pdl_wait();                                      // the counter was zeroed by the prep kernel
+    const uint32_t need = nstatic + d + 1u > (uint32_t)FR_POOL_LOOKAHEAD ? nstatic + d + 1u - (uint32_t)FR_POOL_LOOKAHEAD : 0u;
+    while (*reinterpret_cast<volatile uint32_t*>(&bars->raster_pos) < need) __nanosleep(64);
+    const unsigned idx = atomicAdd(counter, 1u);
+    const int item = idx < (unsigned)nitems() ? (int)idx : -1;
+    bars->item_ring[d & 7u] = item;
+    mbar_arrive(&bars->item_full[d & 7u]);                        // (release: the ring entry is visible to the waiters)
+    ++d;
+    return decode(item);
+  }
+  // MMA warp / epilogue warps (every thread)
+  __device__ bool next_consumer() {
+    if (take_static()) return true;
+    if (counter == nullptr) return false;
+    mbar_wait(&bars->item_full[d & 7u], (d >> 3) & 1u);
+    const int item = *reinterpret_cast<volatile int32_t*>(&bars->item_ring[d & 7u]);
+    ++d;
+    return decode(item);
+  }
+};
+
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float* v) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
@@ -403,6 +487,7 @@ struct RasterTarget {
   const unsigned char* table;        // mesh table blob (device)
   unsigned long long* keys;          // visibility keys [B][height*width], cleared by the prep kernel
   int width, height;
+  unsigned* pool_counter;            // ItemWalk's pool counter (zeroed by the prep kernel with the keys), or null
 };
 
 // tiles: fp16 operand tiles; cluster_vert: the vertex (id | owner flag, -1 = none) behind every row of every tile -- the mesh
@@ -425,6 +510,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
   const size_t tile_bytes = (size_t)3 * nch16 * kChunkBytes;
   constexpr int kStepFaces = C::kStepFaces;                        // faces the epilogue warps read per step (raster: one stage)
   const int nsteps = (min(kN, batch - b0) + kStepFaces - 1) / kStepFaces;
+  unsigned* const pool_counter = (kRaster && gridDim.y == 1) ? target.pool_counter : nullptr;   // (ItemWalk)
   if (threadIdx.x == 0) { FR_TL(0); FR_TLG(15); }
   FR_MARK_MIN(2);
 
@@ -440,6 +526,8 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     }
     mbar_init(&bars->b_full, 1);
     for (int i = 0; i < 4; ++i) bars->oct_taken[i] = 0u;
+    for (int i = 0; i < 8; ++i) mbar_init(&bars->item_full[i], 1);
+    bars->raster_pos = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kProducerWarp) {
@@ -477,7 +565,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
 #if FR_BASIS_EVICT_FIRST
       const uint64_t stream_policy = tc::l2_evict_first_policy();
 #endif
-      for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next();) {
+      for (ItemWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1, pool_counter, bars); tw.next_producer();) {
         const unsigned char* src = tiles + (size_t)tw.tile * tile_bytes;
         for (int sg = 0; sg < nch16; ++sg, ++it) {             // nch16 stages of 3 chunks per tile
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
@@ -502,7 +590,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
     const uint64_t db1 = tc::make_smem_desc(smem_u32(smem + L.b1), 128u, L.sbo);
     const uint64_t da0 = tc::make_smem_desc(smem_u32(smem + L.raw), 2048u, 128u);   // same descriptor format for A
     uint32_t it = 0, tcount = 0;
-    for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next(); ++tcount) {
+    for (ItemWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1, pool_counter, bars); tw.next_consumer(); ++tcount) {
       const uint32_t dbuf = tcount % kDBufs;
       mbar_wait(&bars->d_empty[dbuf], ((tcount / kDBufs) & 1u) ^ 1u);          // epilogue has drained this accumulator set
       tc_fence_after();
@@ -551,7 +639,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       const int wq = warp >> 2;                                   // position within the quarter: faces wq * 16 ... of a step
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // the epilogue warps only
       uint32_t tcount = 0;
-      for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next(); ++tcount) {
+      for (ItemWalk tw(nclusters, nsteps, false, nullptr, bars); tw.next_consumer(); ++tcount) {
         const int tile = tw.tile;
         const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
         // vertex of this row, and whether this tile is the one that writes it
@@ -606,7 +694,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
       const int npix = target.width * target.height;
       asm volatile("bar.sync 4, %0;" ::"n"(kEpiWarps * 32) : "memory");   // poses in place (all epilogue warps)
       uint32_t tcount = 0;
-      for (TileWalk tw(nclusters, nsteps, kRaster && gridDim.y == 1); tw.next(); ++tcount) {
+      for (ItemWalk tw(nclusters, nsteps, gridDim.y == 1, pool_counter, bars); tw.next_consumer(); ++tcount) {
         const int tile = tw.tile;
         const uint32_t dbuf = tcount % kDBufs, dph = (tcount / kDBufs) & 1u;
         // Octets of this tile: every group starts with one static octet (rotated from tile to tile), the rest are handed out
@@ -622,6 +710,7 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         // must not run ahead and arrive for a later tile in this one's phase
         mbar_wait(&bars->d_full[dbuf], dph);
         if (threadIdx.x == 0 && tcount == 0) FR_TL(8);
+        if (gtid == 0 && pool_counter != nullptr) atomicMax(&bars->raster_pos, tcount + 1u);
         if (first >= tw.step1) {
           if (gtid == 0) bars->oct_taken[(tcount + 2u) & 3u] = 0u;
           __syncwarp();
