@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(kRasterThreads)
 raster_resolve_depth_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ depth, float* __restrict__ tri_ind,
                             unsigned long long n) {
   FR_MARK_MIN(6);
+  pdl_trigger();   // the next call's prep kernel (a dependent launch that waits for this grid before it touches anything) may become resident
   pdl_wait();      // every atomicMax of the visibility pass has landed
   FR_MARK_MIN(4);
   const unsigned long long i = (unsigned long long)blockIdx.x * kRasterThreads + threadIdx.x;

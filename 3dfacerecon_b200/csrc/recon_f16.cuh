@@ -240,6 +240,11 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
   __shared__ float s_pose[kPoseStride];
   __shared__ double s_sc[6];
   pdl_trigger();                                   // the reconstruction kernel may become resident (it waits before reading our output)
+  // This grid is itself launched as a programmatic dependent of whatever precedes it in the stream -- in a serving loop the
+  // previous call's resolve kernel, which triggers at its start: then these blocks and, behind them, the reconstruction
+  // kernel's CTAs (TMEM allocation, first basis stages: nothing that depends on the stream's past) are already resident
+  // when that kernel ends.  Everything below reads or overwrites what earlier work in the stream produced or still uses.
+  pdl_wait();
   FR_MARK_MIN(0);
   const int tid = threadIdx.x;
   // fused call: the CTAs behind the (padded) faces only clear the visibility keys for the rasterizer that follows, 16 bytes
@@ -840,9 +845,9 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
   const int bpad = batch_padded(batch);
   const int dparam = FR_NDIM_POSE + g.ks + g.ke;
   const int nclear = clear_keys ? 2 * nsm : 0;
-  f16::recon_prep_f16_kernel<<<bpad + nclear, 256, 0, st>>>(params, inv_scale, dparam, batch, g.ks, g.ke, g.kpad16, flags, im_size,
-                                                           static_cast<unsigned char*>(bsplit), pose16, bpad, clear_keys,
-                                                           clear_bytes / 16);   // normal launch: waits for everything before
+  FR_CUDA(launch_pdl(f16::recon_prep_f16_kernel, dim3(bpad + nclear), dim3(256), 0, st, pdl_enabled(), params, inv_scale, dparam, batch,
+                     g.ks, g.ke, g.kpad16, flags, im_size, static_cast<unsigned char*>(bsplit), pose16, bpad, clear_keys,
+                     clear_bytes / 16));   // (waits for everything before it in the stream at its first instruction)
   FR_LAUNCHED("recon_prep_f16_kernel");
   const int nbt = ceil_div(batch, f16::kN);
   const int ntiles_f = target != nullptr ? g.nclusters : g.ntiles;             // row tiles of the section this flavour streams
