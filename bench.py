@@ -578,8 +578,9 @@ def run_ours(args):
             ms_b = a.elapsed_time(b) / nrun
             b2b["streams_%d" % S] = {"ms_per_call": ms_b, "faces_per_s": B / (ms_b * 1e-3)}
             del calls, streams
-        b2b["note"] = ("independent batch-64 calls back to back, no L2 flush between them (the 184 MB basis stream exceeds the L2); "
-                       "not the headline: `value` times isolated calls with a flushed L2")
+        b2b["note"] = ("independent batch-64 calls back to back on S streams (own workspace / outputs per stream), no L2 flush: "
+                       "streams_1 repeats the headline's methodology on a side stream; with several calls in flight the next call's "
+                       "CTAs fill the SMs the previous call's slowest CTAs leave idle")
         extras["back_to_back_b64"] = b2b
 
         # the records pipeline (a basis packed without FR_CLUSTER_TILES): reconstruction kernel writing 16-byte vertex
