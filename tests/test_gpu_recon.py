@@ -149,13 +149,25 @@ def test_session_host_buffers_match_tensor_path(bfm):
     sess.close()
 
 
-@pytest.mark.parametrize("B,tiles", [(3, False), (20, False), (3, True), (20, True), (70, True)])
-def test_fused_call_matches_separate_calls(bfm, B, tiles):
+@pytest.fixture(scope="module")
+def mid_model():
+    """~31 000 vertices: ~300 clusters on 148 SMs -- a shared first round, ONE full round and a pool of ~80 clusters (the
+    BFM-sized model has two full rounds and a pool of 140)."""
+    return fr("synth").make_synthetic_model(grid=(150, 208), ndim_shape=40, ndim_exp=10, seed=5, jitter=0.2)
+
+
+@pytest.mark.parametrize("B,tiles,which", [(3, False, "bfm"), (20, False, "bfm"), (3, True, "bfm"), (20, True, "bfm"), (70, True, "bfm"),
+                                           (9, True, "bfm"), (33, True, "bfm"), (64, True, "bfm"), (64, True, "mid"), (41, True, "mid")])
+def test_fused_call_matches_separate_calls(bfm, mid_model, B, tiles, which):
     """fr_recon_render_forward == fr_recon_project_forward + fr_render_depth_forward bit for bit, with and without the vertex
     tensor: FFMA path (B = 3) and tcgen05 path writing the rasterizer's records (default), and the FR_CLUSTER_TILES
-    flavour whose tcgen05 epilogue rasterizes each cluster from shared memory (B = 20, 70)."""
+    flavour whose tcgen05 epilogue rasterizes each cluster from shared memory: two batch tiles with the static schedule
+    (B = 70), one batch tile with 2 / 3 / 5 / 6 / 8 octets per cluster -- the schedule with dynamic octets and the dynamic
+    pool of half-clusters (ItemWalk) -- on two pool geometries."""
     lib, check = fr("_lib").lib(), fr("_lib").check
-    p = fr("synth").sample_params_constrained(B, seed=60 + B)
+    bfm = bfm if which == "bfm" else mid_model
+    S = 200
+    p = fr("synth").sample_params_constrained(B, bfm["ndim_shape"], bfm["ndim_exp"], S, seed=60 + B)
     dm, vp = _gpu_vertices(bfm, p, 200, cluster_tiles=tiles)
     image = torch.empty((B, 200, 200, 3), device=DEV)
     want = fr("rendering_layer.ops").render_depth(torch.from_numpy(vp).to(DEV), dm.tri, dm.vertex_code.unsqueeze(0).expand(B, -1, -1), image)
