@@ -13,15 +13,17 @@
 //   MMA issuer  1 warp   whole warp converged, one elected lane: per chunk  D += Phi.b0 + Plo.b0 + Phi.b1
 //                        (tcgen05.mma kind::f16, M128 N64 K16, BOTH operands from shared memory); a tcgen05.commit per
 //                        stage hands the shared-memory stage back to the producer when its MMAs have retired
-//   epilogue    8 / 16 warps: tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices),
+//   epilogue    8 / 24 warps: tcgen05.ld of the three 128x64 accumulators (x, y, z of the same vertices),
 //                        (2^-t f.R).v + t, y flip; double-buffered against the next tile's MMAs.  Two flavours:
 //       planar  (8 warps)   coalesced stores of vertex_proj [B,3,N]                  (fr_recon_project_forward)
-//       raster  (28 warps)  the row tile is a CLUSTER of the mesh table (mesh_table.h): the projected vertices go, 16 faces
-//                           at a time, to the shared-memory tile of the tile rasterizer (raster_tile.cuh) and the same
-//                           warps cull and draw the cluster's triangles from there while the tensor pipe works on the
-//                           next cluster -- the vertices of the fused params -> depth-map call never touch global
-//                           memory, and the rasterizer's instruction stream fills the issue slots the HBM-bound basis
-//                           stream leaves idle   (fr_recon_render_forward with FR_CLUSTER_TILES)
+//       raster  (24 warps)  the row tile is a CLUSTER of the mesh table (mesh_table.h): three independent groups of 8 warps
+//                           take the projected vertices, 8 faces (an octet) at a time, into their shared-memory tiles of the
+//                           tile rasterizer (raster_tile.cuh) and cull and draw the cluster's triangles from there while
+//                           the tensor pipe works on the next cluster -- the vertices of the fused params -> depth-map
+//                           call never touch global memory.  At 64 faces the rasterization, not the basis stream, bounds
+//                           the kernel (12 us per cluster and SM against 7.5 us for its tile), so the work is dealt
+//                           dynamically: octets within a CTA (Barriers::oct_taken), the clusters of the last round between
+//                           the CTAs (ItemWalk)                           (fr_recon_render_forward with FR_CLUSTER_TILES)
 // Measured on B200 (tools/mma_bench3.cu): an SS-form M128 N64 MMA takes 48 cycles (operand reads at 128 B/clk), K8 tf32
 // and K16 f16 alike, so a 16-k chunk costs 144 tensor cycles here against 192 for the 3xTF32 TS-form kernel
 // (tools/experiments/recon_tc_3xtf32.cuh) -- and that kernel also needs 8 converter warps and a TMEM operand ring only 4 chunks deep.
