@@ -34,6 +34,7 @@
 
 #include "raster_tile.cuh"
 #include "recon.cuh"
+#include "schedule.h"
 #include "tcgen05_common.cuh"
 
 #ifndef FR_BASIS_EVICT_FIRST
@@ -346,71 +347,6 @@ __device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Tile schedule of one CTA: the clusters are dealt round-robin to the gridDim.x CTAs of a batch tile.  When the last round
-// is short (nclusters % gridDim.x != 0) its clusters are SPLIT by epilogue steps over several CTAs, each of which repeats the
-// cluster's (cheap) tensor-core pass but projects / rasterizes only its share of the faces: the per-SM epilogue work, which
-// bounds the raster flavour, then ends together instead of leaving most SMs idle for a whole cluster time.
-// share_first (raster flavour): the FIRST round is shared by PAIRS of CTAs -- both stream cluster j / 2 (the second reader
-// hits the lines the first one is fetching: half the HBM bytes) and each rasterizes half of its steps.  Nothing can be
-// rasterized before a CTA's first cluster is complete, and with every SM pulling its own 360 KB that takes ~11 us of a
-// 90 us step; halving the bytes of the first round halves that wait, and the half-size first job is still long enough to
-// cover the stream of the next cluster.  Measured: 91.3 -> 89.0 us per step at 64 faces; with several batch tiles per launch the
-// wait is amortised and the pairing only costs balance (4096 faces: 4.08 -> 4.14 ms), so it is used for single-tile launches only.
-#ifndef FR_SHARE_FIRST_ROUND
-#define FR_SHARE_FIRST_ROUND 1
-#endif
-struct TileWalk {
-  int tile, step0, step1;          // current cluster and its epilogue steps [step0, step1)
-  int g, j, nfullw, rem, split, nsteps, k, c0;
-  int pool0, npool;                // dynamic pool: clusters [pool0, pool0 + npool) are not part of the static schedule
-  __device__ TileWalk(int nclusters, int nsteps_, bool share_first = false, bool pool = false)
-      : g((int)gridDim.x), j((int)blockIdx.x), nsteps(nsteps_), k(-1), c0(0), pool0(nclusters), npool(0) {
-    if (FR_SHARE_FIRST_ROUND && share_first && g >= 2 && nsteps >= 2 && nclusters >= g) c0 = (g + 1) / 2;   // clusters of the shared round
-    const int n = nclusters - c0;
-    nfullw = n / g;
-    rem = n - nfullw * g;
-    if (pool && nsteps >= 2 && nfullw >= 1) {
-      // the last, partial round -- plus a full one when it is short -- is left to the pool (ItemWalk)
-      if (rem < g / 2 && nfullw >= 2) --nfullw;
-      pool0 = c0 + nfullw * g;
-      npool = nclusters - pool0;
-      rem = 0;
-    }
-    split = (rem > 0) ? min(nsteps, g / rem) : 1;
-    if (split < 1) split = 1;
-    tile = step0 = step1 = 0;
-  }
-  __device__ bool next() {
-    ++k;
-    int kk = k;
-    if (c0 > 0) {
-      if (k == 0) {                                  // shared round: CTAs 2 t and 2 t + 1 take the two halves of cluster t
-        tile = j >> 1;
-        const bool alone = (j == g - 1) && (g & 1);  // odd CTA count: the last CTA has its cluster to itself
-        const int half = nsteps >> 1;
-        step0 = (alone || !(j & 1)) ? 0 : half;
-        step1 = (alone || (j & 1)) ? nsteps : half;
-        return true;
-      }
-      kk = k - 1;
-    }
-    if (kk < nfullw) {
-      tile = c0 + j + kk * g;
-      step0 = 0;
-      step1 = nsteps;
-      return true;
-    }
-    if (kk == nfullw && j < rem * split) {
-      tile = c0 + nfullw * g + j / split;
-      const int part = j - (j / split) * split;
-      step0 = part * nsteps / split;
-      step1 = (part + 1) * nsteps / split;
-      return true;
-    }
-    return false;
-  }
-};
-
 // The CTA's sequence of work items (cluster, epilogue steps): the static schedule (TileWalk), then -- single-tile launches of
 // the raster flavour -- items from a POOL shared by all CTAs of the launch.  Per-cluster raster times differ by +-16 % and
 // every CTA only sees three or four clusters, so with a purely static deal the slowest CTA ran ~10 us behind the median of
@@ -421,9 +357,6 @@ struct TileWalk {
 // warps have begun item T - FR_POOL_LOOKAHEAD (Barriers::raster_pos): left to the pipeline's own back-pressure (three stages,
 // two accumulator sets) the producers run two to three items ahead and empty the pool in a round-robin long before the
 // CTAs' raster times have diverged (measured: no gain); one item of lookahead is what the tile's stream and MMAs need.
-#ifndef FR_POOL_PARTS
-#define FR_POOL_PARTS 2
-#endif
 #ifndef FR_POOL_LOOKAHEAD
 #define FR_POOL_LOOKAHEAD 1
 #endif
@@ -437,7 +370,7 @@ struct ItemWalk {
   bool static_done;
   int tile, step0, step1;
   __device__ ItemWalk(int nclusters, int nsteps, bool share_first, unsigned* counter_, Barriers* bars_)
-      : tw(nclusters, nsteps, share_first, counter_ != nullptr), bars(bars_), counter(tw.npool > 0 ? counter_ : nullptr), d(0),
+      : tw(nclusters, nsteps, share_first, counter_ != nullptr, (int)gridDim.x, (int)blockIdx.x), bars(bars_), counter(tw.npool > 0 ? counter_ : nullptr), d(0),
         nstatic(0), static_done(false), tile(0), step0(0), step1(0) {}
   __device__ bool take_static() {
     if (!static_done && tw.next()) {
@@ -448,14 +381,9 @@ struct ItemWalk {
     static_done = true;
     return false;
   }
-  __device__ int parts() const { return min(FR_POOL_PARTS, tw.nsteps); }
-  __device__ int nitems() const { return tw.npool * parts(); }
   __device__ bool decode(int item) {
     if (item < 0) return false;
-    const int p = parts(), part = item % p;
-    tile = tw.pool0 + item / p;
-    step0 = part * tw.nsteps / p;
-    step1 = (part + 1) * tw.nsteps / p;
+    pool_decode(tw, item, &tile, &step0, &step1);
     return true;
   }
   // producer (one thread): draws from the pool and publishes
@@ -466,7 +394,7 @@ struct ItemWalk {
     const uint32_t need = nstatic + d + 1u > (uint32_t)FR_POOL_LOOKAHEAD ? nstatic + d + 1u - (uint32_t)FR_POOL_LOOKAHEAD : 0u;
     while (*reinterpret_cast<volatile uint32_t*>(&bars->raster_pos) < need) __nanosleep(64);
     const unsigned idx = atomicAdd(counter, 1u);
-    const int item = idx < (unsigned)nitems() ? (int)idx : -1;
+    const int item = idx < (unsigned)pool_items(tw) ? (int)idx : -1;
     bars->item_ring[d & 7u] = item;
     mbar_arrive(&bars->item_full[d & 7u]);                        // (release: the ring entry is visible to the waiters)
     ++d;

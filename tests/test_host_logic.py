@@ -230,3 +230,37 @@ def test_read_3dmm_model_from_mat_files(tmp_path):
     assert parser.tri_is_one_based(m["tri"], n) and not parser.tri_is_one_based(m["tri"] - 1, n)
     with pytest.raises(FileNotFoundError):
         parser.read_3dmm_model(str(tmp_path / "missing"))
+
+
+def test_forward_kernel_schedule_covers_every_cluster_step_once():
+    """csrc/schedule.h on the host: for every launch geometry (clusters, CTAs per batch tile, epilogue steps, pair-shared first
+    round, dynamic pool) the static walks of all CTAs plus the pool items visit every (cluster, step) exactly once; the static
+    load is balanced to within two clusters; pool items never reach into the static part."""
+    import ctypes
+    import subprocess
+    src = os.path.join(ROOT, "tests", "host_emul", "schedule_emul.cc")
+    so = os.path.join(ROOT, "tests", "host_emul", "libschedule_emul.so")
+    hdr = os.path.join(ROOT, "3dfacerecon_b200", "csrc", "schedule.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
+    lib = ctypes.CDLL(so)
+    lib.fr_emul_schedule_cover.restype = ctypes.c_int
+    stats = (ctypes.c_int * 4)()
+    seen_pool = 0
+    for nclusters in (1, 2, 3, 7, 74, 75, 147, 148, 149, 160, 195, 221, 222, 223, 296, 304, 370, 371, 416, 510, 511, 998, 2000):
+        for g in (1, 2, 3, 9, 37, 74, 132, 147, 148):
+            if g > nclusters:
+                continue                                               # the launcher never uses more CTAs than row tiles
+            for nsteps in (1, 2, 3, 5, 8):
+                for share in (0, 1):
+                    for pool in (0, 1):
+                        rc = lib.fr_emul_schedule_cover(nclusters, g, nsteps, share, pool, stats)
+                        assert rc == 0, (rc, nclusters, g, nsteps, share, pool)
+                        lo, hi, npool, nitems = list(stats)
+                        assert hi - lo <= 2 * nsteps, (nclusters, g, nsteps, share, pool, lo, hi)
+                        if pool and nsteps >= 2 and npool:
+                            seen_pool += 1
+                            assert nitems == npool * min(2, nsteps)
+    assert seen_pool > 100
+    # the benchmark's geometry: 510 clusters on 148 CTAs, 8 octets -> 74 shared + 2 x 148 static + a pool of 140 clusters in halves
+    assert lib.fr_emul_schedule_cover(510, 148, 8, 1, 1, stats) == 0 and list(stats)[2:] == [140, 280]
