@@ -319,6 +319,10 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
     }
     pose16[(size_t)b * kPose16Stride + tid] = v;
   }
+  // the operands written above are read by the next kernel's bulk-copy engine (async proxy) behind a programmatic dependency
+  // wait instead of an ordinary kernel boundary: order this thread's generic-proxy stores against that proxy on the writer's
+  // side as well (the reader fences after its wait)
+  asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- forward
