@@ -709,8 +709,10 @@ def run_ours(args):
                              how="device time between the CUDA events the library records around its kernels inside one real fused "
                                  "call (stage_events), L2 flushed before the call; bytes = SURVEY 8(d) bytes_fwd(B) minus the resolve "
                                  "pass's outputs (basis + mean + params + tri read, projected vertices written and read once)",
-                             limiter="instruction issue of the rasterizer half (DESIGN.md 4): ~36 M warp instructions per step, 24 "
-                                     "rasterizing warps per SM at ~55 % issue utilisation; the basis stream (200 MB) would take ~46 us",
+                             limiter="instruction issue of the rasterizer half (DESIGN.md 6): ~39 M warp instructions per step, 24 "
+                                     "rasterizing warps per SM at ~56 % issue utilisation -- 12 us of projection / cull / draw per "
+                                     "cluster and SM against 7.5 us for the cluster's basis tile; the 200 MB stream alone would take "
+                                     "~31 us at the measured peak",
                              resolve_kernel=roof(2 * out_bytes, ms_res),
                              whole_step={"back_to_back": roof(rb + nb, ms_b2b_max),
                                          "survey_8d_bytes": roof(rb + nb, ms_full_max),
