@@ -11,13 +11,13 @@ Public surface (mirrors the reference's modules on this path):
 * ``fr.FaceRecNet(...).vertices_transform / rendering_layer / depth_rendering_layer / set_constraints``
                                                            <- ``nets/network.py:140-218, 300-308``
 * ``fr.read_3dmm_model(path)`` / ``fr.synthetic_3dmm_model()``  <- ``utils/parser_3dmm.py:36-61``
-* ``fr.DeviceModel``, ``fr.recon_project``, ``fr.Session`` (host-buffer C-ABI session), ``fr.shard_batch``
+* ``fr.DeviceModel``, ``fr.recon_project``, ``fr.recon_render_depth``, ``fr.Session`` (host-buffer C-ABI session), ``fr.shard_batch``
 """
 from . import _lib  # noqa: F401
 from .utils.parser_3dmm import read_3dmm_model, synthetic_3dmm_model  # noqa: F401
 from .sharding import shard_batch  # noqa: F401
 
-__all__ = ["render_depth", "render_depth_grad", "FaceRecNet", "DeviceModel", "recon_project", "Session", "shard_batch",
+__all__ = ["render_depth", "render_depth_grad", "FaceRecNet", "DeviceModel", "recon_project", "recon_render_depth", "Session", "shard_batch",
            "read_3dmm_model", "synthetic_3dmm_model", "library_path"]
 
 
@@ -31,7 +31,7 @@ def __getattr__(name):
     if name in ("render_depth", "render_depth_grad"):
         from .rendering_layer import ops
         return getattr(ops, name)
-    if name in ("FaceRecNet", "recon_project"):
+    if name in ("FaceRecNet", "recon_project", "recon_render_depth"):
         from .nets import network
         return getattr(network, name)
     if name == "DeviceModel":

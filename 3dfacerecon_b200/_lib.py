@@ -50,6 +50,8 @@ SIGNATURES = {
     "fr_rendering_layer_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fr_pipeline_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "fr_recon_render_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _u, _vp, _sz, _vp, _vp]),
+    "fr_recon_render_forward_all": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _u, _vp, _sz,
+                                         _vp]),
     "fr_session_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u, _i, ctypes.POINTER(_vp)]),
     "fr_session_destroy": (None, [_vp]),
     "fr_session_forward": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),

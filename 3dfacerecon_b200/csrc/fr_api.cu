@@ -256,13 +256,16 @@ int launch_keys(const float4* rec, const float* tri, const fr_mesh_table* mesh, 
 }
 
 // fr_render_depth_forward: pack pass (vertex tensor -> 16-byte records, clears the keys), visibility pass, resolve pass.
-// With records_ready the workspace already holds this batch's vertex records and cleared visibility keys (written by the
-// fused call's reconstruction kernels); `vertex` may then be null unless normals or texture are requested.
+// `ready`: what the workspace already holds for this batch -- kNothingReady; kRecordsReady: vertex records and cleared
+// visibility keys (written by the fused call's reconstruction kernels); kKeysReady: records AND final visibility keys (the
+// reconstruction kernel rasterized in its epilogue).  `vertex` may be null with records unless normals or texture are requested.
+enum { kNothingReady = 0, kRecordsReady = 1, kKeysReady = 2 };
 int render_depth_forward_impl(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
                               float* depth, float* texture_image, float* normal, float* tri_ind, int batch, int nver,
                               int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
-                              void* stream, bool records_ready, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false},
+                              void* stream, int ready, LayerOut layer = LayerOut{nullptr, nullptr, nullptr, false},
                               cudaEvent_t after_keys = nullptr) {
+  const bool records_ready = ready >= kRecordsReady;
   if (int rc = check_render_dims(batch, nver, ntri, height, width)) return rc;
   if (int rc = check_mesh(mesh, nver, ntri)) return rc;
   if (batch == 0) return FR_OK;
@@ -284,7 +287,8 @@ int render_depth_forward_impl(const float* vertex, const float* tri, const float
           vertex, rec, keys, mesh_vert_rank(mesh), nver, npix, width, height);
       FR_LAUNCHED("raster_pack_kernel");
     }
-    if (int rc = launch_keys(rec, tri, mesh, keys, batch, nver, ntri, height, width, pdl, records_ready, st)) return rc;
+    if (ready < kKeysReady)
+      if (int rc = launch_keys(rec, tri, mesh, keys, batch, nver, ntri, height, width, pdl, records_ready, st)) return rc;
     if (after_keys != nullptr) FR_CUDA(cudaEventRecord(after_keys, st));
   } else if (!records_ready) {
     FR_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)batch * npix, st));
@@ -526,7 +530,8 @@ size_t fr_render_workspace_bytes(int batch, int nver, int height, int width) {
   if (batch <= 0 || nver <= 0 || height <= 0 || width <= 0) return 0;
   return key_bytes(batch, height, width) +                                   // visibility keys
          align_up(sizeof(float4) * (size_t)batch * nver, kAlign) +           // vertex records
-         align_up(sizeof(float4) * (size_t)nver, kAlign);                    // a shared texture repacked by vertex rank
+         align_up(sizeof(float4) * (size_t)nver, kAlign) +                   // a shared texture repacked by vertex rank
+         kAlign;                                                             // schedule counters of the fused forward kernel
 }
 
 int fr_render_depth_forward(const float* vertex, const float* tri, const float* texture, long long texture_batch_stride,
@@ -534,7 +539,7 @@ int fr_render_depth_forward(const float* vertex, const float* tri, const float* 
                             int ntri, int height, int width, const fr_mesh_table* mesh, void* workspace, size_t workspace_bytes,
                             void* stream) {
   return render_depth_forward_impl(vertex, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver,
-                                   ntri, height, width, mesh, workspace, workspace_bytes, stream, false);
+                                   ntri, height, width, mesh, workspace, workspace_bytes, stream, kNothingReady);
 }
 
 int fr_render_depth_backward(const float* depth_grad, const float* tri, const float* tri_ind, float* vertex_grad,
@@ -563,7 +568,7 @@ int fr_rendering_layer_forward(const float* vertex, const float* tri, const floa
   FR_REQUIRE(batch <= 0 || (pncc && normalimg && maskimg && depthimg && texture), "null pointer argument");
   const LayerOut layer = {maskimg, im_gray, raw_depth, true};
   return render_depth_forward_impl(vertex, tri, texture, texture_batch_stride, depthimg, pncc, normalimg, tri_ind, batch, nver, ntri,
-                                   height, width, mesh, workspace, workspace_bytes, stream, false, layer);
+                                   height, width, mesh, workspace, workspace_bytes, stream, kNothingReady, layer);
 }
 
 int fr_rendering_layer_backward(const float* depthimg_grad, const float* maskimg_grad, const float* im_gray, const float* raw_depth,
@@ -599,21 +604,27 @@ size_t fr_pipeline_workspace_bytes(int batch, int nver, int ndim_shape, int ndim
   return fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp) + fr_render_workspace_bytes(batch, nver, height, width);
 }
 
-int fr_recon_render_forward(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
-                            float* vertex_proj, float* depth, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
-                            int ndim_exp, int height, int width, float im_size, unsigned flags, void* workspace,
-                            size_t workspace_bytes, void* stream, void* const* stage_events) {
+// fr_recon_render_forward / fr_recon_render_forward_all: texture_image / normal null = depth + tri_ind only.
+static int recon_render_forward_impl(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
+                                     const float* texture, long long texture_batch_stride, float* vertex_proj, float* depth,
+                                     float* texture_image, float* normal, float* tri_ind, int batch, int nver, int ntri,
+                                     int ndim_shape, int ndim_exp, int height, int width, float im_size, unsigned flags,
+                                     void* workspace, size_t workspace_bytes, void* stream, void* const* stage_events) {
   if (int rc = check_model_dims(batch, nver, ndim_shape, ndim_exp)) return rc;
   if (int rc = check_render_dims(batch, nver, ntri, height, width)) return rc;
   if (int rc = check_mesh(mesh, nver, ntri)) return rc;
   if (batch == 0) return FR_OK;
   FR_REQUIRE(params && packed && (tri || ntri == 0) && depth && tri_ind, "null pointer argument");
+  const bool all = texture_image != nullptr || normal != nullptr;
+  FR_REQUIRE(!all || vertex_proj != nullptr, "normals / texture need the vertex_proj output");
+  FR_REQUIRE(texture_image == nullptr || texture != nullptr, "texture_image requested without a texture");
   const size_t rb = fr_recon_workspace_bytes(batch, nver, ndim_shape, ndim_exp);
   const size_t vb = fr_render_workspace_bytes(batch, nver, height, width);
   if (int rc = check_workspace(workspace, workspace_bytes, rb + vb)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* rws = static_cast<char*>(workspace) + rb;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(rws);
+  float4* rec = reinterpret_cast<float4*>(rws + key_bytes(batch, height, width));
   const size_t kbytes = sizeof(unsigned long long) * (size_t)batch * height * width;
   const bool timed = stage_events != nullptr && (stage_events[0] != nullptr || stage_events[1] != nullptr);
   auto record = [&](int i) -> cudaError_t {
@@ -621,40 +632,64 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
                                                                    : cudaSuccess;
   };
   if (fused_raster(mesh, flags, batch, nver, ndim_shape, ndim_exp, height, width)) {
-    // prep kernel (clears the keys) -> tensor-core reconstruction with the tile rasterizer in its epilogue -> resolve
-    // (the pool counter of the forward kernel's item schedule sits behind the keys, where the records pipeline keeps its
-    // vertex records, and is cleared with them)
-    const size_t kpad_bytes = key_bytes(batch, height, width);
+    // prep kernel (clears the keys and the schedule counters at the end of the render workspace) -> tensor-core
+    // reconstruction with the tile rasterizer in its epilogue -> resolve.  With normals / texture requested the epilogue also
+    // leaves the 16-byte vertex records (by rank) the resolve pass gathers them from: no repack pass, no visibility kernel.
     const f16::RasterTarget target = {static_cast<const unsigned char*>(mesh->dev), keys, width, height,
-                                      reinterpret_cast<unsigned*>(rws + kpad_bytes)};
-    const ReconOut out = {vertex_proj, nullptr, 0, 0, nullptr};
-    if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, keys, kpad_bytes + 16, batch, nver, ndim_shape, ndim_exp,
-                                            im_size, flags, workspace, rb, stream))
+                                      reinterpret_cast<unsigned*>(rws + vb - kAlign)};
+    const ReconOut out = {vertex_proj, all ? rec : nullptr, width, height, nullptr};
+    if (int rc = recon_project_forward_impl(params, packed, mesh, out, &target, keys, kbytes, batch, nver, ndim_shape, ndim_exp, im_size,
+                                            flags, workspace, rb, stream))
       return rc;
     FR_CUDA(record(0));
     FR_CUDA(record(1));
-    const LayerOut layer = {nullptr, nullptr, nullptr, false};
-    if (int rc = launch_resolve(keys, nullptr, nullptr, nullptr, nullptr, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height * width,
-                                layer, pdl_enabled() && !timed, st))
-      return rc;
+    if (all) {
+      if (int rc = render_depth_forward_impl(vertex_proj, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch,
+                                             nver, ntri, height, width, mesh, rws, vb, stream, kKeysReady))
+        return rc;
+    } else {
+      const LayerOut layer = {nullptr, nullptr, nullptr, false};
+      if (int rc = launch_resolve(keys, nullptr, nullptr, nullptr, nullptr, nullptr, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri,
+                                  height * width, layer, pdl_enabled() && !timed, st))
+        return rc;
+    }
     FR_CUDA(record(2));
     return FR_OK;
   }
   // The reconstruction kernels write the rasterizer's vertex records straight into the render workspace (same carve-up as
   // render_depth_forward_impl: keys first, records after) and clear its keys, so the repack pass over vertex_proj disappears;
   // vertex_proj itself is optional here.
-  const ReconOut out = {vertex_proj, reinterpret_cast<float4*>(rws + key_bytes(batch, height, width)), width, height,
-                        mesh_vert_rank(mesh)};
+  const ReconOut out = {vertex_proj, rec, width, height, mesh_vert_rank(mesh)};
   if (int rc = recon_project_forward_impl(params, packed, mesh, out, nullptr, keys, kbytes, batch, nver, ndim_shape, ndim_exp, im_size,
                                           flags, workspace, rb, stream))
     return rc;
   FR_CUDA(record(0));
   const cudaEvent_t after_keys = (stage_events != nullptr) ? static_cast<cudaEvent_t>(stage_events[1]) : nullptr;
-  if (int rc = render_depth_forward_impl(vertex_proj, tri, nullptr, 0, depth, nullptr, nullptr, tri_ind, batch, nver, ntri, height, width,
-                                         mesh, rws, vb, stream, true, LayerOut{nullptr, nullptr, nullptr, false}, after_keys))
+  if (int rc = render_depth_forward_impl(vertex_proj, tri, texture, texture_batch_stride, depth, texture_image, normal, tri_ind, batch, nver,
+                                         ntri, height, width, mesh, rws, vb, stream, kRecordsReady,
+                                         LayerOut{nullptr, nullptr, nullptr, false}, after_keys))
     return rc;
   FR_CUDA(record(2));
   return FR_OK;
+}
+
+int fr_recon_render_forward(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
+                            float* vertex_proj, float* depth, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
+                            int ndim_exp, int height, int width, float im_size, unsigned flags, void* workspace,
+                            size_t workspace_bytes, void* stream, void* const* stage_events) {
+  return recon_render_forward_impl(params, packed, tri, mesh, nullptr, 0, vertex_proj, depth, nullptr, nullptr, tri_ind, batch, nver, ntri,
+                                   ndim_shape, ndim_exp, height, width, im_size, flags, workspace, workspace_bytes, stream, stage_events);
+}
+
+int fr_recon_render_forward_all(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
+                                const float* texture, long long texture_batch_stride, float* vertex_proj, float* depth,
+                                float* texture_image, float* normal, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
+                                int ndim_exp, int height, int width, float im_size, unsigned flags, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  FR_REQUIRE(vertex_proj && texture_image && normal, "null pointer argument");
+  return recon_render_forward_impl(params, packed, tri, mesh, texture, texture_batch_stride, vertex_proj, depth, texture_image, normal,
+                                   tri_ind, batch, nver, ntri, ndim_shape, ndim_exp, height, width, im_size, flags, workspace,
+                                   workspace_bytes, stream, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ session

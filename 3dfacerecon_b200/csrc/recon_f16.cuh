@@ -238,7 +238,8 @@ pack_basis_f16_kernel(const float* __restrict__ mu, const float* __restrict__ pc
 __global__ void __launch_bounds__(256)
 recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict__ inv_scale, int dparam, int batch, int ks,
                       int ke, int kpad16, unsigned flags, float im_size, unsigned char* __restrict__ bsplit,
-                      float* __restrict__ pose16, int bpad, unsigned long long* __restrict__ keys, size_t key_vecs) {
+                      float* __restrict__ pose16, int bpad, unsigned long long* __restrict__ keys, size_t key_vecs,
+                      unsigned* __restrict__ counters) {
   __shared__ float red[8];
   __shared__ float s_pose[kPoseStride];
   __shared__ double s_sc[6];
@@ -261,6 +262,7 @@ recon_prep_f16_kernel(const float* __restrict__ params, const float* __restrict_
   }
   const int b = blockIdx.x;
   const bool live = b < batch;
+  if (b == 0 && tid < 4 && counters != nullptr) counters[tid] = 0u;     // the forward kernel's pool counter (ItemWalk)
   float cmax = 0.0f;
   for (int k = tid; k < kpad16; k += 256) {
     float v = 0.0f;
@@ -426,7 +428,7 @@ struct RasterTarget {
   const unsigned char* table;        // mesh table blob (device)
   unsigned long long* keys;          // visibility keys [B][height*width], cleared by the prep kernel
   int width, height;
-  unsigned* pool_counter;            // ItemWalk's pool counter (zeroed by the prep kernel with the keys), or null
+  unsigned* pool_counter;            // ItemWalk's pool counter (16 bytes, zeroed by the prep kernel), or null
 };
 
 // tiles: fp16 operand tiles; cluster_vert: the vertex (id | owner flag, -1 = none) behind every row of every tile -- the mesh
@@ -658,12 +660,13 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         }
         tc_fence_after();
         // vertex of this row and whether this cluster owns it (optional vertex_proj output only)
-        int n = 0;
+        int n = 0, rank = 0;
         bool owner = false;
-        if (out.planar != nullptr) {
+        if (out.planar != nullptr || out.rec != nullptr) {
           const int32_t raw = __ldg(cluster_vert + (size_t)tile * kTileVerts + v);
           n = (int)((uint32_t)raw & kVertIdMask);
           owner = raw >= 0 && ((uint32_t)raw & kVertOwner) != 0u;
+          if (out.rec != nullptr) rank = __ldg(tv.cluster_rank + (size_t)tile * kTileVerts + v);   // record index of this slot
         }
         // the cluster's triangle list: this thread's entry travels in registers until the group's tile is free
         const int tb = __ldg(tv.tri_begin + tile);
@@ -700,7 +703,11 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
               const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
               project_vertex(P, x[j], y[j], z[j], im_size, flags, &r[j].x, &r[j].y, &r[j].z);
               r[j].w = __uint_as_float(fr_snap_code(r[j].x, r[j].y, target.width, target.height));
-              if (owner && fh * kFPW + j < nlive) store_planar(out.planar, fb + fh * kFPW + j, nver, n, r[j].x, r[j].y, r[j].z);
+              if (owner && fh * kFPW + j < nlive) {
+                if (out.planar != nullptr) store_planar(out.planar, fb + fh * kFPW + j, nver, n, r[j].x, r[j].y, r[j].z);
+                // (optional: the 16-byte records the resolve pass gathers normals from -- the training path's all-outputs call)
+                if (out.rec != nullptr) out.rec[(size_t)(fb + fh * kFPW + j) * nver + rank] = r[j];
+              }
             }
           }
           asm volatile("bar.sync %0, %1;" ::"r"(gbar), "n"(kGT) : "memory");   // the group's previous draw is complete
@@ -781,7 +788,7 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
   const int nclear = clear_keys ? 2 * nsm : 0;
   FR_CUDA(launch_pdl(f16::recon_prep_f16_kernel, dim3(bpad + nclear), dim3(256), 0, st, pdl_enabled(), params, inv_scale, dparam, batch,
                      g.ks, g.ke, g.kpad16, flags, im_size, static_cast<unsigned char*>(bsplit), pose16, bpad, clear_keys,
-                     clear_bytes / 16));   // (waits for everything before it in the stream at its first instruction)
+                     clear_bytes / 16, target != nullptr ? target->pool_counter : static_cast<unsigned*>(nullptr)));   // (waits for everything before it in the stream at its first instruction)
   FR_LAUNCHED("recon_prep_f16_kernel");
   const int nbt = ceil_div(batch, f16::kN);
   const int ntiles_f = target != nullptr ? g.nclusters : g.ntiles;             // row tiles of the section this flavour streams

@@ -137,6 +137,73 @@ class _RenderingLayer(torch.autograd.Function):
         return vertex_grad, None, None, None, None, None, None
 
 
+class _ReconRenderDepth(torch.autograd.Function):
+    """params [B,d] -> (vertex_proj, depth, texture_image, normal, tri_ind) in ONE library call (``fr_recon_render_forward_all``):
+    ``vertices_transform`` followed by ``render_depth`` (``nets/network.py:300-308``) without the repack pass and -- with a
+    cluster-tile model -- without a separate visibility kernel.  Bit-identical to the two separate ops; gradients as they compose
+    (``fr_render_depth_backward`` into ``fr_recon_project_backward``; none for texture / normal, ``rendering_layer/ops.py:95``)."""
+
+    @staticmethod
+    def forward(ctx, params, model: DeviceModel, texture, height, width, im_size, flags):
+        if not params.is_cuda:
+            raise RuntimeError("params is on %s: there is no CPU path" % params.device)
+        if params.dim() != 2 or params.shape[1] != model.ndim:
+            raise ValueError("params must be [B, %d] (pose 7 | shape %d | expression %d)" % (model.ndim, model.ndim_shape, model.ndim_exp))
+        if params.device != model.device:
+            raise ValueError("params is on %s but the model lives on %s" % (params.device, model.device))
+        params = params.float().contiguous()
+        B, N, dev = int(params.shape[0]), model.nver, params.device
+        if texture.dim() not in (2, 3) or texture.shape[-2] != 3 or texture.shape[-1] != N or (texture.dim() == 3 and texture.shape[0] != B):
+            raise ValueError("colors must be [3,N] or [B,3,N] (got %s)" % (tuple(texture.shape),))
+        if texture.dim() == 2 or (texture.stride(0) == 0 and texture[0].is_contiguous()):
+            tex, tex_stride = (texture if texture.dim() == 2 else texture[0]).float().contiguous(), 0
+        else:
+            tex, tex_stride = texture.float().contiguous(), 3 * N
+        vertex = torch.empty((B, 3, N), dtype=torch.float32, device=dev)
+        new = lambda c: torch.empty((B, height, width, c), dtype=torch.float32, device=dev)
+        depth, teximg, normal, tri_ind = new(1), new(3), new(3), new(1)
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, lib().fr_pipeline_workspace_bytes(B, N, model.ndim_shape, model.ndim_exp, height, width))
+            check(lib().fr_recon_render_forward_all(params.data_ptr(), model.packed.data_ptr(), model.tri.data_ptr(), model.mesh.handle,
+                                                    tex.data_ptr(), tex_stride, vertex.data_ptr(), depth.data_ptr(), teximg.data_ptr(),
+                                                    normal.data_ptr(), tri_ind.data_ptr(), B, N, model.ntri, model.ndim_shape,
+                                                    model.ndim_exp, height, width, float(im_size), flags, ws.data_ptr(), ws.numel(),
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(params, tri_ind)
+        ctx.model, ctx.flags, ctx.im_size, ctx.hw = model, flags, float(im_size), (height, width)
+        ctx.mark_non_differentiable(teximg, normal, tri_ind)
+        return vertex, depth, teximg, normal, tri_ind
+
+    @staticmethod
+    def backward(ctx, g_vertex, g_depth, _g_tex, _g_normal, _g_tri):
+        params, tri_ind = ctx.saved_tensors
+        model, (H, W) = ctx.model, ctx.hw
+        B, N, dev = int(params.shape[0]), model.nver, params.device
+        vertex_grad = torch.empty((B, 3, N), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            sp = torch.cuda.current_stream(dev).cuda_stream
+            if g_depth is None:
+                vertex_grad.zero_()
+            else:
+                check(lib().fr_render_depth_backward(g_depth.float().contiguous().data_ptr(), model.tri.data_ptr(), tri_ind.data_ptr(),
+                                                     vertex_grad.data_ptr(), B, N, model.ntri, H, W, sp))
+            if g_vertex is not None:
+                vertex_grad += g_vertex.float()
+            dparams = torch.empty_like(params)
+            ws = _workspace(dev, lib().fr_recon_workspace_bytes(B, N, model.ndim_shape, model.ndim_exp))
+            check(lib().fr_recon_project_backward(params.data_ptr(), model.packed.data_ptr(), vertex_grad.data_ptr(), dparams.data_ptr(), B, N,
+                                                  model.ndim_shape, model.ndim_exp, ctx.im_size, ctx.flags, ws.data_ptr(), ws.numel(), sp))
+        return dparams, None, None, None, None, None, None
+
+
+def recon_render_depth(params, model: DeviceModel, texture, height=200, width=200, im_size=200, flags=None, raw=False):
+    """``vertices_transform`` + ``render_depth`` for a [B,d] parameter tensor in one call: returns (vertex_proj [B,3,N], depth,
+    texture_image, normal, tri_ind) exactly as ``recon_project`` followed by ``render_depth`` does, gradients included."""
+    flags = model.run_flags if flags is None else int(flags)
+    return _ReconRenderDepth.apply(params, model, texture, int(height), int(width), float(im_size),
+                                   flags | (_lib.FR_PARAMS_RAW if raw else 0))
+
+
 def recon_project(params, model: DeviceModel, im_size=200, flags=None, raw=False):
     """Functional form of ``vertices_transform`` for a [B,d] parameter tensor.  ``raw=True``: ``params`` are the regressor's raw
     outputs and ``set_constraints`` (``nets/network.py:204-218``) is applied inside the prep kernels; the

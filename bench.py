@@ -534,12 +534,27 @@ def run_ours(args):
                 vp4 = net.recon_project(p4, dm, IM_SIZE)
                 ops.render_depth(vp4, dm.tri, tex4, img4)
 
+        def fwd_bwd_one_call():                                          # the same outputs and gradient from recon_render_depth
+            p4.grad = None
+            _, d4, _, _, ti4 = net.recon_render_depth(p4, dm, dm.vertex_code, H, W, IM_SIZE)
+            (d4 * (gd4 * (ti4 >= 0))).sum().backward()
+
+        def fwd_only4_one_call():
+            with torch.no_grad():
+                net.recon_render_depth(p4, dm, dm.vertex_code, H, W, IM_SIZE)
+
         ms_fb = time_torch(fwd_bwd, 10, flush_l2=True)
         ms_f4 = time_torch(fwd_only4, 10, flush_l2=True)
+        ms_fb1 = time_torch(fwd_bwd_one_call, 10, flush_l2=True)
+        ms_f41 = time_torch(fwd_only4_one_call, 10, flush_l2=True)
         rb4, nb4 = algorithmic_bytes(B4, nver, ntri, K)
         b4 = rb4 + nb4 + backward_bytes(B4, nver, ntri, K)
         extras["config4_b256_fwd_bwd"] = dict(roof(b4, ms_fb), faces_per_s=B4 / (ms_fb * 1e-3), fwd_only_ms=ms_f4,
                                               with_extra_outputs=roof(b4 + B4 * 4 * (6 * H * W + 3 * nver), ms_fb),
+                                              one_call=dict(roof(b4, ms_fb1), faces_per_s=B4 / (ms_fb1 * 1e-3), fwd_only_ms=ms_f41,
+                                                            api="recon_render_depth (fr_recon_render_forward_all: vertices + all four "
+                                                                "outputs from the rasterizing reconstruction kernel, no repack / visibility "
+                                                                "kernels) + the same autograd backward; bit-identical outputs"),
                                               api="recon_project + render_depth (all four outputs) + autograd backward, torch API, "
                                                   "L2 flushed; bytes = SURVEY 8(d) bytes_fwd(256) + bytes_bwd(256)")
         del p4, img4, gd4

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FR_VERSION 201
+#define FR_VERSION 202
 
 /* status codes */
 #define FR_OK 0
@@ -171,6 +171,18 @@ int fr_recon_render_forward(const float* params, const float* packed, const floa
                             float* vertex_proj, float* depth, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
                             int ndim_exp, int height, int width, float im_size, unsigned flags, void* workspace,
                             size_t workspace_bytes, void* stream, void* const* stage_events);
+
+/* The same call with ALL FOUR outputs of render_depth (rendering_layer/ops.py:78-81) plus vertex_proj: what the training path
+ * (nets/network.py:300-308, depth_rendering_layer) needs from one batch of parameters.  Bit-identical to
+ * fr_recon_project_forward + fr_render_depth_forward; with FR_CLUSTER_TILES the rasterizing epilogue also leaves the 16-byte
+ * vertex records the resolve pass gathers normals from, so neither the repack pass nor the visibility kernel runs.
+ * texture: [3,nver] (texture_batch_stride 0) or per face, as in fr_render_depth_forward.  Gradients: fr_render_depth_backward
+ * followed by fr_recon_project_backward. */
+int fr_recon_render_forward_all(const float* params, const float* packed, const float* tri, const fr_mesh_table* mesh,
+                                const float* texture, long long texture_batch_stride, float* vertex_proj, float* depth,
+                                float* texture_image, float* normal, float* tri_ind, int batch, int nver, int ntri, int ndim_shape,
+                                int ndim_exp, int height, int width, float im_size, unsigned flags, void* workspace,
+                                size_t workspace_bytes, void* stream);
 
 /* ---- host-buffer session (what a non-GPU caller binds) ----------------------
  * A session owns the device copy of the model, device staging for `max_batch` faces and one stream.

@@ -192,6 +192,44 @@ def test_fused_call_matches_separate_calls(bfm, mid_model, B, tiles, which):
             assert bool(torch.isnan(vertex).all())                         # untouched
 
 
+@pytest.mark.parametrize("B,tiles,which", [(5, True, "bfm"), (20, True, "bfm"), (70, True, "bfm"), (20, False, "bfm"), (41, True, "mid")])
+def test_recon_render_depth_all_outputs(bfm, mid_model, B, tiles, which):
+    """recon_render_depth (fr_recon_render_forward_all: the training path's vertices + all four render_depth outputs from one
+    call -- FFMA path, records pipeline, rasterizing epilogue that also leaves the vertex records) against recon_project +
+    render_depth: five outputs bit for bit, parameter gradients of a loss on depth and vertices equal to 1e-5."""
+    net, ops = fr("nets.network"), fr("rendering_layer.ops")
+    m = bfm if which == "bfm" else mid_model
+    S = 200
+    p = fr("synth").sample_params_constrained(B, m["ndim_shape"], m["ndim_exp"], S, seed=80 + B)
+    dm = fr("model").DeviceModel(m, DEV, cluster_tiles=tiles)
+    rng = np.random.default_rng(B)
+    gd = torch.from_numpy(rng.normal(size=(B, S, S, 1)).astype(np.float32)).to(DEV)
+    gv = torch.from_numpy((1e-3 * rng.normal(size=(B, 3, dm.nver))).astype(np.float32)).to(DEV)
+    tex = dm.vertex_code                                                   # [3,N], shared by all faces
+    # separate ops
+    p1 = torch.from_numpy(p).to(DEV).requires_grad_(True)
+    v1 = net.recon_project(p1, dm, S)
+    image = torch.empty((B, S, S, 3), device=DEV)
+    d1, t1, n1, i1 = ops.render_depth(v1, dm.tri, tex.unsqueeze(0).expand(B, -1, -1), image)
+    ((d1 * gd).sum() + (v1 * gv).sum()).backward()
+    # one call
+    p2 = torch.from_numpy(p).to(DEV).requires_grad_(True)
+    v2, d2, t2, n2, i2 = net.recon_render_depth(p2, dm, tex, S, S, S)
+    ((d2 * gd).sum() + (v2 * gv).sum()).backward()
+    torch.cuda.synchronize()
+    for a, b, name in ((v1, v2, "vertex_proj"), (d1, d2, "depth"), (t1, t2, "texture_image"), (n1, n2, "normal"), (i1, i2, "tri_ind")):
+        assert a.detach().cpu().numpy().tobytes() == b.detach().cpu().numpy().tobytes(), name
+    g1, g2 = p1.grad.cpu().numpy().astype(np.float64), p2.grad.cpu().numpy().astype(np.float64)
+    assert int((i2 >= 0).sum()) > 1000 and np.abs(g1).max() > 0
+    scale = np.abs(g1).max(axis=1, keepdims=True)
+    assert (np.abs(g1 - g2) <= 1e-5 * scale).all()
+    # per-face texture through the same call
+    texb = (tex.unsqueeze(0) * torch.linspace(0.5, 1.0, B, device=DEV).view(B, 1, 1)).contiguous()
+    _, _, t3, _, _ = net.recon_render_depth(torch.from_numpy(p).to(DEV), dm, texb, S, S, S)
+    _, t4, _, _ = ops.render_depth(v1.detach(), dm.tri, texb, image)
+    assert t3.cpu().numpy().tobytes() == t4.cpu().numpy().tobytes()
+
+
 @pytest.mark.parametrize("tiles", [False, True])
 @pytest.mark.parametrize("B,H,W", [(70, 33, 31), (9, 48, 64), (130, 20, 20), (1500, 16, 16)])
 def test_fused_call_small_model_odd_shapes(small_model, B, H, W, tiles):

@@ -41,7 +41,7 @@ def _assert_same(got, want, tag=""):
 
 def test_library_is_the_cuda_build():
     lib = fr("_lib").lib()
-    assert lib.fr_version() == 201
+    assert lib.fr_version() == 202
     before = lib.fr_launch_count()
     _gpu_render(np.zeros((1, 3, 3), np.float32), np.array([[0], [1], [2]], np.float32), np.zeros((1, 3, 3), np.float32), 8, 8)
     assert lib.fr_launch_count() >= before + 2

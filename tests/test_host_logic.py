@@ -24,10 +24,10 @@ def test_abi_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), n
     lib = lib_mod.lib()
-    assert lib.fr_version() == 201
+    assert lib.fr_version() == 202
     # size queries are pure host arithmetic: safe without a GPU
     assert lib.fr_packed_basis_bytes(53215, 199, 29, 0, None) == 416 * 3 * 58 * 128 * 16 + 416 * 3 * 15 * 8192 + 1024 + 416 * 3 * 8 * 16384 + 3 * 416 * 128 * 4   # fp32 + fp16-pair tiles + column scales + backward tiles + fp32 mean
-    assert lib.fr_render_workspace_bytes(64, 53215, 200, 200) == 64 * 200 * 200 * 8 + 64 * 53215 * 16 + (53215 * 16 + 255) // 256 * 256   # keys + 16-byte vertex records + a shared texture repacked by rank
+    assert lib.fr_render_workspace_bytes(64, 53215, 200, 200) == 64 * 200 * 200 * 8 + 64 * 53215 * 16 + (53215 * 16 + 255) // 256 * 256 + 256   # keys + 16-byte vertex records + a shared texture repacked by rank + schedule counters
     assert lib.fr_recon_workspace_bytes(64, 53215, 199, 29) >= 232 * 64 * 4
     assert lib.fr_packed_basis_bytes(0, 199, 29, 0, None) == 0
 
