@@ -433,7 +433,10 @@ struct RasterTarget {
 
 // tiles: fp16 operand tiles; cluster_vert: the vertex (id | owner flag, -1 = none) behind every row of every tile -- the mesh
 // table's cluster lists (FR_CLUSTER_TILES) or its rank order (one tile = 128 consecutive ranks); null = consecutive vertex ids.
-template <bool kRaster>
+// kRecords (raster flavour only): the epilogue also writes the 16-byte vertex records (out.rec, by rank) for a resolve pass with
+// normals / texture (fr_recon_render_forward_all).  A separate instantiation: the depth-only kernel runs at its register limit
+// and the extra live values (record index, the branch) cost 4 us per 64 faces when they are merely optional at run time.
+template <bool kRaster, bool kRecords = false>
 __global__ void __launch_bounds__(Cfg<kRaster>::kThreads, 1)
 recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned char* __restrict__ bsplit,
                      const float* __restrict__ pose16, const int32_t* __restrict__ cluster_vert, ReconOut out,
@@ -660,13 +663,14 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
         }
         tc_fence_after();
         // vertex of this row and whether this cluster owns it (optional vertex_proj output only)
-        int n = 0, rank = 0;
+        int n = 0;
+        [[maybe_unused]] int rank = 0;
         bool owner = false;
-        if (out.planar != nullptr || out.rec != nullptr) {
+        if (kRecords || out.planar != nullptr) {
           const int32_t raw = __ldg(cluster_vert + (size_t)tile * kTileVerts + v);
           n = (int)((uint32_t)raw & kVertIdMask);
           owner = raw >= 0 && ((uint32_t)raw & kVertOwner) != 0u;
-          if (out.rec != nullptr) rank = __ldg(tv.cluster_rank + (size_t)tile * kTileVerts + v);   // record index of this slot
+          if constexpr (kRecords) rank = __ldg(tv.cluster_rank + (size_t)tile * kTileVerts + v);   // record index of this slot
         }
         // the cluster's triangle list: this thread's entry travels in registers until the group's tile is free
         const int tb = __ldg(tv.tri_begin + tile);
@@ -703,10 +707,13 @@ recon_fwd_f16_kernel(const unsigned char* __restrict__ tiles, const unsigned cha
               const float P[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
               project_vertex(P, x[j], y[j], z[j], im_size, flags, &r[j].x, &r[j].y, &r[j].z);
               r[j].w = __uint_as_float(fr_snap_code(r[j].x, r[j].y, target.width, target.height));
-              if (owner && fh * kFPW + j < nlive) {
-                if (out.planar != nullptr) store_planar(out.planar, fb + fh * kFPW + j, nver, n, r[j].x, r[j].y, r[j].z);
-                // (optional: the 16-byte records the resolve pass gathers normals from -- the training path's all-outputs call)
-                if (out.rec != nullptr) out.rec[(size_t)(fb + fh * kFPW + j) * nver + rank] = r[j];
+              if constexpr (kRecords) {                               // vertices + the records the resolve pass gathers normals from
+                if (owner && fh * kFPW + j < nlive) {
+                  if (out.planar != nullptr) store_planar(out.planar, fb + fh * kFPW + j, nver, n, r[j].x, r[j].y, r[j].z);
+                  out.rec[(size_t)(fb + fh * kFPW + j) * nver + rank] = r[j];
+                }
+              } else {
+                if (owner && fh * kFPW + j < nlive) store_planar(out.planar, fb + fh * kFPW + j, nver, n, r[j].x, r[j].y, r[j].z);
               }
             }
           }
@@ -794,7 +801,10 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
   const int ntiles_f = target != nullptr ? g.nclusters : g.ntiles;             // row tiles of the section this flavour streams
   const f16::RasterTarget none = {nullptr, nullptr, 0, 0};
   const f16::SmemLayout L = target != nullptr ? f16::smem_layout<true>(g.nch16) : f16::smem_layout<false>(g.nch16);
-  if (target != nullptr)
+  const bool records = target != nullptr && out.rec != nullptr;
+  if (records)
+    FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  else if (target != nullptr)
     FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   else
     FR_CUDA(cudaFuncSetAttribute(f16::recon_fwd_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -810,7 +820,11 @@ inline int launch_recon_fwd_f16(const float* params, const float* packed, void* 
       nb = nsm / ctas;
     }
     if (ctas > ntiles_f) ctas = ntiles_f;
-    if (target != nullptr) {
+    if (records) {
+      FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<true, true>, dim3(ctas, nb), dim3(f16::Cfg<true>::kThreads), L.total, st, pdl_enabled(),
+                         base + g.f16c_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
+                         out, *target, batch, nver, g.nch16, g.nclusters, im_size, flags, bt0));
+    } else if (target != nullptr) {
       FR_CUDA(launch_pdl(f16::recon_fwd_f16_kernel<true>, dim3(ctas, nb), dim3(f16::Cfg<true>::kThreads), L.total, st, pdl_enabled(),
                          base + g.f16c_offset(), static_cast<const unsigned char*>(bsplit), static_cast<const float*>(pose16), cluster_vert,
                          out, *target, batch, nver, g.nch16, g.nclusters, im_size, flags, bt0));

@@ -172,6 +172,7 @@ class _ReconRenderDepth(torch.autograd.Function):
         ctx.save_for_backward(params, tri_ind)
         ctx.model, ctx.flags, ctx.im_size, ctx.hw = model, flags, float(im_size), (height, width)
         ctx.mark_non_differentiable(teximg, normal, tri_ind)
+        ctx.set_materialize_grads(False)                 # an unused vertex_proj output must not cost a [B,3,N] tensor of zeros
         return vertex, depth, teximg, normal, tri_ind
 
     @staticmethod
@@ -182,6 +183,8 @@ class _ReconRenderDepth(torch.autograd.Function):
         vertex_grad = torch.empty((B, 3, N), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             sp = torch.cuda.current_stream(dev).cuda_stream
+            if g_depth is None and g_vertex is None:
+                return None, None, None, None, None, None, None
             if g_depth is None:
                 vertex_grad.zero_()
             else:
