@@ -398,7 +398,12 @@ struct ItemWalk {
     if (counter == nullptr) return false;
     if (d == 0) pdl_wait();                                      // the counter was zeroed by the prep kernel
     const uint32_t need = nstatic + d + 1u > (uint32_t)FR_POOL_LOOKAHEAD ? nstatic + d + 1u - (uint32_t)FR_POOL_LOOKAHEAD : 0u;
-    while (*reinterpret_cast<volatile uint32_t*>(&bars->raster_pos) < need) __nanosleep(64);
+    // (bounded like mbar_wait: a protocol bug traps -- a launch error the API reports -- instead of hanging the GPU)
+    uint32_t spin = 0;
+    while (*reinterpret_cast<volatile uint32_t*>(&bars->raster_pos) < need) {
+      __nanosleep(64);
+      if (++spin > (1u << 25)) __trap();
+    }
     const unsigned idx = atomicAdd(counter, 1u);
     const int item = idx < (unsigned)pool_items(tw) ? (int)idx : -1;
     bars->item_ring[d & 7u] = item;
