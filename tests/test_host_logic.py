@@ -47,6 +47,21 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     with pytest.raises(ValueError):
         lib_mod.check(rc)
     assert lib.fr_render_depth_forward(None, None, None, 0, None, None, None, None, 0, 10, 5, 8, 8, None, None, 0, None) == 0   # empty batch
+    # the all-outputs call: needs every output pointer, validates the model / image dimensions first
+    args_all = [None] * 5 + [0] + [None] * 5
+    rc = lib.fr_recon_render_forward_all(*args_all, 4, 10, 5, 3, 2, 8, 8, 8.0, 0, None, 0, None)
+    assert rc == lib_mod.FR_ERR_INVALID_ARGUMENT and "null pointer" in lib_mod.last_error()
+
+
+def test_one_call_op_has_no_cpu_path():
+    """recon_render_depth refuses CPU tensors before it touches the library (no silent fallback)."""
+    import torch
+    net = fr("nets.network")
+
+    class FakeModel:
+        run_flags, ndim, ndim_shape, ndim_exp, nver = 0, 235, 199, 29, 10
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net.recon_render_depth(torch.zeros(2, 235), FakeModel(), torch.zeros(3, 10), 8, 8, 8)
 
 
 def test_product_has_no_oracle_or_cpu_path():
